@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- Bellman cell-updates/s of the MDP value-iteration hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun ... bench.py --gpus N ...        (N > 1: one rank per GPU, NCCL)
+
+Workload (BASELINE.json configs[2]): synthetic 4096 x
+4096 grid per GPU, i.i.d. 20 % occupied (numpy PCG64 seed 12345), goal at the
+centre forced free, 9 actions, gamma = 0.95f.  N > 1 stacks N such tiles
+vertically (rows = 4096*N, weak scaling) and row-shards them, ghost rows over
+NCCL every 2 sweeps, MAX all-reduce of the residual every 100.
+A "step" is one convergence-check period of the reference
+(src/mdp/path_planning_2d.cu:226-251): 100 Jacobi sweeps of the whole grid +
+the inf-norm residual.  value = cells * 100 * K / t (device time, max over
+ranks).  e2e = the same work through the public API with HOST buffers: map
+upload, 100 sweeps, residual, download of J and the action grid.
+
+--impl reference: the reference has no CPU solver; the
+arm times the oracle port of its kernel arithmetic (oracle/mdp_oracle.c,
+OpenMP over all host cores) on a bounded sample of the same grid.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+TILE = 4096
+SWEEPS_PER_STEP = 100
+ALGO_BYTES_PER_CELL_UPDATE = 10
+METRIC = "bellman_cell_updates_per_sec"
+UNIT = "cell-updates/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,"
+         "clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_grid(n_tiles):
+    import cases
+    h, w = TILE * n_tiles, TILE
+    grid, goal = cases.synthetic_map(h, w, 0.20, seed=12345,
+                                     goal=(w // 2, TILE // 2))
+    return grid, goal
+
+
+# --------------------------------------------------------------------------
+def cpu_port_throughput(grid, goal, gamma, budget_s=12.0, sample=2048):
+    """Oracle port (OpenMP, all cores) on the top-left sample x sample crop."""
+    import oracle_py
+    crop = np.ascontiguousarray(grid[:sample, :sample])
+    g = goal if (goal[0] < sample and goal[1] < sample) else None
+    if g is None or crop[g[1], g[0]]:
+        free = np.argwhere(crop == 0)[0]
+        g = (int(free[1]), int(free[0]))
+    ora = oracle_py.OracleMdp(crop, g, gamma)
+    ora.sweeps(2)                                   # warm-up + calibration
+    t0 = time.perf_counter()
+    ora.sweeps(2)
+    per = (time.perf_counter() - t0) / 2
+    n = max(2, min(200, int(budget_s / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    ora.sweeps(n)
+    dt = time.perf_counter() - t0
+    cores = len(os.sched_getaffinity(0))
+    return {"value": crop.size * n / dt, "unit": UNIT, "cores": cores,
+            "kind": "port",
+            "sample": f"{n} sweeps of the {sample}x{sample} top-left crop of the "
+                      f"workload grid, oracle/mdp_oracle.c with OpenMP on {cores} threads"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import cases
+    grid, goal = make_grid(1)
+    import oracle_py
+    sample = 2048
+    crop = np.ascontiguousarray(grid[:sample, :sample])
+    free = np.argwhere(crop == 0)[0]
+    g = (int(free[1]), int(free[0]))
+    ora = oracle_py.OracleMdp(crop, g, cases.GAMMA)
+    ora.sweeps(1)
+    t0 = time.perf_counter()
+    ora.sweeps(1)
+    per = time.perf_counter() - t0
+    # bounded: the whole run (warm-up + steps) stays within ~2 minutes
+    total_steps = max(1, args.steps + args.warmup)
+    sweeps_per_step = max(1, min(SWEEPS_PER_STEP, int(100.0 / total_steps / max(per, 1e-6))))
+    for _ in range(args.warmup):
+        ora.sweeps(sweeps_per_step)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ora.sweeps(sweeps_per_step)
+    dt = time.perf_counter() - t0
+    cores = len(os.sched_getaffinity(0))
+    value = crop.size * sweeps_per_step * args.steps / dt
+    sample_txt = (f"each step = {sweeps_per_step} sweeps of the {sample}x{sample} "
+                  f"top-left crop of the 4096x4096 workload grid")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "syn4k: 4096x4096 i.i.d. 20% occupied, seed 12345, "
+                               "9 actions, gamma 0.95f; " + sample_txt,
+                   "note": "the reference has no CPU value-iteration path; this is "
+                           "the oracle port of its CUDA kernel arithmetic"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
+                         "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+def reference_cuda_on_this_gpu(grid, goal, gamma):
+    """The reference's own kernels (oracle/_ref) on the same B200, if built."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libpp2d_ref_mdp.so")
+    if not os.path.exists(so):
+        return None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import ctypes
+        import make_golden
+        lib = make_golden.ref_lib()
+        ms = ctypes.c_float()
+        h, w = grid.shape
+        lib.ref_mdp_time_sweeps(h, w, grid.ctypes.data, goal[0], goal[1], gamma,
+                                20, 4, ctypes.byref(ms))
+        return {"value": h * w * 20 / (ms.value * 1e-3), "unit": UNIT,
+                "what": "unmodified reference kernels (oracle/_ref, sm_100a, "
+                        "--use_fast_math), 20 sweeps, same grid, same GPU"}
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)}
+
+
+def run_main_arm(args):
+    import torch
+    import torch.distributed as dist
+    import cases
+    from path_planning_2d_b200 import MdpPathPlanning2d, _lib
+    from path_planning_2d_b200.distributed import ShardedValueIteration
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    gamma = cases.GAMMA
+    grid, goal = make_grid(world)
+    H, W = grid.shape
+    cells = H * W
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    vi = ShardedValueIteration(grid, goal, gamma, rank=rank, world_size=world)
+    rows = vi.rows[1] - vi.rows[0]
+
+    def step(ev=None):
+        # 98 value-only sweeps = 49 launches of the fused 2-sweep kernel
+        if ev is not None:
+            ev[0].record()
+        vi.sweeps(SWEEPS_PER_STEP - 2, want_action=False)
+        if ev is not None:
+            ev[1].record()
+        vi.sweeps(2, want_action=True)
+        r = vi.shard.residual_tensor()
+        if world > 1:
+            dist.all_reduce(r, op=dist.ReduceOp.MAX)
+        return r
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.pp2d_kernel_launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for i in range(args.steps):
+        r = step(evs[i])
+    end.record()
+    barrier()
+    launches = lib.pp2d_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = start.elapsed_time(end)
+    fused_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms, fused_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, fused_ms = t.tolist()
+    value = cells * SWEEPS_PER_STEP * args.steps / (ms * 1e-3)
+    residual = float(r.item())
+
+    # roofline of the dominant kernel (fused 2-sweep kernel), per launch
+    n_fused = (SWEEPS_PER_STEP - 2) // 2 * args.steps
+    launch_s = fused_ms * 1e-3 / n_fused
+    algo_bytes = rows * W * 2 * ALGO_BYTES_PER_CELL_UPDATE
+    peak, which = peaks()
+    achieved = algo_bytes / launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "mdp_sweep_kernel<T=2> (2 fused sweeps per launch)",
+                "launch_ms": launch_s * 1e3, "peak_source": which,
+                "algorithmic_bytes_per_launch": algo_bytes}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # e2e: public API, host buffers, copies inside the timed region
+    vi.close()
+    del vi
+    from path_planning_2d_b200.distributed import partition_rows
+    bounds = partition_rows(H, world)[rank]
+    pinned_map = torch.from_numpy(grid).pin_memory()
+    map_np = pinned_map.numpy()
+    cost_host = torch.empty((bounds[1] - bounds[0]) * W, dtype=torch.float32).pin_memory()
+    act_host = torch.empty((bounds[1] - bounds[0]) * W, dtype=torch.uint8).pin_memory()
+    def e2e_step():
+        v = ShardedValueIteration(map_np, goal, gamma, rank=rank, world_size=world)
+        v.sweeps(SWEEPS_PER_STEP)
+        res = v.residual()
+        torch.cuda.current_stream().synchronize()
+        _lib.check(lib.pp2d_mdp_download(v.shard.mdp._h, cost_host.data_ptr(),
+                                         act_host.data_ptr()))
+        v.close()
+        return res
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = cells * SWEEPS_PER_STEP * e2e_steps / float(e2e_s.item())
+    occ_rows = min(H, bounds[1] + 3) - max(0, bounds[0] - 3)
+    e2e = {"value": e2e_val, "unit": UNIT,
+           "h2d_bytes_per_step": occ_rows * W,
+           "d2h_bytes_per_step": (bounds[1] - bounds[0]) * W * 5 + 4,
+           "steps": e2e_steps,
+           "what": "create(map from pinned host) + 100 sweeps + residual + "
+                   "download(J f32, action u8 to pinned host) + destroy, per step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"syn4k x{world}: {H}x{W} grid ({TILE}x{TILE} per GPU), "
+                            "i.i.d. 20% occupied (PCG64 seed 12345), goal "
+                            f"{goal}, 9 actions, gamma 0.95f, J0 = 0",
+                "step": "100 Jacobi sweeps + inf-norm residual (one reference "
+                        "check period)",
+                "parallelism": f"rows{world}" if world > 1 else "single",
+                "l2": "working set (2 x J + codes, ~164 MiB per GPU) exceeds the "
+                      "126 MB L2; no explicit flush",
+                "hbm_gbs_algorithmic": value * ALGO_BYTES_PER_CELL_UPDATE / 1e9 / world,
+            },
+            "roofline": roofline,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "residual_after_timed_steps": residual,
+        }
+        ref_cuda = reference_cuda_on_this_gpu(grid[:TILE], goal, gamma) \
+            if world == 1 and not args.no_ref_cuda else None
+        if ref_cuda:
+            line["reference_cuda_same_gpu"] = ref_cuda
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_port_throughput(grid, goal, gamma)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline")
+    ap.add_argument("--no-ref-cuda", action="store_true",
+                    help="skip the reference-kernels-on-this-GPU line")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_main_arm(args)
+
+
+if __name__ == "__main__":
+    main()

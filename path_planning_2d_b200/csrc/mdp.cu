@@ -1,0 +1,524 @@
+// mdp.cu -- host side of the MDP value-iteration C ABI (include/pp2d.h).
+//
+// Replaces, for the reference's MdpPathPlanning2d
+// (/root/reference/path_planning_2d/src/mdp/path_planning_2d.cu):
+//   allocateDeviceMemory / freeDeviceMemory / the six global device pointers
+//   (path_planning_2d_cuda.cu:26-74), the map upload and model generation
+//   (path_planning_2d.cu:90-106), valueIteration() (207-269) and the result
+//   download (118-126).
+// There is no CPU fallback in this file: without a CUDA device every entry
+// point fails with PP2D_ERR_CUDA.
+#include "../../include/pp2d.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "mdp_kernels.cuh"
+
+namespace pp2d {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PP2D_CUDA(expr)                                                      \
+  do {                                                                       \
+    cudaError_t e_ = (expr);                                                 \
+    if (e_ != cudaSuccess)                                                   \
+      return fail(PP2D_ERR_CUDA, "CUDA error at %s:%d code=%d(%s) \"%s\"",   \
+                  __FILE__, __LINE__, (int)e_, cudaGetErrorName(e_), #expr); \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// Model numbers of one cell, restated from the reference for the table build:
+// cudaTransitionProbability (path_planning_2d_cuda.cu:76-150) and
+// cudaStageCost (152-172) for a FREE centre cell whose neighbour occupancy is
+// `occ` (9 entries, slot 4 ignored).  Outputs per action u: the stage cost
+// g[u] and the probability of staying P_u[4] after the blocked mass has been
+// shifted to the centre.  The order of the float additions is the
+// reference's (ascending slot index).
+static void cell_model(const uint8_t occ[9], float g[9], float p4[9]) {
+  static const float naive[9][9] = {
+      {0.7f, 0.1f, 0.f, 0.1f, 0.1f, 0.f, 0.f, 0.f, 0.f},
+      {0.1f, 0.7f, 0.1f, 0.f, 0.1f, 0.f, 0.f, 0.f, 0.f},
+      {0.f, 0.1f, 0.7f, 0.f, 0.1f, 0.1f, 0.f, 0.f, 0.f},
+      {0.1f, 0.f, 0.f, 0.7f, 0.1f, 0.f, 0.1f, 0.f, 0.f},
+      {0.f, 0.f, 0.f, 0.f, 1.0f, 0.f, 0.f, 0.f, 0.f},
+      {0.f, 0.f, 0.1f, 0.f, 0.1f, 0.7f, 0.f, 0.f, 0.1f},
+      {0.f, 0.f, 0.f, 0.1f, 0.1f, 0.f, 0.7f, 0.1f, 0.f},
+      {0.f, 0.f, 0.f, 0.f, 0.1f, 0.f, 0.1f, 0.7f, 0.1f},
+      {0.f, 0.f, 0.f, 0.f, 0.1f, 0.1f, 0.f, 0.1f, 0.7f}};
+  for (int u = 0; u < 9; ++u) {
+    float stay = naive[u][4];
+    float cost = 0.0f;
+    for (int i = 0; i < 9; ++i) {
+      const bool blocked = (i != 4) && occ[i];
+      if (blocked) stay += naive[u][i];                 // cuda.cu:142-147
+      // map_cost is 1 or 2: the product is exact, fmaf == the device FFMA.
+      cost = fmaf(blocked ? 2.0f : 1.0f, naive[u][i], cost);  // cuda.cu:166-169
+    }
+    g[u] = cost;
+    p4[u] = stay;
+  }
+}
+
+// Ring position -> neighbour slot (see mdp_kernels.cuh).
+static const int kRingSlot[10] = {0, 1, 2, 5, 8, 7, 6, 3, 0, 1};
+// Action pair p reads ring bits 2p..2p+3; {first, second} action of the pair.
+static const int kPairAction[4][2] = {{1, 2}, {5, 8}, {7, 6}, {3, 0}};
+
+static void build_lut(float gamma, std::vector<float4>& lut) {
+  lut.assign(kLutFloat4, make_float4(0, 0, 0, 0));
+  for (int p = 0; p < 4; ++p) {
+    for (int f = 0; f < 16; ++f) {
+      uint8_t occ[9] = {0};
+      for (int b = 0; b < 4; ++b)
+        if (f >> b & 1) occ[kRingSlot[2 * p + b]] = 1;
+      float g[9], p4[9];
+      cell_model(occ, g, p4);
+      const int u0 = kPairAction[p][0], u1 = kPairAction[p][1];
+      // gamma*tp[i] is rounded to float before the FFMA (SASS of the
+      // reference kernel: FMUL then FFMA).
+      float4 row = make_float4(g[u0], gamma * p4[u0], g[u1], gamma * p4[u1]);
+      for (int c = 0; c < 8; ++c) lut[(p * 16 + f) * 8 + c] = row;
+    }
+  }
+}
+
+}  // namespace pp2d
+
+using namespace pp2d;
+
+struct pp2d_mdp {
+  uint32_t Htot = 0, W = 0;        // whole grid
+  uint32_t row_begin = 0, H = 0;   // owned rows
+  uint32_t gx = 0, gy = 0;
+  float gamma = 0.f;
+  bool sharded = false;
+  int pitch = 0;
+  size_t plane = 0;                // elements of one padded plane
+  float* j[2] = {nullptr, nullptr};
+  float* jchk = nullptr;
+  uint16_t* code = nullptr;
+  uint8_t* action = nullptr;       // dense [H][W]
+  uint8_t* occ = nullptr;          // dense rows [occ_row0, occ_row0+occ_rows)
+  float* dense = nullptr;          // export staging [H][W]
+  float4* lut = nullptr;
+  uint32_t* resid = nullptr;       // device float bits
+  uint32_t* resid_host = nullptr;  // pinned
+  int cur = 0;                     // j[cur] holds J_n
+  uint32_t n_sweeps = 0;
+  uint32_t n_chk = 0;              // sweep count at the last residual call
+  uint32_t action_sweep = 0;       // sweep count the action grid belongs to
+  bool has_occupied = false;
+  std::vector<float> trapped;      // trapped[n] = J_n of an occupied cell
+  std::vector<uint8_t> action_host;
+  bool action_host_valid = false;
+  cudaStream_t stream = nullptr;
+  bool async = false;
+  int sm_count = 148;
+  // tuning knobs (environment overridable, see mdp_config)
+  int cw2 = 2, cw1 = 4, rows_per_unit = 0;
+};
+
+namespace pp2d {
+
+static float trapped_cost(pp2d_mdp* h, uint32_t n) {
+  // Occupied cell: every action has P = e_4 and g = 2
+  // (path_planning_2d_cuda.cu:131-134), so J_n = fma(gamma*1.0f, J_{n-1}, 2).
+  while (h->trapped.size() <= n)
+    h->trapped.push_back(fmaf(h->gamma, h->trapped.back(), 2.0f));
+  return h->trapped[n];
+}
+
+template <int T, int CW, bool POLICY>
+static int launch_sweep(pp2d_mdp* h) {
+  using G = StripGeom<T, CW>;
+  SweepParams p;
+  p.jin = h->j[h->cur];
+  p.jout = h->j[h->cur ^ 1];
+  p.code = h->code;
+  p.action = h->action;
+  p.lut = h->lut;
+  p.W = (int)h->W;
+  p.H = (int)h->H;
+  p.pitch = h->pitch;
+  p.n_strips = ((int)h->W + G::S - 1) / G::S;
+  int rpu = h->rows_per_unit;
+  if (rpu <= 0) {
+    // Enough units for ~4 CTAs of 8 warps per SM, at least 16 rows each so
+    // the 2*T halo rows stay a small fraction.
+    long target_units = (long)h->sm_count * 8 * 4;
+    long rb = (target_units + p.n_strips - 1) / p.n_strips;
+    rpu = (int)((h->H + rb - 1) / rb);
+    if (rpu < 16) rpu = 16;
+    if (rpu > 128) rpu = 128;
+  }
+  p.rows_per_unit = rpu;
+  const int n_rb = ((int)h->H + rpu - 1) / rpu;
+  p.n_units = p.n_strips * n_rb;
+  p.gamma = h->gamma * 1.0f;
+  p.ga = h->gamma * 0.7f;
+  p.gb = h->gamma * 0.1f;
+  const int warps_per_cta = 8;
+  const int grid = (p.n_units + warps_per_cta - 1) / warps_per_cta;
+  mdp_sweep_kernel<T, CW, POLICY><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  PP2D_CUDA(cudaGetLastError());
+  h->cur ^= 1;
+  h->n_sweeps += T;
+  return PP2D_OK;
+}
+
+template <int T, bool POLICY>
+static int launch_sweep_cw(pp2d_mdp* h, int cw) {
+  switch (cw) {
+    case 1: return launch_sweep<T, 1, POLICY>(h);
+    case 2: return launch_sweep<T, 2, POLICY>(h);
+    default: return launch_sweep<T, 4, POLICY>(h);
+  }
+}
+
+static int sync_if_needed(pp2d_mdp* h) {
+  if (!h->async) PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  return PP2D_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
+                       uint32_t gx, uint32_t gy, float gamma,
+                       uint32_t row_begin, uint32_t row_end, bool sharded,
+                       pp2d_mdp** out) {
+  if (!out) return fail(PP2D_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!map || height == 0 || width == 0)
+    return fail(PP2D_ERR_INVALID, "empty map");
+  if (gx >= width || gy >= height)
+    return fail(PP2D_ERR_INVALID, "goal (%u %u) outside the %ux%u map", gx, gy,
+                width, height);
+  if (row_begin >= row_end || row_end > height)
+    return fail(PP2D_ERR_INVALID, "bad row range [%u, %u)", row_begin, row_end);
+  if (sharded && row_end - row_begin < (uint32_t)kPadRows)
+    return fail(PP2D_ERR_INVALID, "a shard needs at least %d rows", kPadRows);
+  if ((uint64_t)height * width >= (1ull << 40))
+    return fail(PP2D_ERR_INVALID, "map too large");
+  if (map[(size_t)gy * width + gx] > 0)   // path_planning_2d.cu:84-88
+    return fail(PP2D_ERR_GOAL_OCCUPIED,
+                "The assigned goal (%u %u) is at a occupied cell...", gx, gy);
+  int dev_count = 0;
+  PP2D_CUDA(cudaGetDeviceCount(&dev_count));
+  if (dev_count == 0) return fail(PP2D_ERR_CUDA, "no CUDA device");
+  int dev = 0;
+  PP2D_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  PP2D_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(PP2D_ERR_CUDA, "device %s is sm_%d%d; this library is sm_100a only",
+                prop.name, prop.major, prop.minor);
+
+  pp2d_mdp* h = new (std::nothrow) pp2d_mdp;
+  if (!h) return fail(PP2D_ERR_INVALID, "out of host memory");
+  h->Htot = height; h->W = width; h->row_begin = row_begin;
+  h->H = row_end - row_begin; h->gx = gx; h->gy = gy; h->gamma = gamma;
+  h->sharded = sharded;
+  h->sm_count = prop.multiProcessorCount;
+  h->pitch = (int)((kPadLeft + width + 128 + 31) / 32 * 32);
+  h->plane = (size_t)(h->H + 2 * kPadRows) * h->pitch;
+  h->trapped.push_back(0.0f);
+  h->cw2 = env_int("PP2D_MDP_CW2", 2);
+  h->cw1 = env_int("PP2D_MDP_CW1", 4);
+  h->rows_per_unit = env_int("PP2D_MDP_ROWS_PER_UNIT", 0);
+
+  // Occupancy rows needed for the codes of rows row_begin-2 .. row_end+1.
+  const int occ_row0 = (int)row_begin - 3 < 0 ? 0 : (int)row_begin - 3;
+  const int occ_row1 = row_end + 3 > height ? (int)height : (int)row_end + 3;
+  const int occ_rows = occ_row1 - occ_row0;
+  const size_t owned = (size_t)h->H * width;
+  for (size_t i = 0; i < owned && !h->has_occupied; ++i)
+    if (map[(size_t)row_begin * width + i] == 1) h->has_occupied = true;
+
+  int rc = [&]() -> int {
+    PP2D_CUDA(cudaMalloc(&h->j[0], h->plane * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&h->j[1], h->plane * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&h->jchk, h->plane * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&h->code, h->plane * sizeof(uint16_t)));
+    PP2D_CUDA(cudaMalloc(&h->action, owned));
+    PP2D_CUDA(cudaMalloc(&h->occ, (size_t)occ_rows * width));
+    PP2D_CUDA(cudaMalloc(&h->lut, kLutFloat4 * sizeof(float4)));
+    PP2D_CUDA(cudaMalloc(&h->resid, sizeof(uint32_t)));
+    PP2D_CUDA(cudaMallocHost(&h->resid_host, sizeof(uint32_t)));
+    // J1 = J2 = 0, action = 0 (path_planning_2d_cuda.cu:55-61).
+    PP2D_CUDA(cudaMemset(h->j[0], 0, h->plane * sizeof(float)));
+    PP2D_CUDA(cudaMemset(h->j[1], 0, h->plane * sizeof(float)));
+    PP2D_CUDA(cudaMemset(h->jchk, 0, h->plane * sizeof(float)));
+    PP2D_CUDA(cudaMemset(h->action, 0, owned));
+    // Map upload (path_planning_2d.cu:94-95).
+    PP2D_CUDA(cudaMemcpy(h->occ, map + (size_t)occ_row0 * width,
+                         (size_t)occ_rows * width, cudaMemcpyHostToDevice));
+    std::vector<float4> lut;
+    build_lut(gamma, lut);
+    PP2D_CUDA(cudaMemcpy(h->lut, lut.data(), kLutFloat4 * sizeof(float4),
+                         cudaMemcpyHostToDevice));
+    CodeParams cp;
+    cp.occ = h->occ; cp.code = h->code; cp.W = (int)width; cp.Htot = (int)height;
+    cp.pitch = h->pitch; cp.rows_phys = (int)h->H + 2 * kPadRows;
+    cp.row_begin = (int)row_begin; cp.occ_row0 = occ_row0; cp.occ_rows = occ_rows;
+    cp.gx = (int)gx; cp.gy = (int)gy;
+    dim3 grid((h->pitch + 255) / 256, cp.rows_phys);
+    mdp_code_kernel<<<grid, 256>>>(cp);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PP2D_CUDA(cudaGetLastError());
+    PP2D_CUDA(cudaDeviceSynchronize());
+    return PP2D_OK;
+  }();
+  if (rc != PP2D_OK) { pp2d_mdp_destroy(h); return rc; }
+  *out = h;
+  return PP2D_OK;
+}
+
+}  // namespace pp2d
+
+extern "C" {
+
+const char* pp2d_last_error(void) { return g_err; }
+int pp2d_abi_version(void) { return 1; }
+uint64_t pp2d_kernel_launches(void) { return g_launches.load(); }
+
+int pp2d_mdp_create(uint32_t height, uint32_t width, const uint8_t* map,
+                    uint32_t goal_x, uint32_t goal_y, float gamma,
+                    pp2d_mdp** out) {
+  return create_impl(height, width, map, goal_x, goal_y, gamma, 0, height,
+                     false, out);
+}
+
+int pp2d_mdp_create_shard(uint32_t height, uint32_t width, const uint8_t* map,
+                          uint32_t goal_x, uint32_t goal_y, float gamma,
+                          uint32_t row_begin, uint32_t row_end,
+                          pp2d_mdp** out) {
+  return create_impl(height, width, map, goal_x, goal_y, gamma, row_begin,
+                     row_end, true, out);
+}
+
+void pp2d_mdp_destroy(pp2d_mdp* h) {
+  if (!h) return;
+  cudaFree(h->j[0]); cudaFree(h->j[1]); cudaFree(h->jchk); cudaFree(h->code);
+  cudaFree(h->action); cudaFree(h->occ); cudaFree(h->dense); cudaFree(h->lut);
+  cudaFree(h->resid);
+  if (h->resid_host) cudaFreeHost(h->resid_host);
+  delete h;
+}
+
+int pp2d_mdp_set_stream(pp2d_mdp* h, void* stream) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  h->stream = (cudaStream_t)stream;
+  return PP2D_OK;
+}
+
+int pp2d_mdp_set_async(pp2d_mdp* h, int async) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  h->async = async != 0;
+  return PP2D_OK;
+}
+
+int pp2d_mdp_sweeps_ex(pp2d_mdp* h, uint32_t n, int want_action) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (n == 0) return PP2D_OK;
+  if (h->sharded && n > 2)
+    return fail(PP2D_ERR_STATE,
+                "a shard can advance at most 2 sweeps between halo exchanges");
+  // Value-only sweeps are fused in pairs; when the action grid is wanted the
+  // last sweep is the arg-min variant, which leaves exactly what the
+  // reference holds after n launches of cudaOneStepValueIteration.
+  uint32_t plain = want_action ? n - 1 : n;
+  int rc;
+  while (plain >= 2) {
+    if ((rc = launch_sweep_cw<2, false>(h, h->cw2)) != PP2D_OK) return rc;
+    plain -= 2;
+  }
+  if (plain == 1)
+    if ((rc = launch_sweep_cw<1, false>(h, h->cw1)) != PP2D_OK) return rc;
+  if (want_action) {
+    if ((rc = launch_sweep_cw<1, true>(h, h->cw1)) != PP2D_OK) return rc;
+    h->action_sweep = h->n_sweeps;
+  }
+  h->action_host_valid = false;
+  return sync_if_needed(h);
+}
+
+int pp2d_mdp_sweeps(pp2d_mdp* h, uint32_t n) {
+  return pp2d_mdp_sweeps_ex(h, n, 1);
+}
+
+uint32_t pp2d_mdp_sweep_count(const pp2d_mdp* h) { return h ? h->n_sweeps : 0; }
+
+int pp2d_mdp_residual_device(pp2d_mdp* h, void** dev_float_out) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  PP2D_CUDA(cudaMemsetAsync(h->resid, 0, sizeof(uint32_t), h->stream));
+  // Occupied cells are stored as 0; their change since the last check point
+  // is the closed form and enters the reduction as a floor value.
+  float floor_val = 0.0f;
+  if (h->has_occupied)
+    floor_val = fabsf(trapped_cost(h, h->n_sweeps) - trapped_cost(h, h->n_chk));
+  uint32_t floor_bits;
+  memcpy(&floor_bits, &floor_val, sizeof(floor_bits));
+  // Owned rows only (ghost rows belong to the neighbours).
+  const size_t off = (size_t)kPadRows * h->pitch;
+  const size_t n4 = (size_t)h->H * h->pitch / 4;
+  int grid = h->sm_count * 8;
+  if ((size_t)grid * 256 > n4) grid = (int)((n4 + 255) / 256);
+  if (grid < 1) grid = 1;
+  mdp_residual_kernel<<<grid, 256, 0, h->stream>>>(
+      reinterpret_cast<const float4*>(h->j[h->cur] + off),
+      reinterpret_cast<float4*>(h->jchk + off), n4, floor_bits, h->resid);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  PP2D_CUDA(cudaGetLastError());
+  h->n_chk = h->n_sweeps;
+  if (dev_float_out) *dev_float_out = h->resid;
+  return sync_if_needed(h);
+}
+
+int pp2d_mdp_residual(pp2d_mdp* h, float* inf_norm) {
+  if (!h || !inf_norm) return fail(PP2D_ERR_INVALID, "NULL argument");
+  int rc = pp2d_mdp_residual_device(h, nullptr);
+  if (rc != PP2D_OK) return rc;
+  PP2D_CUDA(cudaMemcpyAsync(h->resid_host, h->resid, sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, h->stream));
+  PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  memcpy(inf_norm, h->resid_host, sizeof(float));
+  return PP2D_OK;
+}
+
+int pp2d_mdp_solve(pp2d_mdp* h, uint32_t* sweeps_out, double* residuals,
+                   uint32_t max_residuals) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (h->sharded)
+    return fail(PP2D_ERR_STATE, "pp2d_mdp_solve needs an unsharded handle");
+  // path_planning_2d.cu:219-263.
+  double cost_inf_norm = 0.0;
+  const double max_optimal_cost = 5.0 / (1.0 - h->gamma);
+  uint32_t batch = 0, total = 0;
+  do {
+    int rc = pp2d_mdp_sweeps(h, 100);
+    if (rc != PP2D_OK) return rc;
+    total += 100;
+    float r = 0.f;
+    rc = pp2d_mdp_residual(h, &r);
+    if (rc != PP2D_OK) return rc;
+    cost_inf_norm = r;
+    if (residuals && batch < max_residuals) residuals[batch] = cost_inf_norm;
+    ++batch;
+  } while (cost_inf_norm > max_optimal_cost * 1e-3);
+  if (sweeps_out) *sweeps_out = total;
+  return PP2D_OK;
+}
+
+int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  const size_t owned = (size_t)h->H * h->W;
+  if (cost) {
+    if (!h->dense) PP2D_CUDA(cudaMalloc(&h->dense, owned * sizeof(float)));
+    dim3 grid((h->W + 255) / 256, h->H);
+    mdp_export_kernel<<<grid, 256, 0, h->stream>>>(
+        h->j[h->cur], h->code, h->dense, (int)h->W, (int)h->H, h->pitch,
+        trapped_cost(h, h->n_sweeps));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PP2D_CUDA(cudaGetLastError());
+    PP2D_CUDA(cudaMemcpyAsync(cost, h->dense, owned * sizeof(float),
+                              cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (action)
+    PP2D_CUDA(cudaMemcpyAsync(action, h->action, owned, cudaMemcpyDeviceToHost,
+                              h->stream));
+  PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  return PP2D_OK;
+}
+
+int pp2d_mdp_plan_batch(pp2d_mdp* h, const float* beliefs, uint32_t n_beliefs,
+                        uint8_t* actions) {
+  if (!h || !beliefs || !actions) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (h->sharded)
+    return fail(PP2D_ERR_STATE, "pp2d_mdp_plan needs an unsharded handle");
+  if (n_beliefs == 0) return PP2D_OK;
+  const size_t n = (size_t)h->H * h->W;
+  float* d_b = nullptr;
+  uint8_t* d_a = nullptr;
+  PP2D_CUDA(cudaMalloc(&d_b, n * n_beliefs * sizeof(float)));
+  cudaError_t e = cudaMalloc(&d_a, n_beliefs);
+  if (e != cudaSuccess) { cudaFree(d_b); PP2D_CUDA(e); }
+  int rc = [&]() -> int {
+    PP2D_CUDA(cudaMemcpyAsync(d_b, beliefs, n * n_beliefs * sizeof(float),
+                              cudaMemcpyHostToDevice, h->stream));
+    mdp_plan_kernel<<<n_beliefs, 256, 0, h->stream>>>(d_b, n, h->action, d_a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PP2D_CUDA(cudaGetLastError());
+    PP2D_CUDA(cudaMemcpyAsync(actions, d_a, n_beliefs, cudaMemcpyDeviceToHost,
+                              h->stream));
+    PP2D_CUDA(cudaStreamSynchronize(h->stream));
+    return PP2D_OK;
+  }();
+  cudaFree(d_b);
+  cudaFree(d_a);
+  return rc;
+}
+
+int pp2d_mdp_plan(pp2d_mdp* h, const float* belief, uint8_t* action) {
+  return pp2d_mdp_plan_batch(h, belief, 1, action);
+}
+
+int pp2d_mdp_waypoints(pp2d_mdp* h, uint32_t sx, uint32_t sy, uint32_t* cells,
+                       uint32_t max_len, uint32_t* n_out) {
+  if (!h || !cells || !n_out) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (h->sharded)
+    return fail(PP2D_ERR_STATE, "pp2d_mdp_waypoints needs an unsharded handle");
+  if (sx >= h->W || sy >= h->H)
+    return fail(PP2D_ERR_INVALID, "start (%u %u) outside the map", sx, sy);
+  if (!h->action_host_valid) {
+    h->action_host.resize((size_t)h->H * h->W);
+    int rc = pp2d_mdp_download(h, nullptr, h->action_host.data());
+    if (rc != PP2D_OK) return rc;
+    h->action_host_valid = true;
+  }
+  uint32_t n = 0;
+  int64_t x = sx, y = sy;
+  while (n < max_len && x >= 0 && x < (int64_t)h->W && y >= 0 &&
+         y < (int64_t)h->H) {
+    cells[n++] = (uint32_t)(y * h->W + x);
+    const uint8_t u = h->action_host[(size_t)y * h->W + x];
+    if (u == 4) break;
+    x += (int)(u % 3) - 1;   // path_planning_2d_cuda.cu:83-88
+    y += (int)(u / 3) - 1;
+  }
+  *n_out = n;
+  return PP2D_OK;
+}
+
+int pp2d_mdp_halo(pp2d_mdp* h, pp2d_halo* out) {
+  if (!h || !out) return fail(PP2D_ERR_INVALID, "NULL argument");
+  float* j = h->j[h->cur];
+  const size_t row = (size_t)h->pitch;
+  out->recv_top = j;                                       // rows -2, -1
+  out->send_top = j + kPadRows * row;                      // rows 0, 1
+  out->send_bottom = j + (size_t)h->H * row;               // rows H-2, H-1
+  out->recv_bottom = j + (size_t)(h->H + kPadRows) * row;  // rows H, H+1
+  out->bytes = kPadRows * row * sizeof(float);
+  return PP2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+"""Generate the committed fixtures under tests/golden/.
+
+  python tests/golden/make_golden.py maps
+      (build container only: needs /root/reference and cv2)  Exports the five
+      bundled PNG maps as uint8 occupancy grids with the reference's own calls
+      (src/mdp/path_planning_2d.cu:191-197: imread GRAYSCALE, threshold 250
+      BINARY_INV) into tests/golden/maps/<name>.npy.
+
+  python tests/golden/make_golden.py ref [outdir]
+      (GPU box: needs oracle/_ref/libpp2d_ref_mdp.so, never reads
+      /root/reference)  Runs the UNMODIFIED reference CUDA kernels on every
+      bundled map and on small synthetic maps and stores J, action, sweep
+      count, per-batch residuals (and the model tables for the small maps)
+      as <outdir>/ref_<name>.npz.  The files committed in tests/golden/ were
+      produced this way on a B200 (see DESIGN.md "Oracle pin").
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+
+
+def make_maps():
+    import cv2
+    src = "/root/reference/path_planning_2d/maps"
+    os.makedirs(os.path.join(HERE, "maps"), exist_ok=True)
+    for name in cases.BUNDLED:
+        img = cv2.imread(os.path.join(src, name + ".png"), cv2.IMREAD_GRAYSCALE)
+        _, grid = cv2.threshold(img, 250.0, 1.0, cv2.THRESH_BINARY_INV)
+        grid = np.ascontiguousarray(grid, dtype=np.uint8)
+        np.save(os.path.join(HERE, "maps", name + ".npy"), grid)
+        print(name, grid.shape, int(grid.sum()), "occupied")
+
+
+def ref_lib():
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libpp2d_ref_mdp.so"))
+    vp, u32 = ctypes.c_void_p, ctypes.c_uint32
+    lib.ref_mdp_solve.restype = ctypes.c_int
+    lib.ref_mdp_solve.argtypes = [u32, u32, vp, u32, u32, ctypes.c_float, vp,
+                                  vp, vp, ctypes.c_int]
+    lib.ref_mdp_tables.restype = ctypes.c_int
+    lib.ref_mdp_tables.argtypes = [u32, u32, vp, u32, u32, vp, vp]
+    lib.ref_mdp_time_sweeps.restype = ctypes.c_int
+    lib.ref_mdp_time_sweeps.argtypes = [u32, u32, vp, u32, u32, ctypes.c_float,
+                                        ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_float)]
+    return lib
+
+
+def ref_solve(lib, grid, goal, gamma, max_batches=0):
+    h, w = grid.shape
+    J = np.zeros(h * w, np.float32)
+    A = np.zeros(h * w, np.uint8)
+    res = np.zeros(256, np.float64)
+    n = lib.ref_mdp_solve(h, w, grid.ctypes.data, goal[0], goal[1], gamma,
+                          J.ctypes.data, A.ctypes.data, res.ctypes.data,
+                          max_batches)
+    return J.reshape(h, w), A.reshape(h, w), n, res[:n // 100].copy()
+
+
+def ref_tables(lib, grid, goal):
+    h, w = grid.shape
+    tp = np.zeros(h * w * 81, np.float32)
+    sc = np.zeros(h * w * 9, np.float32)
+    lib.ref_mdp_tables(h, w, grid.ctypes.data, goal[0], goal[1],
+                       tp.ctypes.data, sc.ctypes.data)
+    return tp.reshape(h * w, 9, 9), sc.reshape(h * w, 9)
+
+
+def golden_cases():
+    """(name, grid, goal, gamma, max_batches, with_tables)"""
+    out = []
+    for name, (goal, _start) in cases.BUNDLED.items():
+        out.append((name, cases.load_bundled(name), goal, cases.GAMMA, 0, True))
+    # synthetic: ragged sizes, other discount factors, one batch only
+    for i, (h, w, p, g) in enumerate([(37, 53, 0.2, 0.95), (64, 130, 0.35, 0.9),
+                                      (129, 31, 0.1, 0.99), (1, 17, 0.2, 0.95),
+                                      (23, 1, 0.2, 0.95), (2, 2, 0.0, 0.5)]):
+        grid, goal = cases.synthetic_map(h, w, p, seed=100 + i)
+        out.append((f"syn{i}_{h}x{w}", grid, goal, g, 1, h * w <= 4096))
+    return out
+
+
+def make_ref(outdir):
+    os.makedirs(outdir, exist_ok=True)
+    lib = ref_lib()
+    for name, grid, goal, gamma, max_batches, with_tables in golden_cases():
+        J, A, n, res = ref_solve(lib, grid, goal, gamma, max_batches)
+        data = dict(grid=grid, goal=np.array(goal), gamma=np.float32(gamma),
+                    J=J, action=A, sweeps=np.int32(n), residuals=res)
+        if with_tables:
+            tp, sc = ref_tables(lib, grid, goal)
+            data.update(trans_prob=tp, stage_cost=sc)
+        np.savez_compressed(os.path.join(outdir, f"ref_{name}.npz"), **data)
+        print(name, grid.shape, "sweeps", n, "residuals", res)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 2 and sys.argv[1] == "maps":
+        make_maps()
+    elif len(sys.argv) >= 2 and sys.argv[1] == "ref":
+        make_ref(sys.argv[2] if len(sys.argv) > 2 else
+                 os.path.join(ROOT, "gpurun_out", "golden_ref"))
+    else:
+        print(__doc__)
