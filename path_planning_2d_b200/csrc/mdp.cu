@@ -157,18 +157,25 @@ static int launch_sweep(pp2d_mdp* h) {
   p.H = (int)h->H;
   p.pitch = h->pitch;
   p.n_strips = ((int)h->W + G::S - 1) / G::S;
+  // A value-only single sweep also produces the first ghost row on each
+  // side, so that a second sweep can follow without an exchange (the fused
+  // kernel does the same in registers).  Outside the map those rows are
+  // padding and stay 0.
+  p.y_begin = (T == 1 && !POLICY) ? -1 : 0;
+  p.y_end = (T == 1 && !POLICY) ? (int)h->H + 1 : (int)h->H;
+  const int rows = p.y_end - p.y_begin;
   int rpu = h->rows_per_unit;
   if (rpu <= 0) {
     // Enough units for ~4 CTAs of 8 warps per SM, at least 16 rows each so
     // the 2*T halo rows stay a small fraction.
     long target_units = (long)h->sm_count * 8 * 4;
     long rb = (target_units + p.n_strips - 1) / p.n_strips;
-    rpu = (int)((h->H + rb - 1) / rb);
+    rpu = (int)((rows + rb - 1) / rb);
     if (rpu < 16) rpu = 16;
     if (rpu > 128) rpu = 128;
   }
   p.rows_per_unit = rpu;
-  const int n_rb = ((int)h->H + rpu - 1) / rpu;
+  const int n_rb = (rows + rpu - 1) / rpu;
   p.n_units = p.n_strips * n_rb;
   p.gamma = h->gamma * 1.0f;
   p.ga = h->gamma * 0.7f;
@@ -240,7 +247,7 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->sharded = sharded;
   h->sm_count = prop.multiProcessorCount;
   h->pitch = (int)((kPadLeft + width + 128 + 31) / 32 * 32);
-  h->plane = (size_t)(h->H + 2 * kPadRows) * h->pitch;
+  h->plane = (size_t)(h->H + 2 * kPadRows + kSlackRows) * h->pitch;
   h->trapped.push_back(0.0f);
   h->cw2 = env_int("PP2D_MDP_CW2", 2);
   h->cw1 = env_int("PP2D_MDP_CW1", 4);

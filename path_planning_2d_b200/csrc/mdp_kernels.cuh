@@ -43,6 +43,8 @@
 namespace pp2d {
 
 constexpr int kPadRows = 2;   // ghost rows above and below the owned rows
+constexpr int kSlackRows = 4; // extra rows at the bottom: prefetch may overrun
+constexpr int kPrefetch = 3;  // rows of J / codes in flight per lane
 constexpr int kPadLeft = 8;   // zero columns left of x = 0 (32 B)
 constexpr int kLutFloat4 = 4 * 16 * 8;  // 4 action pairs x 16 rows x 8 copies
 
@@ -59,6 +61,7 @@ struct SweepParams {
   const float4* lut;     // kLutFloat4 entries, already lane-replicated
   int W, H, pitch;
   int n_strips, rows_per_unit, n_units;
+  int y_begin, y_end;    // rows to produce (may extend 1 row into the ghosts)
   float gamma, ga, gb;   // gamma*1.0f, gamma*0.7f, gamma*0.1f
 };
 
@@ -158,17 +161,35 @@ __device__ __forceinline__ void fill_row(const float (&own)[CW],
   for (int j = 0; j < CW; ++j) row[1 + j] = own[j];
 }
 
-// Fetch the 4 table rows of one cell.  lut_lane already points at this
-// lane's replica ((lane & 7) * 16 bytes into the table).
-__device__ __forceinline__ void lut_fetch(const char* lut_lane, uint32_t code,
+// Fetch the 4 table rows of one cell.  `word` holds two 16-bit codes; HI
+// selects the upper one.  lane_base = shared address of the table (8 KB
+// aligned) | (lane & 7) * 16, so the row offset can be OR-ed in: one shift
+// and one LOP3 per row.
+template <int IMM>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(addr), "n"(IMM));
+  return v;
+}
+
+template <bool HI, int P>
+__device__ __forceinline__ float4 lut_row(uint32_t lane_base, uint32_t word) {
+  const uint32_t sh = HI ? (word >> (9 + 2 * P)) : (word << (7 - 2 * P));
+  return lds128<P * 2048>((sh & 0x780u) | lane_base);
+}
+
+template <bool HI>
+__device__ __forceinline__ void lut_fetch(uint32_t lane_base, uint32_t word,
                                           float4 (&t)[4], float& g4) {
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    uint32_t off = (code & (0xFu << (2 * p))) << (7 - 2 * p);
-    t[p] = *reinterpret_cast<const float4*>(lut_lane + p * 2048 + off);
-  }
-  // live bit (14) -> 2.0f (0x40000000); goal, occupied, padding -> 0.0f.
-  g4 = __uint_as_float((code << 16) & 0x40000000u);
+  t[0] = lut_row<HI, 0>(lane_base, word);
+  t[1] = lut_row<HI, 1>(lane_base, word);
+  t[2] = lut_row<HI, 2>(lane_base, word);
+  t[3] = lut_row<HI, 3>(lane_base, word);
+  // live bit (14 of the code) -> 2.0f (0x40000000); goal, occupied cells and
+  // padding -> 0.0f, which makes "stay" cost exactly 0 there (their J is 0).
+  g4 = __uint_as_float((HI ? word : (word << 16)) & 0x40000000u);
 }
 
 template <int T, int CW>
@@ -185,42 +206,46 @@ struct Sweeper {
   float B[3][CW + 2];        // J^1 rows y-2, y-1, y (T == 2)
   float4 L[2][CW][4];        // LUT rows of row y (cur) and y-1 (prev)
   float G4[2][CW];
-  float nxt[CW];             // prefetched raw J^0 row
-  uint32_t cnx[(CW + 1) / 2];  // prefetched codes of the next row
+  float nxt[kPrefetch][CW];              // prefetched raw J^0 rows
+  uint32_t cnx[kPrefetch][(CW + 1) / 2]; // prefetched code rows
 
   const SweepParams& p;
-  const char* lut_lane;
-  const float* jin;          // lane's column, row 0
-  float* jout;
-  const uint16_t* code;
+  uint32_t lane_base;        // shared address of this lane's table replica
+  const float* pin;          // next J^0 row to prefetch (row y+1+kPrefetch)
+  const uint16_t* pcode;     // next code row to prefetch (row y+kPrefetch)
+  float* pout;               // row written at step y (y for T=1, y-1 for T=2)
+  uint8_t* pact;             // action row y (POLICY)
   int x0;                    // map x of the lane's first cell
-  int y0, y1;                // owned rows of this unit [y0, y1)
   bool valid;
 
-  __device__ __forceinline__ Sweeper(const SweepParams& p_, const char* lut_)
-      : p(p_), lut_lane(lut_) {}
+  __device__ __forceinline__ Sweeper(const SweepParams& p_, uint32_t lb)
+      : p(p_), lane_base(lb) {}
 
-  template <int I>
-  __device__ __forceinline__ void step(int y) {
+  // One marching step on row y.  I: rotation index (compile time).  J2: also
+  // produce the second sweep of row y-1 (steady state of T == 2).
+  template <int I, bool J2>
+  __device__ __forceinline__ void step() {
     constexpr int a0 = I % 3, a1 = (I + 1) % 3, a2 = (I + 2) % 3;
     constexpr int lc = I % 2, lp = (I + 1) % 2;
-    const int pitch = p.pitch;
-    // Row y+1 arrived (prefetched one step ago): add the horizontal halo.
-    fill_row<CW>(nxt, A[a2]);
+    constexpr int q = I % kPrefetch;
+    // Row y+1 arrived (prefetched kPrefetch steps ago): add the horizontal
+    // halo from the neighbour lanes.
+    fill_row<CW>(nxt[q], A[a2]);
     uint32_t cc[(CW + 1) / 2];
 #pragma unroll
-    for (int j = 0; j < (CW + 1) / 2; ++j) cc[j] = cnx[j];
-    // Prefetch row y+2 and the codes of row y+1.
-    const int ylast = (T == 2) ? y1 : y1 - 1;   // last y this unit steps on
-    if (y < ylast) {
-      load_own<CW>(jin + (size_t)(y + 2 + kPadRows) * pitch, nxt);
-      load_codes<CW>(code + (size_t)(y + 1 + kPadRows) * pitch, cnx);
-    }
+    for (int j = 0; j < (CW + 1) / 2; ++j) cc[j] = cnx[q][j];
+    // Refill the slot: row y+1+kPrefetch and the codes of row y+kPrefetch
+    // (the planes have kSlackRows spare rows at the bottom, so the last
+    // steps may read past the last row they need).
+    load_own<CW>(pin, nxt[q]);
+    load_codes<CW>(pcode, cnx[q]);
+    pin += p.pitch;
+    pcode += p.pitch;
     // Table rows of row y.
 #pragma unroll
     for (int j = 0; j < CW; ++j) {
-      uint32_t cj = (j & 1) ? (cc[j >> 1] >> 16) : cc[j >> 1];
-      lut_fetch(lut_lane, cj, L[lc][j], G4[lc][j]);
+      if (j & 1) lut_fetch<true>(lane_base, cc[j >> 1], L[lc][j], G4[lc][j]);
+      else lut_fetch<false>(lane_base, cc[j >> 1], L[lc][j], G4[lc][j]);
     }
     float v1[CW];
     uint32_t act[CW];
@@ -233,22 +258,23 @@ struct Sweeper {
     }
     if constexpr (T == 1) {
       if (valid) {
-        store_own<CW>(jout + (size_t)(y + kPadRows) * pitch, v1);
+        store_own<CW>(pout, v1);
         if constexpr (POLICY) {
 #pragma unroll
           for (int j = 0; j < CW; ++j) {
             if (x0 + j < p.W) {
-              uint32_t cj = (j & 1) ? (cc[j >> 1] >> 16) : cc[j >> 1];
+              const uint32_t cj = (j & 1) ? (cc[j >> 1] >> 16) : cc[j >> 1];
               // Occupied cells tie on every action in the reference -> 0.
-              p.action[(size_t)y * p.W + x0 + j] =
-                  (cj & kCodeOccBit) ? 0 : (uint8_t)act[j];
+              pact[j] = (cj & kCodeOccBit) ? 0 : (uint8_t)act[j];
             }
           }
         }
       }
+      pout += p.pitch;
+      if constexpr (POLICY) pact += p.W;
     } else {
       fill_row<CW>(v1, B[a2]);
-      if (y > y0) {
+      if constexpr (J2) {
         float v2[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
@@ -258,7 +284,8 @@ struct Sweeper {
                                 L[lp][j], G4[lp][j], p.gamma, p.ga, p.gb,
                                 act[j]);
         }
-        if (valid) store_own<CW>(jout + (size_t)(y - 1 + kPadRows) * pitch, v2);
+        if (valid) store_own<CW>(pout, v2);
+        pout += p.pitch;
       }
     }
   }
@@ -266,35 +293,56 @@ struct Sweeper {
   __device__ __forceinline__ void run(int unit, int lane) {
     const int k = unit % p.n_strips;
     const int rb = unit / p.n_strips;
-    y0 = rb * p.rows_per_unit;
-    y1 = min(y0 + p.rows_per_unit, p.H);
+    const int y0 = p.y_begin + rb * p.rows_per_unit;      // rows [y0, y1)
+    const int y1 = min(y0 + p.rows_per_unit, p.y_end);
     x0 = k * G::S + G::XOFF + lane * CW;
     valid = (lane >= G::HL) && (lane < 32 - G::HL) && (x0 < p.W);
     const size_t col = (size_t)(x0 + kPadLeft);
-    jin = p.jin + col;
-    jout = p.jout + col;
-    code = p.code + col;
-    const int pitch = p.pitch;
+    const size_t pitch = (size_t)p.pitch;
     // First row stepped on: y0-1 for T=2 (J^1 of the row above), y0 for T=1.
     const int ys = (T == 2) ? y0 - 1 : y0;
-    const int ye = (T == 2) ? y1 : y1 - 1;
+    int steps = y1 - ys + (T == 2 ? 1 : 0);               // rows ys .. ye
+    const float* jin = p.jin + col + (size_t)(ys - 1 + kPadRows) * pitch;
     {
       float r[CW];
-      load_own<CW>(jin + (size_t)(ys - 1 + kPadRows) * pitch, r);
+      load_own<CW>(jin, r);
       fill_row<CW>(r, A[0]);
-      load_own<CW>(jin + (size_t)(ys + kPadRows) * pitch, r);
+      load_own<CW>(jin + pitch, r);
       fill_row<CW>(r, A[1]);
-      load_own<CW>(jin + (size_t)(ys + 1 + kPadRows) * pitch, nxt);
-      load_codes<CW>(code + (size_t)(ys + kPadRows) * pitch, cnx);
     }
-    int y = ys;
-    while (true) {
-      step<0>(y); if (++y > ye) break;
-      step<1>(y); if (++y > ye) break;
-      step<2>(y); if (++y > ye) break;
-      step<3>(y); if (++y > ye) break;
-      step<4>(y); if (++y > ye) break;
-      step<5>(y); if (++y > ye) break;
+    pin = jin + 2 * pitch;                                  // row ys+1
+    pcode = p.code + col + (size_t)(ys + kPadRows) * pitch; // row ys
+#pragma unroll
+    for (int d = 0; d < kPrefetch; ++d) {
+      load_own<CW>(pin, nxt[d]);
+      load_codes<CW>(pcode, cnx[d]);
+      pin += pitch;
+      pcode += pitch;
+    }
+    pout = p.jout + col + (size_t)(y0 + kPadRows) * pitch;
+    if constexpr (POLICY) pact = p.action + (size_t)y0 * p.W + x0;
+    if constexpr (T == 2) {
+      // Two priming steps (rows y0-1 and y0) produce J^1 only.
+      step<0, false>();
+      step<1, false>();
+      steps -= 2;
+      while (true) {
+        step<2, true>(); if (--steps == 0) break;
+        step<3, true>(); if (--steps == 0) break;
+        step<4, true>(); if (--steps == 0) break;
+        step<5, true>(); if (--steps == 0) break;
+        step<0, true>(); if (--steps == 0) break;
+        step<1, true>(); if (--steps == 0) break;
+      }
+    } else {
+      while (true) {
+        step<0, false>(); if (--steps == 0) break;
+        step<1, false>(); if (--steps == 0) break;
+        step<2, false>(); if (--steps == 0) break;
+        step<3, false>(); if (--steps == 0) break;
+        step<4, false>(); if (--steps == 0) break;
+        step<5, false>(); if (--steps == 0) break;
+      }
     }
   }
 };
@@ -303,14 +351,25 @@ struct Sweeper {
 template <int T, int CW, bool POLICY>
 __global__ void __launch_bounds__(256)
 mdp_sweep_kernel(const SweepParams p) {
-  __shared__ float4 lut_s[kLutFloat4];
+  // The table must start on a 2 KB boundary of the shared window so that the
+  // row offset (bits 7..10) and the lane replica (bits 4..6) can be OR-ed
+  // into the base.  The window itself starts at 1 KB (system reserved), so
+  // the alignment is done at run time on an over-allocated buffer.
+  __shared__ __align__(16) unsigned char lut_raw[kLutFloat4 * 16 + 2048];
+  const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(lut_raw);
+  const uint32_t lut_addr = (raw_addr + 2047u) & ~2047u;
+  float4* lut_s = reinterpret_cast<float4*>(lut_raw + (lut_addr - raw_addr));
   for (int i = threadIdx.x; i < kLutFloat4; i += blockDim.x) lut_s[i] = p.lut[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (unit >= p.n_units) return;
-  Sweeper<T, CW, POLICY> s(p, reinterpret_cast<const char*>(lut_s) +
-                                  (lane & 7) * 16);
+  // Produced by a volatile asm after the barrier: the table loads (plain asm,
+  // free to be scheduled) depend on it and so cannot move above the barrier.
+  uint32_t lane_base;
+  asm volatile("or.b32 %0, %1, %2;"
+               : "=r"(lane_base) : "r"(lut_addr), "r"((lane & 7) << 4) : "memory");
+  Sweeper<T, CW, POLICY> s(p, lane_base);
   s.run(unit, lane);
 }
 
