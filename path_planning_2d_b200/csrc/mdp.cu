@@ -131,7 +131,7 @@ struct pp2d_mdp {
   bool async = false;
   int sm_count = 148;
   // tuning knobs (environment overridable, see mdp_config)
-  int cw2 = 2, cw1 = 4, rows_per_unit = 0;
+  int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6;
 };
 
 namespace pp2d {
@@ -177,6 +177,7 @@ static int launch_sweep(pp2d_mdp* h) {
   p.rows_per_unit = rpu;
   const int n_rb = (rows + rpu - 1) / rpu;
   p.n_units = p.n_strips * n_rb;
+  p.prefetch_rows = h->prefetch_rows;
   p.gamma = h->gamma * 1.0f;
   p.ga = h->gamma * 0.7f;
   p.gb = h->gamma * 0.1f;
@@ -252,6 +253,9 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->cw2 = env_int("PP2D_MDP_CW2", 2);
   h->cw1 = env_int("PP2D_MDP_CW1", 4);
   h->rows_per_unit = env_int("PP2D_MDP_ROWS_PER_UNIT", 0);
+  h->prefetch_rows = env_int("PP2D_MDP_PREFETCH_ROWS", 6);
+  if (h->prefetch_rows < kPrefetch) h->prefetch_rows = kPrefetch;
+  if (h->prefetch_rows > kSlackRows) h->prefetch_rows = kSlackRows;
 
   // Occupancy rows needed for the codes of rows row_begin-2 .. row_end+1.
   const int occ_row0 = (int)row_begin - 3 < 0 ? 0 : (int)row_begin - 3;

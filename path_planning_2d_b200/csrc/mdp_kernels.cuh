@@ -43,8 +43,8 @@
 namespace pp2d {
 
 constexpr int kPadRows = 2;   // ghost rows above and below the owned rows
-constexpr int kSlackRows = 4; // extra rows at the bottom: prefetch may overrun
-constexpr int kPrefetch = 3;  // rows of J / codes in flight per lane
+constexpr int kSlackRows = 8; // extra rows at the bottom: prefetch may overrun
+constexpr int kPrefetch = 2;  // rows of J / codes held in registers ahead of use
 constexpr int kPadLeft = 8;   // zero columns left of x = 0 (32 B)
 constexpr int kLutFloat4 = 4 * 16 * 8;  // 4 action pairs x 16 rows x 8 copies
 
@@ -62,6 +62,7 @@ struct SweepParams {
   int W, H, pitch;
   int n_strips, rows_per_unit, n_units;
   int y_begin, y_end;    // rows to produce (may extend 1 row into the ghosts)
+  int prefetch_rows;     // rows ahead touched with prefetch.global.L1 (>= kPrefetch)
   float gamma, ga, gb;   // gamma*1.0f, gamma*0.7f, gamma*0.1f
 };
 
@@ -111,17 +112,21 @@ __device__ __forceinline__ float backup(float j0, float j1, float j2, float j3,
   }
 }
 
+// Row loads are volatile asm on purpose: a plain __ldg() is sunk by the
+// compiler to just before its first use, which collapses the kPrefetch-deep
+// software pipeline (seen in the ncu source view: long-scoreboard stalls on
+// the first use of every prefetched register).
 template <int CW>
 __device__ __forceinline__ void load_own(const float* __restrict__ p,
                                          float (&o)[CW]) {
   if constexpr (CW == 1) {
-    o[0] = __ldg(p);
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(o[0]) : "l"(p));
   } else if constexpr (CW == 2) {
-    float2 v = __ldg(reinterpret_cast<const float2*>(p));
-    o[0] = v.x; o[1] = v.y;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];"
+                 : "=f"(o[0]), "=f"(o[1]) : "l"(p));
   } else {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "l"(p));
   }
 }
 
@@ -141,12 +146,14 @@ template <int CW>
 __device__ __forceinline__ void load_codes(const uint16_t* __restrict__ p,
                                            uint32_t (&c)[(CW + 1) / 2]) {
   if constexpr (CW == 1) {
-    c[0] = __ldg(p);
+    uint16_t v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    c[0] = v;
   } else if constexpr (CW == 2) {
-    c[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(c[0]) : "l"(p));
   } else {
-    uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-    c[0] = v.x; c[1] = v.y;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];"
+                 : "=r"(c[0]), "=r"(c[1]) : "l"(p));
   }
 }
 
@@ -215,6 +222,7 @@ struct Sweeper {
   const uint16_t* pcode;     // next code row to prefetch (row y+kPrefetch)
   float* pout;               // row written at step y (y for T=1, y-1 for T=2)
   uint8_t* pact;             // action row y (POLICY)
+  size_t l1_ahead;           // kPrefetchL1 rows, in elements
   int x0;                    // map x of the lane's first cell
   bool valid;
 
@@ -239,6 +247,10 @@ struct Sweeper {
     // steps may read past the last row they need).
     load_own<CW>(pin, nxt[q]);
     load_codes<CW>(pcode, cnx[q]);
+    // ptxas sinks the two loads above towards their first use, so the real
+    // latency hiding is done by touching the lines prefetch_rows rows ahead.
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(pin + l1_ahead));
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(pcode + l1_ahead));
     pin += p.pitch;
     pcode += p.pitch;
     // Table rows of row y.
@@ -299,6 +311,7 @@ struct Sweeper {
     valid = (lane >= G::HL) && (lane < 32 - G::HL) && (x0 < p.W);
     const size_t col = (size_t)(x0 + kPadLeft);
     const size_t pitch = (size_t)p.pitch;
+    l1_ahead = (size_t)(p.prefetch_rows - kPrefetch) * pitch;
     // First row stepped on: y0-1 for T=2 (J^1 of the row above), y0 for T=1.
     const int ys = (T == 2) ? y0 - 1 : y0;
     int steps = y1 - ys + (T == 2 ? 1 : 0);               // rows ys .. ye
