@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpp2d.so")
+# PP2D_LIB: alternate build of the same ABI (tuning experiments only).
+LIB_PATH = os.environ.get("PP2D_LIB") or os.path.join(_HERE, "libpp2d.so")
 
 PP2D_OK = 0
 PP2D_ERR_INVALID = -1

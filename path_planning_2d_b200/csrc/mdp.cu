@@ -131,7 +131,7 @@ struct pp2d_mdp {
   bool async = false;
   int sm_count = 148;
   // tuning knobs (environment overridable, see mdp_config)
-  int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6;
+  int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6, waves = 1;
 };
 
 namespace pp2d {
@@ -166,13 +166,18 @@ static int launch_sweep(pp2d_mdp* h) {
   const int rows = p.y_end - p.y_begin;
   int rpu = h->rows_per_unit;
   if (rpu <= 0) {
-    // Enough units for ~4 CTAs of 8 warps per SM, at least 16 rows each so
-    // the 2*T halo rows stay a small fraction.
-    long target_units = (long)h->sm_count * 8 * 4;
-    long rb = (target_units + p.n_strips - 1) / p.n_strips;
+    // Units are equal-sized, so the launch is sized to fill exactly
+    // `waves` full waves of resident CTAs (8 warps = 8 units per CTA): one
+    // more CTA than that would run alone in an extra wave.
+    int ctas_per_sm = 0;
+    PP2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY>, 256, 0));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const long slots = (long)h->sm_count * ctas_per_sm * 8;   // resident warps
+    long rb = slots * h->waves / p.n_strips;                  // floor
+    if (rb < 1) rb = 1;
     rpu = (int)((rows + rb - 1) / rb);
-    if (rpu < 16) rpu = 16;
-    if (rpu > 128) rpu = 128;
+    if (rpu < 8) rpu = 8;
   }
   p.rows_per_unit = rpu;
   const int n_rb = (rows + rpu - 1) / rpu;
@@ -254,6 +259,8 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->cw1 = env_int("PP2D_MDP_CW1", 4);
   h->rows_per_unit = env_int("PP2D_MDP_ROWS_PER_UNIT", 0);
   h->prefetch_rows = env_int("PP2D_MDP_PREFETCH_ROWS", 6);
+  h->waves = env_int("PP2D_MDP_WAVES", 1);
+  if (h->waves < 1) h->waves = 1;
   if (h->prefetch_rows < kPrefetch) h->prefetch_rows = kPrefetch;
   if (h->prefetch_rows > kSlackRows) h->prefetch_rows = kSlackRows;
 

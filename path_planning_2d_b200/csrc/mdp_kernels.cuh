@@ -44,7 +44,11 @@ namespace pp2d {
 
 constexpr int kPadRows = 2;   // ghost rows above and below the owned rows
 constexpr int kSlackRows = 8; // extra rows at the bottom: prefetch may overrun
-constexpr int kPrefetch = 2;  // rows of J / codes held in registers ahead of use
+constexpr int kPrefetch = 2;  // CW == 1 path: rows held in registers ahead of use
+#ifndef PP2D_KRING
+#define PP2D_KRING 3
+#endif
+constexpr int kRing = PP2D_KRING;  // CW >= 2 path: cp.async ring slots per lane (1, 2, 3 or 6)
 constexpr int kPadLeft = 8;   // zero columns left of x = 0 (32 B)
 constexpr int kLutFloat4 = 4 * 16 * 8;  // 4 action pairs x 16 rows x 8 copies
 
@@ -199,11 +203,58 @@ __device__ __forceinline__ void lut_fetch(uint32_t lane_base, uint32_t word,
   g4 = __uint_as_float((HI ? word : (word << 16)) & 0x40000000u);
 }
 
+// ---- cp.async staging (CW >= 2) --------------------------------------------
+// Every lane copies its own CW floats of J and CW codes of a row into its
+// private slot of a per-warp shared-memory ring, kRing rows ahead, and reads
+// them back itself: cp.async.wait_group is per thread, so no warp or block
+// synchronisation is needed.  Unlike register loads (which ptxas sinks to
+// their first use, sharing a scoreboard with younger loads) the copies are
+// issued where they are written and waited for with a counting barrier
+// (LDGDEPBAR / DEPBAR.LE in SASS).
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;"
+               :: "r"(saddr), "l"(g), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+template <int CW, int OFF>
+__device__ __forceinline__ void lds_row(uint32_t saddr, float (&o)[CW]) {
+  if constexpr (CW == 2) {
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];"
+                 : "=f"(o[0]), "=f"(o[1]) : "r"(saddr), "n"(OFF) : "memory");
+  } else {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                 : "r"(saddr), "n"(OFF) : "memory");
+  }
+}
+template <int CW, int OFF>
+__device__ __forceinline__ void lds_codes(uint32_t saddr,
+                                          uint32_t (&c)[(CW + 1) / 2]) {
+  if constexpr (CW == 2) {
+    asm volatile("ld.shared.u32 %0, [%1+%2];"
+                 : "=r"(c[0]) : "r"(saddr), "n"(OFF) : "memory");
+  } else {
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];"
+                 : "=r"(c[0]), "=r"(c[1]) : "r"(saddr), "n"(OFF) : "memory");
+  }
+}
+
 template <int T, int CW>
 struct StripGeom {
   static constexpr int HL = (T + CW - 1) / CW;          // halo lanes per side
   static constexpr int S = (32 - 2 * HL) * CW;          // valid columns/strip
   static constexpr int XOFF = -HL * CW;                 // x of lane 0, cell 0
+  // cp.async ring: per warp and slot, 32 lanes x (CW floats + CW codes).
+  static constexpr int kSlotBytes = 32 * CW * 6;
+  static constexpr int kCodeOff = 32 * CW * 4;
+  static constexpr int kRingBytesPerWarp = (CW >= 2) ? kRing * kSlotBytes : 0;
 };
 
 template <int T, int CW, bool POLICY>
@@ -222,12 +273,14 @@ struct Sweeper {
   const uint16_t* pcode;     // next code row to prefetch (row y+kPrefetch)
   float* pout;               // row written at step y (y for T=1, y-1 for T=2)
   uint8_t* pact;             // action row y (POLICY)
-  size_t l1_ahead;           // kPrefetchL1 rows, in elements
+  size_t l1_ahead;           // CW == 1: rows ahead for prefetch.global.L1
+  uint32_t ring_j, ring_c;   // CW >= 2: shared addresses of this lane's ring slots
   int x0;                    // map x of the lane's first cell
   bool valid;
 
-  __device__ __forceinline__ Sweeper(const SweepParams& p_, uint32_t lb)
-      : p(p_), lane_base(lb) {}
+  __device__ __forceinline__ Sweeper(const SweepParams& p_, uint32_t lb,
+                                     uint32_t ring_warp)
+      : p(p_), lane_base(lb), ring_j(ring_warp), ring_c(ring_warp) {}
 
   // One marching step on row y.  I: rotation index (compile time).  J2: also
   // produce the second sweep of row y-1 (steady state of T == 2).
@@ -235,22 +288,30 @@ struct Sweeper {
   __device__ __forceinline__ void step() {
     constexpr int a0 = I % 3, a1 = (I + 1) % 3, a2 = (I + 2) % 3;
     constexpr int lc = I % 2, lp = (I + 1) % 2;
-    constexpr int q = I % kPrefetch;
-    // Row y+1 arrived (prefetched kPrefetch steps ago): add the horizontal
-    // halo from the neighbour lanes.
-    fill_row<CW>(nxt[q], A[a2]);
     uint32_t cc[(CW + 1) / 2];
-#pragma unroll
-    for (int j = 0; j < (CW + 1) / 2; ++j) cc[j] = cnx[q][j];
-    // Refill the slot: row y+1+kPrefetch and the codes of row y+kPrefetch
-    // (the planes have kSlackRows spare rows at the bottom, so the last
-    // steps may read past the last row they need).
-    load_own<CW>(pin, nxt[q]);
-    load_codes<CW>(pcode, cnx[q]);
-    // ptxas sinks the two loads above towards their first use, so the real
-    // latency hiding is done by touching the lines prefetch_rows rows ahead.
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(pin + l1_ahead));
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(pcode + l1_ahead));
+    if constexpr (CW >= 2) {
+      constexpr int slot = I % kRing;
+      // The oldest of the kRing groups in flight (row y+1, codes of row y)
+      // has landed in this lane's slot.
+      cp_async_wait<kRing - 1>();
+      float own[CW];
+      lds_row<CW, slot * G::kSlotBytes>(ring_j, own);
+      lds_codes<CW, slot * G::kSlotBytes + G::kCodeOff>(ring_c, cc);
+      fill_row<CW>(own, A[a2]);
+      // Refill the slot with row y+1+kRing / codes of row y+kRing (the planes
+      // have kSlackRows spare rows, so the last steps may run past the end).
+      cp_async<CW * 4>(ring_j + slot * G::kSlotBytes, pin);
+      cp_async<CW * 2>(ring_c + slot * G::kSlotBytes + G::kCodeOff, pcode);
+      cp_async_commit();
+    } else {
+      constexpr int q = I % kPrefetch;
+      fill_row<CW>(nxt[q], A[a2]);
+      cc[0] = cnx[q][0];
+      load_own<CW>(pin, nxt[q]);
+      load_codes<CW>(pcode, cnx[q]);
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(pin + l1_ahead));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(pcode + l1_ahead));
+    }
     pin += p.pitch;
     pcode += p.pitch;
     // Table rows of row y.
@@ -325,12 +386,25 @@ struct Sweeper {
     }
     pin = jin + 2 * pitch;                                  // row ys+1
     pcode = p.code + col + (size_t)(ys + kPadRows) * pitch; // row ys
+    if constexpr (CW >= 2) {
+      ring_j += lane * (CW * 4);
+      ring_c += lane * (CW * 2);
 #pragma unroll
-    for (int d = 0; d < kPrefetch; ++d) {
-      load_own<CW>(pin, nxt[d]);
-      load_codes<CW>(pcode, cnx[d]);
-      pin += pitch;
-      pcode += pitch;
+      for (int d = 0; d < kRing; ++d) {
+        cp_async<CW * 4>(ring_j + d * G::kSlotBytes, pin);
+        cp_async<CW * 2>(ring_c + d * G::kSlotBytes + G::kCodeOff, pcode);
+        cp_async_commit();
+        pin += pitch;
+        pcode += pitch;
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < kPrefetch; ++d) {
+        load_own<CW>(pin, nxt[d]);
+        load_codes<CW>(pcode, cnx[d]);
+        pin += pitch;
+        pcode += pitch;
+      }
     }
     pout = p.jout + col + (size_t)(y0 + kPadRows) * pitch;
     if constexpr (POLICY) pact = p.action + (size_t)y0 * p.W + x0;
@@ -357,6 +431,8 @@ struct Sweeper {
         step<5, false>(); if (--steps == 0) break;
       }
     }
+    // Do not leave the CTA with copies in flight into its shared memory.
+    if constexpr (CW >= 2) cp_async_wait<0>();
   }
 };
 
@@ -368,7 +444,10 @@ mdp_sweep_kernel(const SweepParams p) {
   // row offset (bits 7..10) and the lane replica (bits 4..6) can be OR-ed
   // into the base.  The window itself starts at 1 KB (system reserved), so
   // the alignment is done at run time on an over-allocated buffer.
-  __shared__ __align__(16) unsigned char lut_raw[kLutFloat4 * 16 + 2048];
+  using G = StripGeom<T, CW>;
+  constexpr int kWarps = 8;
+  __shared__ __align__(16) unsigned char
+      lut_raw[kLutFloat4 * 16 + 2048 + kWarps * G::kRingBytesPerWarp];
   const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(lut_raw);
   const uint32_t lut_addr = (raw_addr + 2047u) & ~2047u;
   float4* lut_s = reinterpret_cast<float4*>(lut_raw + (lut_addr - raw_addr));
@@ -382,7 +461,9 @@ mdp_sweep_kernel(const SweepParams p) {
   uint32_t lane_base;
   asm volatile("or.b32 %0, %1, %2;"
                : "=r"(lane_base) : "r"(lut_addr), "r"((lane & 7) << 4) : "memory");
-  Sweeper<T, CW, POLICY> s(p, lane_base);
+  const uint32_t ring_warp =
+      lut_addr + kLutFloat4 * 16 + (threadIdx.x >> 5) * G::kRingBytesPerWarp;
+  Sweeper<T, CW, POLICY> s(p, lane_base, ring_warp);
   s.run(unit, lane);
 }
 

@@ -17,9 +17,11 @@ from path_planning_2d_b200 import MdpPathPlanning2d  # noqa: E402
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 grid, goal = cases.synthetic_map(size, size, 0.20, seed=12345)
 rows = []
-for cw2, rpu, pf in [(1, 0, 6), (1, 64, 6), (4, 0, 6), (4, 128, 6)] + [(2, r, f) for r in (0, 32, 64, 128) for f in (2, 4, 6, 8)]:
+quick = len(sys.argv) > 2
+combos = [(4, 0, 1), (4, 0, 2), (4, 0, 3), (2, 0, 1), (2, 0, 2), (2, 0, 3), (2, 0, 4), (2, 128, 1), (4, 128, 1)]
+for cw2, rpu, pf in combos:
     os.environ["PP2D_MDP_CW2"] = str(cw2)
-    os.environ["PP2D_MDP_PREFETCH_ROWS"] = str(pf)
+    os.environ["PP2D_MDP_WAVES"] = str(pf)
     os.environ["PP2D_MDP_ROWS_PER_UNIT"] = str(rpu)
     with MdpPathPlanning2d(grid, goal, cases.GAMMA) as m:
         m.set_stream(torch.cuda.current_stream().cuda_stream, asynchronous=True)
@@ -35,7 +37,7 @@ for cw2, rpu, pf in [(1, 0, 6), (1, 64, 6), (4, 0, 6), (4, 128, 6)] + [(2, r, f)
             best = min(best, e0.elapsed_time(e1))
         rate = size * size * 100 / (best * 1e-3)
         rows.append((cw2, rpu, best / 50, rate))
-        print(f"T=2 cw={cw2} rows_per_unit={rpu:4d} prefetch={pf}  {best/50*1e3:8.1f} us/launch  "
+        print(f"T=2 cw={cw2} rows_per_unit={rpu:4d} waves={pf}  {best/50*1e3:8.1f} us/launch  "
               f"{rate/1e9:8.1f} Gcell/s  {rate*10/6537.6e9:.3f} of HBM roofline", flush=True)
 for cw1 in [1, 2, 4]:
     os.environ["PP2D_MDP_CW1"] = str(cw1)
