@@ -82,6 +82,16 @@ int pp2d_mdp_create_shard(uint32_t height, uint32_t width, const uint8_t* map,
                           uint32_t row_begin, uint32_t row_end,
                           pp2d_mdp** out);
 
+/*
+ * Start over on the same handle with a new map (same height/width/rows) and
+ * goal: J = 0, action = 0, sweep count 0, codes rebuilt.  Same checks as
+ * pp2d_mdp_create; lets a long-running planner re-solve without paying the
+ * device allocations again (the reference allocates once per process,
+ * src/mdp/path_planning_2d.cu:91).
+ */
+int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
+                   uint32_t goal_y);
+
 /* Replaces freeDeviceMemory (src/mdp/path_planning_2d_cuda.cu:66-74). */
 void pp2d_mdp_destroy(pp2d_mdp* h);
 

@@ -34,6 +34,7 @@ SIGNATURES = {
                              ctypes.POINTER(_vp)]),
     "pp2d_mdp_create_shard": (_i, [_u32, _u32, _vp, _u32, _u32, ctypes.c_float,
                                    _u32, _u32, ctypes.POINTER(_vp)]),
+    "pp2d_mdp_reset": (_i, [_vp, _vp, _u32, _u32]),
     "pp2d_mdp_destroy": (None, [_vp]),
     "pp2d_mdp_set_stream": (_i, [_vp, _vp]),
     "pp2d_mdp_set_async": (_i, [_vp, _i]),

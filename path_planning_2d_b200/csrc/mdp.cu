@@ -215,6 +215,41 @@ static int env_int(const char* name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
+// Zero J / action, upload the occupancy rows this handle needs and rebuild
+// the code plane: allocateDeviceMemory's memsets + the map upload + the model
+// generation of the reference (path_planning_2d_cuda.cu:55-61,
+// path_planning_2d.cu:94-106).
+static int upload_map(pp2d_mdp* h, const uint8_t* map) {
+  const size_t owned = (size_t)h->H * h->W;
+  const int occ_row0 = (int)h->row_begin - 3 < 0 ? 0 : (int)h->row_begin - 3;
+  const int row_end = (int)(h->row_begin + h->H);
+  const int occ_row1 = row_end + 3 > (int)h->Htot ? (int)h->Htot : row_end + 3;
+  const int occ_rows = occ_row1 - occ_row0;
+  PP2D_CUDA(cudaMemsetAsync(h->j[0], 0, h->plane * sizeof(float), h->stream));
+  PP2D_CUDA(cudaMemsetAsync(h->j[1], 0, h->plane * sizeof(float), h->stream));
+  PP2D_CUDA(cudaMemsetAsync(h->jchk, 0, h->plane * sizeof(float), h->stream));
+  PP2D_CUDA(cudaMemsetAsync(h->action, 0, owned, h->stream));
+  PP2D_CUDA(cudaMemcpyAsync(h->occ, map + (size_t)occ_row0 * h->W,
+                            (size_t)occ_rows * h->W, cudaMemcpyHostToDevice,
+                            h->stream));
+  CodeParams cp;
+  cp.occ = h->occ; cp.code = h->code; cp.W = (int)h->W; cp.Htot = (int)h->Htot;
+  cp.pitch = h->pitch; cp.rows_phys = (int)h->H + 2 * kPadRows;
+  cp.row_begin = (int)h->row_begin; cp.occ_row0 = occ_row0; cp.occ_rows = occ_rows;
+  cp.gx = (int)h->gx; cp.gy = (int)h->gy;
+  dim3 grid((h->pitch + 255) / 256, cp.rows_phys);
+  mdp_code_kernel<<<grid, 256, 0, h->stream>>>(cp);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  PP2D_CUDA(cudaGetLastError());
+  PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  h->has_occupied =
+      memchr(map + (size_t)h->row_begin * h->W, 1, owned) != nullptr;
+  h->cur = 0;
+  h->n_sweeps = h->n_chk = h->action_sweep = 0;
+  h->action_host_valid = false;
+  return PP2D_OK;
+}
+
 static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
                        uint32_t gx, uint32_t gy, float gamma,
                        uint32_t row_begin, uint32_t row_end, bool sharded,
@@ -264,14 +299,9 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   if (h->prefetch_rows < kPrefetch) h->prefetch_rows = kPrefetch;
   if (h->prefetch_rows > kSlackRows) h->prefetch_rows = kSlackRows;
 
-  // Occupancy rows needed for the codes of rows row_begin-2 .. row_end+1.
-  const int occ_row0 = (int)row_begin - 3 < 0 ? 0 : (int)row_begin - 3;
-  const int occ_row1 = row_end + 3 > height ? (int)height : (int)row_end + 3;
-  const int occ_rows = occ_row1 - occ_row0;
+  const int occ_rows = (int)((row_end + 3 > height ? height : row_end + 3) -
+                             ((int)row_begin - 3 < 0 ? 0 : row_begin - 3));
   const size_t owned = (size_t)h->H * width;
-  for (size_t i = 0; i < owned && !h->has_occupied; ++i)
-    if (map[(size_t)row_begin * width + i] == 1) h->has_occupied = true;
-
   int rc = [&]() -> int {
     PP2D_CUDA(cudaMalloc(&h->j[0], h->plane * sizeof(float)));
     PP2D_CUDA(cudaMalloc(&h->j[1], h->plane * sizeof(float)));
@@ -282,29 +312,11 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
     PP2D_CUDA(cudaMalloc(&h->lut, kLutFloat4 * sizeof(float4)));
     PP2D_CUDA(cudaMalloc(&h->resid, sizeof(uint32_t)));
     PP2D_CUDA(cudaMallocHost(&h->resid_host, sizeof(uint32_t)));
-    // J1 = J2 = 0, action = 0 (path_planning_2d_cuda.cu:55-61).
-    PP2D_CUDA(cudaMemset(h->j[0], 0, h->plane * sizeof(float)));
-    PP2D_CUDA(cudaMemset(h->j[1], 0, h->plane * sizeof(float)));
-    PP2D_CUDA(cudaMemset(h->jchk, 0, h->plane * sizeof(float)));
-    PP2D_CUDA(cudaMemset(h->action, 0, owned));
-    // Map upload (path_planning_2d.cu:94-95).
-    PP2D_CUDA(cudaMemcpy(h->occ, map + (size_t)occ_row0 * width,
-                         (size_t)occ_rows * width, cudaMemcpyHostToDevice));
     std::vector<float4> lut;
     build_lut(gamma, lut);
     PP2D_CUDA(cudaMemcpy(h->lut, lut.data(), kLutFloat4 * sizeof(float4),
                          cudaMemcpyHostToDevice));
-    CodeParams cp;
-    cp.occ = h->occ; cp.code = h->code; cp.W = (int)width; cp.Htot = (int)height;
-    cp.pitch = h->pitch; cp.rows_phys = (int)h->H + 2 * kPadRows;
-    cp.row_begin = (int)row_begin; cp.occ_row0 = occ_row0; cp.occ_rows = occ_rows;
-    cp.gx = (int)gx; cp.gy = (int)gy;
-    dim3 grid((h->pitch + 255) / 256, cp.rows_phys);
-    mdp_code_kernel<<<grid, 256>>>(cp);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    PP2D_CUDA(cudaGetLastError());
-    PP2D_CUDA(cudaDeviceSynchronize());
-    return PP2D_OK;
+    return upload_map(h, map);
   }();
   if (rc != PP2D_OK) { pp2d_mdp_destroy(h); return rc; }
   *out = h;
@@ -332,6 +344,21 @@ int pp2d_mdp_create_shard(uint32_t height, uint32_t width, const uint8_t* map,
                           pp2d_mdp** out) {
   return create_impl(height, width, map, goal_x, goal_y, gamma, row_begin,
                      row_end, true, out);
+}
+
+int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
+                   uint32_t goal_y) {
+  if (!h || !map) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (goal_x >= h->W || goal_y >= h->Htot)
+    return fail(PP2D_ERR_INVALID, "goal (%u %u) outside the %ux%u map", goal_x,
+                goal_y, h->W, h->Htot);
+  if (map[(size_t)goal_y * h->W + goal_x] > 0)
+    return fail(PP2D_ERR_GOAL_OCCUPIED,
+                "The assigned goal (%u %u) is at a occupied cell...", goal_x,
+                goal_y);
+  h->gx = goal_x;
+  h->gy = goal_y;
+  return upload_map(h, map);
 }
 
 void pp2d_mdp_destroy(pp2d_mdp* h) {

@@ -66,6 +66,10 @@ class GpuShard:
     def sweeps(self, n, want_action):
         self.mdp.sweeps(n, want_action)
 
+    def reset(self, grid, goal):
+        torch.cuda.current_stream().synchronize()
+        self.mdp.reset(grid, goal)
+
     def halo_tensors(self):
         h = self.mdp.halo()
         t = lambda p: device_tensor(p, h.bytes)
@@ -93,6 +97,11 @@ class ShardedValueIteration:
         self.bounds = partition_rows(self.height, self.world)
         self.rows = self.bounds[self.rank]
         self.shard = shard_factory(grid, goal, gamma, self.rows)
+        self.n_sweeps = 0
+
+    def reset(self, grid=None, goal=None):
+        """Re-solve from J = 0 with a new map (same shape) and/or goal."""
+        self.shard.reset(grid, goal)
         self.n_sweeps = 0
 
     # -- ghost rows --------------------------------------------------------

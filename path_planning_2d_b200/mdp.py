@@ -72,6 +72,18 @@ class MdpPathPlanning2d:
     def __exit__(self, *exc):
         self.close()
 
+    def reset(self, grid_map=None, goal=None):
+        """New map (same shape) and/or goal on the same device buffers."""
+        if grid_map is not None:
+            grid_map = np.ascontiguousarray(grid_map, dtype=np.uint8)
+            if grid_map.shape != (self.map_height, self.map_width):
+                raise ValueError("reset() needs a map of the same shape")
+            self._map = grid_map
+        if goal is not None:
+            self.goal = (int(goal[0]), int(goal[1]))
+        _lib.check(self._lib.pp2d_mdp_reset(self._h, self._map.ctypes.data,
+                                            self.goal[0], self.goal[1]))
+
     # -- solver -----------------------------------------------------------
     def set_stream(self, cuda_stream_ptr, asynchronous=False):
         _lib.check(self._lib.pp2d_mdp_set_stream(self._h, cuda_stream_ptr))

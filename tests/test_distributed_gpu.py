@@ -1,0 +1,61 @@
+"""GPU tier, needs >= 2 GPUs (skipped otherwise): the NCCL row-sharded driver
+against the single-GPU solve, bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import oracle_py
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from path_planning_2d_b200.distributed import ShardedValueIteration
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        grid, goal = cases.synthetic_map(301, 517, 0.2, seed=77)
+        vi = ShardedValueIteration(grid, goal, cases.GAMMA)
+        vi.sweeps(5, want_action=False)
+        sweeps, residuals = vi.value_iteration(max_batches=2)
+        cost, action = vi.gather()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), cost=cost, action=action,
+                     sweeps=sweeps, residuals=np.array(residuals))
+        vi.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_sharded_solve_matches_single_gpu(tmp_path):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world,
+             join=True)
+    got = np.load(tmp_path / "out.npz")
+    grid, goal = cases.synthetic_map(301, 517, 0.2, seed=77)
+    ora = oracle_py.OracleMdp(grid, goal, cases.GAMMA)
+    ora.sweeps(205)
+    assert int(got["sweeps"]) == 205
+    assert np.array_equal(got["cost"].view(np.uint32), ora.cost.view(np.uint32))
+    assert np.array_equal(got["action"], ora.act)

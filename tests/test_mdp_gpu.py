@@ -237,3 +237,21 @@ def test_full_size_properties_4096():
     sel[8:250, 8:250] = True
     assert np.array_equal(_bits(cc[:256, :256])[sel], _bits(ora.cost)[sel])
     assert np.array_equal(ac[:256, :256][sel], ora.act[sel])
+
+
+def test_reset_reuses_the_handle():
+    grid, goal = cases.synthetic_map(97, 143, 0.25, seed=21)
+    grid2, goal2 = cases.synthetic_map(97, 143, 0.1, seed=22, goal=(5, 90))
+    with MdpPathPlanning2d(grid, goal, cases.GAMMA) as mdp:
+        mdp.sweeps(9)
+        mdp.residual()
+        mdp.reset(grid2, goal2)
+        assert mdp.sweep_count == 0
+        ora = oracle_py.OracleMdp(grid2, goal2, cases.GAMMA)
+        mdp.sweeps(12)
+        ora.sweeps(12)
+        _assert_same(mdp, ora, "after reset")
+        assert mdp.residual() == np.float32(np.abs(ora.cost).max())
+        grid2[goal2[1], goal2[0]] = 1
+        with pytest.raises(_lib.Pp2dError):
+            mdp.reset(grid2, goal2)
