@@ -187,6 +187,91 @@ int pp2d_mdp_halo(pp2d_mdp* h, pp2d_halo* out);
 /* Device-side residual for shards: enqueue the reduction, then read it. */
 int pp2d_mdp_residual_device(pp2d_mdp* h, void** dev_float_out);
 
+/* ------------------------------------------------------------------------
+ * POMDP model, belief propagation, bounds and QV-Tree Search
+ * 
+ * ------------------------------------------------------------------------ */
+typedef struct pp2d_pomdp pp2d_pomdp;
+typedef struct pp2d_tree pp2d_tree;
+
+/*
+ * Replaces allocateDeviceMemoryOfModel + generateModelData
+ * (src/pomdp/model_generation_cuda.cu:41-59, 349-375; call site
+ * src/pomdp/path_planning_2d.cu:109-112): uploads the map and builds
+ * trans_prob f32[HW][9][9], meas_prob f32[HW][16], stage_reward f32[HW][9] on
+ * the device in the reference's layout.  Goal on an occupied cell ->
+ * PP2D_ERR_GOAL_OCCUPIED (src/pomdp/path_planning_2d.cu:93-97).
+ */
+int pp2d_pomdp_create(uint32_t height, uint32_t width, const uint8_t* map,
+                      uint32_t goal_x, uint32_t goal_y, float gamma,
+                      pp2d_pomdp** out);
+/* Replaces freeDeviceMemoryOfModel / ...OfFIB / ...OfPBVI. */
+void pp2d_pomdp_destroy(pp2d_pomdp* h);
+/* The host mirrors host_trans_prob / host_meas_prob / host_stage_reward
+ * (model_generation_cuda.cu:366-371); any pointer may be NULL. */
+int pp2d_pomdp_model_tables(pp2d_pomdp* h, float* trans_prob, float* meas_prob,
+                            float* stage_reward);
+/* The 100 curand_uniform values cudaForwardSampling consumes for its 50
+ * samples (search_tree_cuda.cu:84-92,117,134; XORWOW, seed 1234, subsequence
+ * = sample index, re-initialised per call, hence constant). */
+int pp2d_pomdp_sampling_uniforms(pp2d_pomdp* h, float* out100);
+/*
+ * The alpha vectors the tree reads: replaces host_fib_alphas f32[HW][9] +
+ * host_fib_actions u8[9] (fast_informed_bound_cuda.cu:36-52) and
+ * host_pbvi_alphas f32[n][HW] + host_pbvi_actions u8[n]
+ * (point_based_value_iteration_cuda.cu:44-58), however they were produced
+ * (solvers or loadFibDataFromFile / loadPbviDataFromFile).  fib_actions /
+ * pbvi_actions may be NULL (identity / zeros).
+ */
+int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
+                          const uint8_t* fib_actions, const float* pbvi_alphas,
+                          const uint8_t* pbvi_actions, uint32_t n_pbvi);
+/* Size the device belief pool for n_beliefs resident beliefs (optional). */
+int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs);
+/*
+ * Batched cudaBayesBeliefUpdate (point_based_value_iteration_cuda.cu:88-133;
+ * call sites search_tree_cuda.cu:217, 601): out[i] = update(in[i], actions[i],
+ * observations[i]), beliefs laid out [n][HW] in host memory.  normalize != 0
+ * also applies the host normalisation of search_tree_cuda.cu:226-229 and
+ * returns the pre-normalisation sums (may be NULL).
+ */
+int pp2d_pomdp_bayes_update(pp2d_pomdp* h, const float* beliefs_in, uint32_t n,
+                            const uint8_t* actions, const uint8_t* observations,
+                            int normalize, float* beliefs_out, float* sums);
+/*
+ * Batched evaluateFibCpu / evaluatePbviCpu
+ * (fast_informed_bound_cuda.cu:278-297,
+ * point_based_value_iteration_cuda.cu:678-699): upper = max_a <b, fib_a>,
+ * lower = max_i <b, pbvi_i> and the action attached to the maximiser, same
+ * summation order and roundings as the reference.  Outputs may be NULL.
+ */
+int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
+                        float* upper, uint8_t* upper_action, float* lower,
+                        uint8_t* lower_action);
+/*
+ * n independent PomdpPathPlanning2d::beliefCallback first calls
+ * (src/pomdp/path_planning_2d.cu:199-241): per belief a fresh SearchTree,
+ * up to max_iter expansions while depth < max_depth, then the action with the
+ * largest upper bound and that bound.  Every query uses its own rand()
+ * stream seeded like a fresh process (the planner never calls srand()).
+ * stats (optional): 4 values per query {V nodes, Q nodes, depth, expansions}.
+ */
+int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
+                          uint32_t max_depth, uint32_t max_iter,
+                          uint8_t* actions, float* values, uint32_t* stats);
+
+/* SearchTree (include/path_planning_2d/search_tree.h:130-165). */
+int pp2d_tree_create(pp2d_pomdp* h, const float* belief, pp2d_tree** out);
+void pp2d_tree_destroy(pp2d_tree* t);
+int pp2d_tree_expand(pp2d_tree* t);                       /* expand() */
+uint32_t pp2d_tree_depth(const pp2d_tree* t);             /* getDepth() */
+int pp2d_tree_best_action(const pp2d_tree* t, uint8_t* action, float* value);
+int pp2d_tree_update(pp2d_tree* t, uint8_t action, uint8_t observation);
+int pp2d_tree_root_bounds(const pp2d_tree* t, float* upper, float* lower);
+/* beliefCallback's loop + getOptimalAction on an existing tree. */
+int pp2d_tree_plan(pp2d_tree* t, uint32_t max_depth, uint32_t max_iter,
+                   uint8_t* action, float* value);
+
 #ifdef __cplusplus
 }
 #endif

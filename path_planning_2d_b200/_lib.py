@@ -50,6 +50,24 @@ SIGNATURES = {
                                 ctypes.POINTER(_u32)]),
     "pp2d_mdp_sweep_count": (_u32, [_vp]),
     "pp2d_mdp_halo": (_i, [_vp, ctypes.POINTER(Halo)]),
+    "pp2d_pomdp_create": (_i, [_u32, _u32, _vp, _u32, _u32, ctypes.c_float,
+                               ctypes.POINTER(_vp)]),
+    "pp2d_pomdp_destroy": (None, [_vp]),
+    "pp2d_pomdp_model_tables": (_i, [_vp, _vp, _vp, _vp]),
+    "pp2d_pomdp_sampling_uniforms": (_i, [_vp, _vp]),
+    "pp2d_pomdp_set_alphas": (_i, [_vp, _vp, _vp, _vp, _vp, _u32]),
+    "pp2d_pomdp_reserve": (_i, [_vp, _u32]),
+    "pp2d_pomdp_bayes_update": (_i, [_vp, _vp, _u32, _vp, _vp, _i, _vp, _vp]),
+    "pp2d_pomdp_evaluate": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    "pp2d_pomdp_plan_batch": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "pp2d_tree_create": (_i, [_vp, _vp, ctypes.POINTER(_vp)]),
+    "pp2d_tree_destroy": (None, [_vp]),
+    "pp2d_tree_expand": (_i, [_vp]),
+    "pp2d_tree_depth": (_u32, [_vp]),
+    "pp2d_tree_best_action": (_i, [_vp, _vp, _vp]),
+    "pp2d_tree_update": (_i, [_vp, ctypes.c_uint8, ctypes.c_uint8]),
+    "pp2d_tree_root_bounds": (_i, [_vp, _vp, _vp]),
+    "pp2d_tree_plan": (_i, [_vp, _u32, _u32, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,851 @@
+// pomdp.cu -- host side of the QV-Tree C ABI (include/pp2d.h, pp2d_pomdp_* and
+// pp2d_tree_*).  Replaces, for the reference's PomdpPathPlanning2d
+// (/root/reference/path_planning_2d/src/pomdp/path_planning_2d.cu) and
+// SearchTree (src/pomdp/search_tree_cuda.cu, include/.../search_tree.h):
+//   generateModelData (model_generation_cuda.cu:349-375), the per-child
+//   cudaMalloc / H2D / kernel / sync / D2H / host-normalise / host-bounds
+//   sequence of QNode::QNode (search_tree_cuda.cu:161-242), forwardSampling
+//   (311-366), evaluateFibCpu / evaluatePbviCpu (fast_informed_bound_cuda.cu:
+//   278-297, point_based_value_iteration_cuda.cu:678-699) and the tree
+//   bookkeeping (search_tree_cuda.cu:251-286, 397-450, 479-626).
+// The tree bookkeeping stays on the host, as in the reference; everything
+// that touches a belief runs on the GPU, batched over all the nodes that all
+// the queries of a batch create in one expansion round.  No CPU fallback.
+#include "../../include/pp2d.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "pomdp_kernels.cuh"
+
+namespace pp2d {
+int fail(int code, const char* fmt, ...);            // mdp.cu
+extern std::atomic<uint64_t> g_launches;
+}  // namespace pp2d
+
+using namespace pp2d;
+
+#define PP2D_CUDA(expr)                                                      \
+  do {                                                                       \
+    cudaError_t e_ = (expr);                                                 \
+    if (e_ != cudaSuccess)                                                   \
+      return fail(PP2D_ERR_CUDA, "CUDA error at %s:%d code=%d(%s) \"%s\"",   \
+                  __FILE__, __LINE__, (int)e_, cudaGetErrorName(e_), #expr); \
+  } while (0)
+#define PP2D_TRY(expr)                 \
+  do {                                 \
+    int rc_ = (expr);                  \
+    if (rc_ != PP2D_OK) return rc_;    \
+  } while (0)
+
+namespace {
+
+constexpr int kSamples = 50;      // search_tree_cuda.cu:176
+constexpr int kActions = 9;
+constexpr int kColFib = 0, kColReward = 9, kColPbvi = 18;
+
+// glibc rand() (TYPE_3 additive feedback, what the planner's rand() is since
+// it never calls srand(): search_tree_cuda.cu:332).  Every query owns one
+// stream seeded like a fresh process.
+struct GlibcRand {
+  int32_t r[34];
+  int k;
+  void seed(uint32_t s) {
+    int32_t t[344];
+    if (s == 0) s = 1;
+    t[0] = (int32_t)s;
+    for (int i = 1; i < 31; ++i) {
+      long long v = (16807LL * t[i - 1]) % 2147483647LL;
+      if (v < 0) v += 2147483647LL;
+      t[i] = (int32_t)v;
+    }
+    for (int i = 31; i < 34; ++i) t[i] = t[i - 31];
+    for (int i = 34; i < 344; ++i)
+      t[i] = (int32_t)((uint32_t)t[i - 31] + (uint32_t)t[i - 3]);
+    for (int i = 0; i < 34; ++i) r[i] = t[310 + i];
+    k = 0;
+  }
+  uint32_t next() {
+    uint32_t v = (uint32_t)r[(k + 3) % 34] + (uint32_t)r[(k + 31) % 34];
+    r[k] = (int32_t)v;
+    k = (k + 1) % 34;
+    return v >> 1;
+  }
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return PP2D_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 2 + 64;
+    PP2D_CUDA(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+    return PP2D_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Host-side tree nodes (search_tree.h:30-128), indices instead of pointers.
+struct QNodeH {
+  uint8_t action = 0;
+  int parent = -1;
+  std::vector<int> children;          // V node indices, ascending observation
+  float upper = FLT_MAX, lower = -FLT_MAX, heuristic = FLT_MIN, reward = 0.f;
+  int to_expand = -1;                 // vnode_to_expand (nullptr = -1)
+  uint32_t depth = 1;
+};
+struct VNodeH {
+  int slot = -1;
+  uint8_t obs = 0;
+  float weight = 0.f;
+  int parent = -1;                    // Q node index, -1 for the root
+  std::vector<int> children;          // 9 Q node indices once expanded
+  float upper = FLT_MAX, lower = -FLT_MAX, heuristic = FLT_MIN;
+  int to_expand = -1;
+  uint32_t depth = 0;
+  float reward[kActions] = {0};       // <b, R(:,a)> for a later expansion
+};
+
+struct Tree {
+  std::vector<VNodeH> v;
+  std::vector<QNodeH> q;
+  int root = -1;
+  GlibcRand rng;
+  uint32_t expansions = 0;
+  bool dead = false;                  // reference would dereference nullptr
+};
+
+// search_tree_cuda.cu:251-286
+void qnode_update(Tree& t, int qi, float gamma) {
+  QNodeH& q = t.q[qi];
+  float up = 0.0f, lo = 0.0f;
+  for (int c : q.children) {
+    up += t.v[c].upper * t.v[c].weight;
+    lo += t.v[c].lower * t.v[c].weight;
+  }
+  q.upper = q.reward + gamma * up;
+  q.lower = q.reward + gamma * lo;
+  q.heuristic = 0.0f;
+  for (int c : q.children) {
+    const float h = gamma * t.v[c].weight * t.v[c].heuristic;
+    if (h > q.heuristic) { q.heuristic = h; q.to_expand = t.v[c].to_expand; }
+  }
+  uint32_t child_depth = 0;
+  for (int c : q.children)
+    if (t.v[c].depth > child_depth) { child_depth = t.v[c].depth; q.depth = child_depth + 1; }
+}
+
+// search_tree_cuda.cu:397-435
+void vnode_update(Tree& t, int vi) {
+  VNodeH& v = t.v[vi];
+  int umax = 0, lmax = 0;
+  for (int i = 1; i < (int)v.children.size(); ++i) {
+    if (t.q[v.children[umax]].upper < t.q[v.children[i]].upper) umax = i;
+    if (t.q[v.children[lmax]].lower < t.q[v.children[i]].lower) lmax = i;
+  }
+  v.upper = t.q[v.children[umax]].upper;
+  v.lower = t.q[v.children[lmax]].lower;
+  v.heuristic = -FLT_MAX;
+  for (int c : v.children) {
+    const QNodeH& q = t.q[c];
+    if (q.upper <= v.lower) continue;
+    if (q.heuristic > v.heuristic) { v.heuristic = q.heuristic; v.to_expand = q.to_expand; }
+  }
+  uint32_t child_depth = 0;
+  for (int c : v.children)
+    if (t.q[c].depth > child_depth) { child_depth = t.q[c].depth; v.depth = child_depth + 1; }
+}
+
+}  // namespace
+
+struct pp2d_pomdp {
+  int H = 0, W = 0, HW = 0, gx = 0, gy = 0;
+  float gamma = 0.f;
+  uint8_t* d_map = nullptr;
+  float *d_tp = nullptr, *d_mp = nullptr, *d_sr = nullptr, *d_uniforms = nullptr;
+  // alpha matrix [HW][ld]: FIB | stage reward | PBVI
+  float* d_alpha = nullptr;
+  int ld = 0, ncol = 18, n_pbvi = 0;
+  std::vector<uint8_t> fib_actions, pbvi_actions;
+  bool have_alphas = false;
+  // belief pool [HW][cap]
+  float* d_bel = nullptr;
+  int cap = 0;
+  std::vector<int> free_slots;
+  // scratch
+  DevBuf<int> d_slots;
+  DevBuf<BayesItem> d_items;
+  DevBuf<float> d_prefix, d_draws, d_vals, d_rows, d_sums;
+  DevBuf<uint8_t> d_obs;
+  DevBuf<float> d_out;               // 11 floats per evaluated belief
+  cudaStream_t stream = nullptr;
+  uint64_t n_bayes = 0, n_vnodes = 0;
+};
+
+struct pp2d_tree {
+  pp2d_pomdp* h = nullptr;
+  Tree t;
+};
+
+namespace {
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int pool_reserve(pp2d_pomdp* h, size_t slots_wanted) {
+  if ((size_t)h->cap >= slots_wanted && h->d_bel) return PP2D_OK;
+  if (h->d_bel && h->free_slots.size() != (size_t)h->cap)
+    return fail(PP2D_ERR_STATE, "belief pool is in use (%d slots) and cannot grow to %zu",
+                h->cap, slots_wanted);
+  if (h->d_bel) cudaFree(h->d_bel);
+  h->d_bel = nullptr;
+  size_t cap = (slots_wanted + 31) / 32 * 32;
+  PP2D_CUDA(cudaMalloc(&h->d_bel, cap * (size_t)h->HW * sizeof(float)));
+  h->cap = (int)cap;
+  h->free_slots.resize(cap);
+  for (size_t i = 0; i < cap; ++i) h->free_slots[i] = (int)(cap - 1 - i);
+  return PP2D_OK;
+}
+
+int alloc_slot(pp2d_pomdp* h, int* out) {
+  if (h->free_slots.empty())
+    return fail(PP2D_ERR_STATE, "belief pool exhausted (%d slots)", h->cap);
+  *out = h->free_slots.back();
+  h->free_slots.pop_back();
+  return PP2D_OK;
+}
+
+// Evaluate the beliefs in `slots`: per belief 11 floats
+// {upper, lower, reward[0..8]} into host `out` (B4, B5 and the reward dot of
+// search_tree_cuda.cu:168-173).
+int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
+  const int n = (int)slots.size();
+  if (n == 0) return PP2D_OK;
+  PP2D_TRY(h->d_slots.ensure(n));
+  PP2D_TRY(h->d_vals.ensure((size_t)n * h->ncol));
+  PP2D_TRY(h->d_out.ensure((size_t)n * 11));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((n + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
+  pomdp_values_kernel<<<grid, 256, 0, h->stream>>>(
+      h->HW, h->cap, h->ld, h->ncol, h->d_slots.p, n, h->d_bel, h->d_alpha,
+      h->d_vals.p);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  // bounds + rewards packed: reuse pomdp_bounds_kernel for the maxima, then
+  // copy the 9 reward columns with a strided memcpy.
+  float2* res = reinterpret_cast<float2*>(h->d_out.p);
+  int2* idx = reinterpret_cast<int2*>(h->d_out.p + (size_t)n * 2);
+  pomdp_bounds_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+      n, h->ncol, h->n_pbvi, h->d_vals.p, res, idx);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  std::vector<float> hres((size_t)n * 2), hrew((size_t)n * 9);
+  PP2D_CUDA(cudaMemcpyAsync(hres.data(), res, (size_t)n * 2 * sizeof(float),
+                            cudaMemcpyDeviceToHost, h->stream));
+  PP2D_CUDA(cudaMemcpy2DAsync(hrew.data(), 9 * sizeof(float),
+                              h->d_vals.p + kColReward, h->ncol * sizeof(float),
+                              9 * sizeof(float), n, cudaMemcpyDeviceToHost,
+                              h->stream));
+  PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) {
+    out[i * 11 + 0] = hres[i * 2 + 0];
+    out[i * 11 + 1] = hres[i * 2 + 1];
+    memcpy(out + i * 11 + 2, hrew.data() + (size_t)i * 9, 9 * sizeof(float));
+  }
+  return PP2D_OK;
+}
+
+// search_tree_cuda.cu:368-388 VNode::VNode for already-resident beliefs.
+void init_vnode(VNodeH& v, int slot, uint8_t obs, float weight, int parent,
+                const float* ev, int self) {
+  v.slot = slot; v.obs = obs; v.weight = weight; v.parent = parent;
+  v.upper = ev[0]; v.lower = ev[1];
+  v.heuristic = v.upper - v.lower;
+  v.to_expand = self;
+  v.depth = 0;
+  memcpy(v.reward, ev + 2, 9 * sizeof(float));
+}
+
+// Upload host beliefs ([n][HW]) into fresh slots and create the root V nodes.
+int make_roots(pp2d_pomdp* h, std::vector<Tree*>& trees, const float* beliefs) {
+  const int n = (int)trees.size();
+  std::vector<int> slots(n);
+  for (int i = 0; i < n; ++i) PP2D_TRY(alloc_slot(h, &slots[i]));
+  PP2D_TRY(h->d_slots.ensure(n));
+  PP2D_TRY(h->d_rows.ensure((size_t)n * h->HW));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, beliefs, (size_t)n * h->HW * sizeof(float),
+                            cudaMemcpyHostToDevice, h->stream));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((h->HW + 255) / 256, n);
+  pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n,
+                                                    h->d_rows.p, h->d_bel);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  std::vector<float> ev((size_t)n * 11);
+  PP2D_TRY(evaluate_slots(h, slots, ev.data()));
+  for (int i = 0; i < n; ++i) {
+    Tree& t = *trees[i];
+    t.v.emplace_back();
+    t.root = (int)t.v.size() - 1;
+    init_vnode(t.v.back(), slots[i], 0, 0.0f, -1, ev.data() + (size_t)i * 11, t.root);
+    h->n_vnodes++;
+  }
+  return PP2D_OK;
+}
+
+void free_subtree_v(pp2d_pomdp* h, Tree& t, int vi);
+void free_subtree_q(pp2d_pomdp* h, Tree& t, int qi) {
+  for (int c : t.q[qi].children) free_subtree_v(h, t, c);
+  t.q[qi].children.clear();
+}
+void free_subtree_v(pp2d_pomdp* h, Tree& t, int vi) {
+  for (int c : t.v[vi].children) free_subtree_q(h, t, c);
+  t.v[vi].children.clear();
+  if (t.v[vi].slot >= 0) { h->free_slots.push_back(t.v[vi].slot); t.v[vi].slot = -1; }
+}
+
+// One expansion round (SearchTree::expand, search_tree_cuda.cu:490-508) for
+// every tree in `trees`, all device work batched.
+int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
+  struct Job { Tree* t; int v; };
+  std::vector<Job> jobs;
+  for (Tree* t : trees) {
+    if (t->dead) continue;
+    const int v = t->v[t->root].to_expand;
+    if (v < 0) { t->dead = true; continue; }
+    if (!t->v[v].children.empty()) {            // re-expansion (leak in the ref)
+      for (int c : t->v[v].children) free_subtree_q(h, *t, c);
+      t->v[v].children.clear();
+    }
+    jobs.push_back({t, v});
+  }
+  const int n = (int)jobs.size();
+  if (n == 0) return PP2D_OK;
+  const int HW = h->HW;
+  // --- forward sampling (search_tree_cuda.cu:311-366) ---
+  std::vector<int> slots(n);
+  std::vector<float> draws((size_t)n * kActions * kSamples);
+  for (int i = 0; i < n; ++i) {
+    slots[i] = jobs[i].t->v[jobs[i].v].slot;
+    for (int k = 0; k < kActions * kSamples; ++k)
+      draws[(size_t)i * kActions * kSamples + k] =
+          (float)jobs[i].t->rng.next() / ((float)2147483647 + 1.0f);
+  }
+  PP2D_TRY(h->d_slots.ensure(n));
+  PP2D_TRY(h->d_prefix.ensure((size_t)n * HW));
+  PP2D_TRY(h->d_draws.ensure(draws.size()));
+  PP2D_TRY(h->d_obs.ensure(draws.size()));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_draws.p, draws.data(), draws.size() * sizeof(float),
+                            cudaMemcpyHostToDevice, h->stream));
+  pomdp_prefix_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+      HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_prefix.p);
+  count_launch();
+  const int nt = n * kActions * kSamples;
+  pomdp_sample_kernel<<<(nt + 127) / 128, 128, 0, h->stream>>>(
+      h->H, h->W, n, kSamples, h->d_tp, h->d_mp, h->d_prefix.p, h->d_draws.p,
+      h->d_uniforms, h->d_obs.p);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  std::vector<uint8_t> obs(draws.size());
+  PP2D_CUDA(cudaMemcpyAsync(obs.data(), h->d_obs.p, obs.size(), cudaMemcpyDeviceToHost,
+                            h->stream));
+  PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  // --- unique observations per Q node (search_tree_cuda.cu:181-195) ---
+  std::vector<BayesItem> items;
+  struct Child { int job; uint8_t a, z; float w; int slot; };
+  std::vector<Child> kids;
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < kActions; ++a) {
+      int count[16] = {0};
+      const uint8_t* o = obs.data() + ((size_t)i * kActions + a) * kSamples;
+      for (int k = 0; k < kSamples; ++k) count[o[k] & 15]++;
+      for (int z = 0; z < 16; ++z) {
+        if (!count[z]) continue;
+        Child c{i, (uint8_t)a, (uint8_t)z, (float)count[z] / (float)kSamples, -1};
+        PP2D_TRY(alloc_slot(h, &c.slot));
+        kids.push_back(c);
+        items.push_back(BayesItem{slots[i], c.slot, (uint8_t)a, (uint8_t)z});
+      }
+    }
+  const int nk = (int)kids.size();
+  // --- children beliefs: Bayes update + normalise (search_tree_cuda.cu:213-229)
+  PP2D_TRY(h->d_items.ensure(nk));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), nk * sizeof(BayesItem),
+                            cudaMemcpyHostToDevice, h->stream));
+  dim3 bgrid((nk + 31) / 32, (HW + 7) / 8);
+  pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+                                                   h->d_items.p, nk, h->d_bel, h->d_bel);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  h->n_bayes += nk;
+  std::vector<int> kslots(nk);
+  for (int i = 0; i < nk; ++i) kslots[i] = kids[i].slot;
+  PP2D_TRY(h->d_slots.ensure(nk));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, kslots.data(), nk * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  pomdp_normalize_kernel<<<(nk + 127) / 128, 128, 0, h->stream>>>(
+      HW, h->cap, h->d_slots.p, nk, h->d_bel, nullptr);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  // --- bounds of the new V nodes (search_tree_cuda.cu:376-385) ---
+  std::vector<float> ev((size_t)nk * 11);
+  PP2D_TRY(evaluate_slots(h, kslots, ev.data()));
+  // --- host bookkeeping ---
+  int kpos = 0;
+  for (int i = 0; i < n; ++i) {
+    Tree& t = *jobs[i].t;
+    const int vi = jobs[i].v;
+    t.v[vi].children.resize(kActions);
+    for (int a = 0; a < kActions; ++a) {
+      t.q.emplace_back();
+      const int qi = (int)t.q.size() - 1;
+      t.v[vi].children[a] = qi;
+      t.q[qi].action = (uint8_t)a;
+      t.q[qi].parent = vi;
+      t.q[qi].reward = t.v[vi].reward[a];
+      while (kpos < nk && kids[kpos].job == i && kids[kpos].a == a) {
+        t.v.emplace_back();
+        const int ci = (int)t.v.size() - 1;
+        init_vnode(t.v[ci], kids[kpos].slot, kids[kpos].z, kids[kpos].w, qi,
+                   ev.data() + (size_t)kpos * 11, ci);
+        t.q[qi].children.push_back(ci);
+        h->n_vnodes++;
+        ++kpos;
+      }
+      qnode_update(t, qi, h->gamma);
+    }
+    vnode_update(t, vi);
+    int v = vi;
+    while (t.v[v].parent >= 0) {                 // search_tree_cuda.cu:497-505
+      const int pq = t.v[v].parent;
+      qnode_update(t, pq, h->gamma);
+      const int pv = t.q[pq].parent;
+      vnode_update(t, pv);
+      v = pv;
+    }
+    t.expansions++;
+  }
+  return PP2D_OK;
+}
+
+void best_action(const Tree& t, uint8_t* a, float* r) {   // tree:510-524
+  *a = 0;
+  *r = -FLT_MAX;
+  if (t.root < 0) return;
+  for (int c : t.v[t.root].children)
+    if (t.q[c].upper > *r) { *r = t.q[c].upper; *a = t.q[c].action; }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pp2d_pomdp_create(uint32_t height, uint32_t width, const uint8_t* map,
+                      uint32_t goal_x, uint32_t goal_y, float gamma,
+                      pp2d_pomdp** out) {
+  if (!out) return fail(PP2D_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!map || height == 0 || width == 0) return fail(PP2D_ERR_INVALID, "empty map");
+  if ((uint64_t)height * width > (1u << 26))
+    return fail(PP2D_ERR_INVALID, "map too large for the POMDP path");
+  if (goal_x >= width || goal_y >= height)
+    return fail(PP2D_ERR_INVALID, "goal (%u %u) outside the %ux%u map", goal_x, goal_y,
+                width, height);
+  if (map[(size_t)goal_y * width + goal_x] > 0)   // pomdp path_planning_2d.cu:93-97
+    return fail(PP2D_ERR_GOAL_OCCUPIED,
+                "The assigned goal (%u %u) is at a occupied cell...", goal_x, goal_y);
+  int dev_count = 0;
+  PP2D_CUDA(cudaGetDeviceCount(&dev_count));
+  if (dev_count == 0) return fail(PP2D_ERR_CUDA, "no CUDA device");
+  pp2d_pomdp* h = new (std::nothrow) pp2d_pomdp;
+  if (!h) return fail(PP2D_ERR_INVALID, "out of host memory");
+  h->H = (int)height; h->W = (int)width; h->HW = h->H * h->W;
+  h->gx = (int)goal_x; h->gy = (int)goal_y; h->gamma = gamma;
+  int rc = [&]() -> int {
+    const size_t n = (size_t)h->HW;
+    PP2D_CUDA(cudaMalloc(&h->d_map, n));
+    PP2D_CUDA(cudaMalloc(&h->d_tp, n * 81 * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&h->d_mp, n * 16 * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&h->d_sr, n * 9 * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&h->d_uniforms, 2 * kSamples * sizeof(float)));
+    PP2D_CUDA(cudaMemcpy(h->d_map, map, n, cudaMemcpyHostToDevice));
+    dim3 grid((h->W + 63) / 64, h->H);
+    pomdp_model_kernel<<<grid, 64>>>(h->H, h->W, h->gx, h->gy, h->d_map, h->d_tp,
+                                     h->d_mp, h->d_sr);
+    count_launch();
+    pomdp_uniforms_kernel<<<1, 64>>>(kSamples, h->d_uniforms);
+    count_launch();
+    PP2D_CUDA(cudaGetLastError());
+    PP2D_CUDA(cudaDeviceSynchronize());
+    return PP2D_OK;
+  }();
+  if (rc != PP2D_OK) { pp2d_pomdp_destroy(h); return rc; }
+  *out = h;
+  return PP2D_OK;
+}
+
+void pp2d_pomdp_destroy(pp2d_pomdp* h) {
+  if (!h) return;
+  cudaFree(h->d_map); cudaFree(h->d_tp); cudaFree(h->d_mp); cudaFree(h->d_sr);
+  cudaFree(h->d_uniforms); cudaFree(h->d_alpha); cudaFree(h->d_bel);
+  h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
+  h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
+  h->d_sums.release(); h->d_obs.release(); h->d_out.release();
+  delete h;
+}
+
+int pp2d_pomdp_model_tables(pp2d_pomdp* h, float* trans_prob, float* meas_prob,
+                            float* stage_reward) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  const size_t n = (size_t)h->HW;
+  if (trans_prob)
+    PP2D_CUDA(cudaMemcpy(trans_prob, h->d_tp, n * 81 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (meas_prob)
+    PP2D_CUDA(cudaMemcpy(meas_prob, h->d_mp, n * 16 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (stage_reward)
+    PP2D_CUDA(cudaMemcpy(stage_reward, h->d_sr, n * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+  return PP2D_OK;
+}
+
+int pp2d_pomdp_sampling_uniforms(pp2d_pomdp* h, float* out100) {
+  if (!h || !out100) return fail(PP2D_ERR_INVALID, "NULL argument");
+  PP2D_CUDA(cudaMemcpy(out100, h->d_uniforms, 2 * kSamples * sizeof(float),
+                       cudaMemcpyDeviceToHost));
+  return PP2D_OK;
+}
+
+int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
+                          const uint8_t* fib_actions, const float* pbvi_alphas,
+                          const uint8_t* pbvi_actions, uint32_t n_pbvi) {
+  if (!h || !fib_alphas) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (n_pbvi > 0 && !pbvi_alphas) return fail(PP2D_ERR_INVALID, "pbvi_alphas is NULL");
+  const int ncol = kColPbvi + (int)n_pbvi;
+  const int ld = (ncol + 63) / 64 * 64;
+  const size_t HW = (size_t)h->HW;
+  std::vector<float> mat(HW * ld, 0.0f), sr(HW * 9);
+  PP2D_CUDA(cudaMemcpy(sr.data(), h->d_sr, HW * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t s = 0; s < HW; ++s) {
+    float* row = mat.data() + s * ld;
+    memcpy(row + kColFib, fib_alphas + s * 9, 9 * sizeof(float));
+    memcpy(row + kColReward, sr.data() + s * 9, 9 * sizeof(float));
+    for (uint32_t i = 0; i < n_pbvi; ++i) row[kColPbvi + i] = pbvi_alphas[(size_t)i * HW + s];
+  }
+  if (h->d_alpha) cudaFree(h->d_alpha);
+  h->d_alpha = nullptr;
+  PP2D_CUDA(cudaMalloc(&h->d_alpha, mat.size() * sizeof(float)));
+  PP2D_CUDA(cudaMemcpy(h->d_alpha, mat.data(), mat.size() * sizeof(float),
+                       cudaMemcpyHostToDevice));
+  h->ld = ld; h->ncol = ncol; h->n_pbvi = (int)n_pbvi;
+  h->fib_actions.assign(9, 0);
+  for (int a = 0; a < 9; ++a) h->fib_actions[a] = fib_actions ? fib_actions[a] : (uint8_t)a;
+  h->pbvi_actions.assign(n_pbvi, 0);
+  if (pbvi_actions) memcpy(h->pbvi_actions.data(), pbvi_actions, n_pbvi);
+  h->have_alphas = true;
+  return PP2D_OK;
+}
+
+int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  return pool_reserve(h, n_beliefs);
+}
+
+int pp2d_pomdp_bayes_update(pp2d_pomdp* h, const float* beliefs_in, uint32_t n,
+                            const uint8_t* actions, const uint8_t* observations,
+                            int normalize, float* beliefs_out, float* sums) {
+  if (!h || !beliefs_in || !actions || !observations || !beliefs_out)
+    return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (n == 0) return PP2D_OK;
+  PP2D_TRY(pool_reserve(h, std::max<size_t>(h->cap, 2 * (size_t)n)));
+  if (h->free_slots.size() < 2 * (size_t)n)
+    return fail(PP2D_ERR_STATE, "belief pool too small for %u updates", n);
+  const int HW = h->HW;
+  std::vector<int> in(n), outs(n);
+  std::vector<BayesItem> items(n);
+  for (uint32_t i = 0; i < n; ++i) {
+    PP2D_TRY(alloc_slot(h, &in[i]));
+    PP2D_TRY(alloc_slot(h, &outs[i]));
+    items[i] = BayesItem{in[i], outs[i], actions[i], observations[i]};
+  }
+  int rc = [&]() -> int {
+    PP2D_TRY(h->d_slots.ensure(n));
+    PP2D_TRY(h->d_rows.ensure((size_t)n * HW));
+    PP2D_TRY(h->d_items.ensure(n));
+    PP2D_TRY(h->d_sums.ensure(n));
+    PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, beliefs_in, (size_t)n * HW * sizeof(float),
+                              cudaMemcpyHostToDevice, h->stream));
+    PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, in.data(), n * sizeof(int),
+                              cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((HW + 255) / 256, n);
+    pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(HW, h->cap, h->d_slots.p, n,
+                                                      h->d_rows.p, h->d_bel);
+    count_launch();
+    PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), n * sizeof(BayesItem),
+                              cudaMemcpyHostToDevice, h->stream));
+    dim3 bgrid((n + 31) / 32, (HW + 7) / 8);
+    pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+                                                     h->d_items.p, n, h->d_bel, h->d_bel);
+    count_launch();
+    h->n_bayes += n;
+    PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, outs.data(), n * sizeof(int),
+                              cudaMemcpyHostToDevice, h->stream));
+    if (normalize) {
+      pomdp_normalize_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+          HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_sums.p);
+      count_launch();
+    }
+    pomdp_gather_kernel<<<grid, 256, 0, h->stream>>>(HW, h->cap, h->d_slots.p, n, h->d_bel,
+                                                     h->d_rows.p);
+    count_launch();
+    PP2D_CUDA(cudaGetLastError());
+    PP2D_CUDA(cudaMemcpyAsync(beliefs_out, h->d_rows.p, (size_t)n * HW * sizeof(float),
+                              cudaMemcpyDeviceToHost, h->stream));
+    if (sums && normalize)
+      PP2D_CUDA(cudaMemcpyAsync(sums, h->d_sums.p, n * sizeof(float),
+                                cudaMemcpyDeviceToHost, h->stream));
+    PP2D_CUDA(cudaStreamSynchronize(h->stream));
+    return PP2D_OK;
+  }();
+  for (uint32_t i = 0; i < n; ++i) {
+    h->free_slots.push_back(in[i]);
+    h->free_slots.push_back(outs[i]);
+  }
+  return rc;
+}
+
+int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
+                        float* upper, uint8_t* upper_action, float* lower,
+                        uint8_t* lower_action) {
+  if (!h || !beliefs) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (!h->have_alphas) return fail(PP2D_ERR_STATE, "pp2d_pomdp_set_alphas not called");
+  if (n == 0) return PP2D_OK;
+  PP2D_TRY(pool_reserve(h, std::max<size_t>(h->cap, n)));
+  if (h->free_slots.size() < n)
+    return fail(PP2D_ERR_STATE, "belief pool too small for %u beliefs", n);
+  const int HW = h->HW;
+  std::vector<int> slots(n);
+  for (uint32_t i = 0; i < n; ++i) PP2D_TRY(alloc_slot(h, &slots[i]));
+  int rc = [&]() -> int {
+    PP2D_TRY(h->d_slots.ensure(n));
+    PP2D_TRY(h->d_rows.ensure((size_t)n * HW));
+    PP2D_TRY(h->d_vals.ensure((size_t)n * h->ncol));
+    PP2D_TRY(h->d_out.ensure((size_t)n * 11));
+    PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, beliefs, (size_t)n * HW * sizeof(float),
+                              cudaMemcpyHostToDevice, h->stream));
+    PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+                              cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((HW + 255) / 256, n);
+    pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(HW, h->cap, h->d_slots.p, n,
+                                                      h->d_rows.p, h->d_bel);
+    count_launch();
+    dim3 vgrid((n + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
+    pomdp_values_kernel<<<vgrid, 256, 0, h->stream>>>(HW, h->cap, h->ld, h->ncol,
+                                                      h->d_slots.p, n, h->d_bel,
+                                                      h->d_alpha, h->d_vals.p);
+    count_launch();
+    float2* res = reinterpret_cast<float2*>(h->d_out.p);
+    int2* idx = reinterpret_cast<int2*>(h->d_out.p + (size_t)n * 2);
+    pomdp_bounds_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(n, h->ncol, h->n_pbvi,
+                                                                h->d_vals.p, res, idx);
+    count_launch();
+    PP2D_CUDA(cudaGetLastError());
+    std::vector<float> hres((size_t)n * 2);
+    std::vector<int> hidx((size_t)n * 2);
+    PP2D_CUDA(cudaMemcpyAsync(hres.data(), res, hres.size() * sizeof(float),
+                              cudaMemcpyDeviceToHost, h->stream));
+    PP2D_CUDA(cudaMemcpyAsync(hidx.data(), idx, hidx.size() * sizeof(int),
+                              cudaMemcpyDeviceToHost, h->stream));
+    PP2D_CUDA(cudaStreamSynchronize(h->stream));
+    for (uint32_t i = 0; i < n; ++i) {
+      if (upper) upper[i] = hres[i * 2];
+      if (lower) lower[i] = hres[i * 2 + 1];
+      if (upper_action) upper_action[i] = h->fib_actions[hidx[i * 2]];
+      if (lower_action)
+        lower_action[i] = h->n_pbvi ? h->pbvi_actions[hidx[i * 2 + 1]] : 0;
+    }
+    return PP2D_OK;
+  }();
+  for (uint32_t i = 0; i < n; ++i) h->free_slots.push_back(slots[i]);
+  return rc;
+}
+
+int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
+                          uint32_t max_depth, uint32_t max_iter, uint8_t* actions,
+                          float* values, uint32_t* stats) {
+  if (!h || !beliefs || !actions) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (!h->have_alphas) return fail(PP2D_ERR_STATE, "pp2d_pomdp_set_alphas not called");
+  if (n == 0) return PP2D_OK;
+  if (max_iter > 255) max_iter = 255;           // uint8_t counter, pomdp:218-223
+  // Worst case per query: root + max_iter * 9 * 16 children.
+  const size_t per_query = 1 + (size_t)max_iter * kActions * 16;
+  size_t free_b = 0, total_b = 0;
+  PP2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = free_b / 2 + (size_t)h->cap * h->HW * sizeof(float);
+  const char* env = getenv("PP2D_POMDP_POOL_MB");
+  if (env && *env) budget = (size_t)atol(env) << 20;
+  size_t max_slots = budget / ((size_t)h->HW * sizeof(float));
+  if (max_slots < per_query)
+    return fail(PP2D_ERR_STATE, "belief pool budget too small for one query");
+  size_t group = std::min<size_t>(n, max_slots / per_query);
+  if ((size_t)h->cap < group * per_query) PP2D_TRY(pool_reserve(h, group * per_query));
+  group = std::min<size_t>(n, (size_t)h->cap / per_query);
+  for (size_t g0 = 0; g0 < n; g0 += group) {
+    const size_t gn = std::min<size_t>(group, n - g0);
+    std::vector<Tree> store(gn);
+    std::vector<Tree*> trees(gn);
+    for (size_t i = 0; i < gn; ++i) { store[i].rng.seed(1); trees[i] = &store[i]; }
+    PP2D_TRY(make_roots(h, trees, beliefs + g0 * (size_t)h->HW));
+    for (uint32_t it = 0; it < max_iter; ++it) {
+      std::vector<Tree*> active;
+      for (Tree* t : trees)
+        if (!t->dead && t->v[t->root].depth < max_depth) active.push_back(t);
+      if (active.empty()) break;
+      PP2D_TRY(expand_round(h, active));
+    }
+    for (size_t i = 0; i < gn; ++i) {
+      float r;
+      best_action(store[i], &actions[g0 + i], &r);
+      if (values) values[g0 + i] = r;
+      if (stats) {
+        stats[(g0 + i) * 4 + 0] = (uint32_t)store[i].v.size();
+        stats[(g0 + i) * 4 + 1] = (uint32_t)store[i].q.size();
+        stats[(g0 + i) * 4 + 2] = store[i].v[store[i].root].depth;
+        stats[(g0 + i) * 4 + 3] = store[i].expansions;
+      }
+      free_subtree_v(h, store[i], store[i].root);
+    }
+  }
+  return PP2D_OK;
+}
+
+/* ---- single-query tree: SearchTree of search_tree.h:130-165 ------------- */
+int pp2d_tree_create(pp2d_pomdp* h, const float* belief, pp2d_tree** out) {
+  if (!h || !belief || !out) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (!h->have_alphas) return fail(PP2D_ERR_STATE, "pp2d_pomdp_set_alphas not called");
+  *out = nullptr;
+  if (h->cap == 0) PP2D_TRY(pool_reserve(h, 4096));
+  pp2d_tree* t = new (std::nothrow) pp2d_tree;
+  if (!t) return fail(PP2D_ERR_INVALID, "out of host memory");
+  t->h = h;
+  t->t.rng.seed(1);
+  std::vector<Tree*> trees{&t->t};
+  int rc = make_roots(h, trees, belief);
+  if (rc != PP2D_OK) { delete t; return rc; }
+  *out = t;
+  return PP2D_OK;
+}
+
+void pp2d_tree_destroy(pp2d_tree* t) {
+  if (!t) return;
+  if (t->t.root >= 0) free_subtree_v(t->h, t->t, t->t.root);
+  delete t;
+}
+
+int pp2d_tree_expand(pp2d_tree* t) {
+  if (!t) return fail(PP2D_ERR_INVALID, "tree is NULL");
+  if (t->t.dead || t->t.v[t->t.root].to_expand < 0)
+    return fail(PP2D_ERR_STATE, "no V node to expand (the reference dereferences nullptr here)");
+  std::vector<Tree*> trees{&t->t};
+  return expand_round(t->h, trees);
+}
+
+uint32_t pp2d_tree_depth(const pp2d_tree* t) { return t ? t->t.v[t->t.root].depth : 0; }
+
+int pp2d_tree_best_action(const pp2d_tree* t, uint8_t* action, float* value) {
+  if (!t || !action) return fail(PP2D_ERR_INVALID, "NULL argument");
+  float r;
+  best_action(t->t, action, &r);
+  if (value) *value = r;
+  return PP2D_OK;
+}
+
+int pp2d_tree_root_bounds(const pp2d_tree* t, float* upper, float* lower) {
+  if (!t) return fail(PP2D_ERR_INVALID, "tree is NULL");
+  if (upper) *upper = t->t.v[t->t.root].upper;
+  if (lower) *lower = t->t.v[t->t.root].lower;
+  return PP2D_OK;
+}
+
+/* SearchTree::update(a, z), search_tree_cuda.cu:548-626 */
+int pp2d_tree_update(pp2d_tree* tt, uint8_t a, uint8_t z) {
+  if (!tt) return fail(PP2D_ERR_INVALID, "tree is NULL");
+  pp2d_pomdp* h = tt->h;
+  Tree& t = tt->t;
+  VNodeH& root = t.v[t.root];
+  if (root.children.empty())
+    return fail(PP2D_ERR_STATE, "update() on an unexpanded root (nullptr in the reference)");
+  int root_q = -1;
+  for (int c : root.children) {
+    if (t.q[c].action == a) root_q = c;
+    else free_subtree_q(h, t, c);
+  }
+  if (root_q < 0) return fail(PP2D_ERR_INVALID, "no Q node for action %u", a);
+  int root_v = -1;
+  for (int c : t.q[root_q].children) {
+    if (t.v[c].obs == z) root_v = c;
+    else free_subtree_v(h, t, c);
+  }
+  if (root_v >= 0) {
+    t.v[root_v].parent = -1;
+  } else {
+    // new root from one Bayes update of the old root belief (tree:586-614)
+    int slot = -1;
+    PP2D_TRY(alloc_slot(h, &slot));
+    BayesItem it{root.slot, slot, a, z};
+    PP2D_TRY(h->d_items.ensure(1));
+    PP2D_TRY(h->d_slots.ensure(1));
+    PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, &it, sizeof(it), cudaMemcpyHostToDevice, h->stream));
+    dim3 bgrid(1, (h->HW + 7) / 8);
+    pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+                                                     h->d_items.p, 1, h->d_bel, h->d_bel);
+    count_launch();
+    h->n_bayes++;
+    PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, &slot, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    pomdp_normalize_kernel<<<1, 128, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, 1, h->d_bel,
+                                                     nullptr);
+    count_launch();
+    PP2D_CUDA(cudaGetLastError());
+    std::vector<int> s1{slot};
+    float ev[11];
+    PP2D_TRY(evaluate_slots(h, s1, ev));
+    t.v.emplace_back();
+    root_v = (int)t.v.size() - 1;
+    init_vnode(t.v[root_v], slot, 0, 0.0f, -1, ev, root_v);
+    h->n_vnodes++;
+  }
+  // drop the old root and the chosen Q node (their beliefs only)
+  VNodeH& old_root = t.v[t.root];
+  if (old_root.slot >= 0) { h->free_slots.push_back(old_root.slot); old_root.slot = -1; }
+  old_root.children.clear();
+  t.q[root_q].children.clear();
+  t.root = root_v;
+  t.dead = false;
+  return PP2D_OK;
+}
+
+int pp2d_tree_plan(pp2d_tree* t, uint32_t max_depth, uint32_t max_iter,
+                   uint8_t* action, float* value) {
+  if (!t || !action) return fail(PP2D_ERR_INVALID, "NULL argument");
+  uint8_t counter = 0;                          // pomdp path_planning_2d.cu:218-223
+  while (pp2d_tree_depth(t) < max_depth && counter++ < max_iter) {
+    if (t->t.v[t->t.root].to_expand < 0) break;
+    PP2D_TRY(pp2d_tree_expand(t));
+  }
+  return pp2d_tree_best_action(t, action, value);
+}
+
+}  // extern "C"

@@ -1,0 +1,347 @@
+// pomdp_kernels.cuh -- sm_100a kernels of the QV-Tree half (SURVEY.md rows
+// B1-B7).  Reference files, relative to /root/reference/path_planning_2d/:
+//   model_gen = src/pomdp/model_generation_cuda.cu
+//   pbvi      = src/pomdp/point_based_value_iteration_cuda.cu
+//   fib       = src/pomdp/fast_informed_bound_cuda.cu
+//   tree      = src/pomdp/search_tree_cuda.cu
+//
+// Layout: every belief of a batch is a COLUMN of one matrix
+//   bel[s * cap + slot]      s = cell (y*W+x), slot = belief id, cap % 32 == 0
+// so that "one thread per belief, sequential over the cells" kernels are
+// coalesced.  That shape is what makes bit-exact parity possible: the
+// reference normalises, prefix-sums and takes inner products with sequential
+// single-accumulator float loops on the host (tree:226-229, 326-328,
+// fib:289-292, pbvi:689-694).  Here each of those loops is run by one thread
+// in the same order with the same roundings (separate multiply and add, IEEE
+// division, subnormals kept), and the parallelism comes from the thousands of
+// beliefs a batch of queries holds.  The device-side arithmetic of the
+// reference (--use_fast_math: FFMA contraction, flush-to-zero) is reproduced
+// with explicit .ftz PTX.
+#pragma once
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <stdint.h>
+
+namespace pp2d {
+
+__device__ __forceinline__ float fma_ftz(float a, float b, float c) {
+  float d;
+  asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float mul_ftz(float a, float b) {
+  float d;
+  asm("mul.rn.ftz.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float add_ftz(float a, float b) {
+  float d;
+  asm("add.rn.ftz.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+
+// ---------------------------------------------------------------- B1 -------
+// model_gen:161-347: per cell trans_prob[9][9] (blocked mass moved to "stay"
+// in ascending slot order, trapped override AFTER the naive copy),
+// meas_prob[16] and stage_reward[9] (-1 free / -2 occupied over the naive
+// probabilities; stay = -2, 0 at the goal).  Same table layout as the
+// reference so that save_data / the FIB and PBVI solvers can consume them.
+__global__ void pomdp_model_kernel(int H, int W, int gx, int gy,
+                                   const uint8_t* __restrict__ map,
+                                   float* __restrict__ trans_prob,
+                                   float* __restrict__ meas_prob,
+                                   float* __restrict__ stage_reward) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t idx = (size_t)y * W + x;
+  uint8_t m[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int nx = x + i % 3 - 1, ny = y + i / 3 - 1;
+    m[i] = (nx < 0 || nx >= W || ny < 0 || ny >= H) ? 1
+           : (map[(size_t)ny * W + nx] == 1 ? 1 : 0);
+  }
+  // naive probabilities of action u: 0.7 at slot u, 0.1 at the two side
+  // slots and at the centre (model_gen:175-211).
+  const int side[9][2] = {{1, 3}, {0, 2}, {1, 5}, {0, 6}, {4, 4},
+                          {2, 8}, {3, 7}, {6, 8}, {5, 7}};
+  for (int u = 0; u < 9; ++u) {
+    float tp[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tp[i] = 0.0f;
+    if (u == 4) {
+      tp[4] = 1.0f;
+    } else {
+      tp[u] = 0.7f; tp[side[u][0]] = 0.1f; tp[side[u][1]] = 0.1f; tp[4] = 0.1f;
+    }
+    // stage reward over the naive probabilities (model_gen:287-290): the
+    // reward is -1 / -2, so the product is exact and the chain is the
+    // reference's FFMA chain.
+    float r = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r = fma_ftz(m[i] ? -2.0f : -1.0f, tp[i], r);
+    if (u == 4) r = (x != gx || y != gy) ? -2.0f : 0.0f;
+    stage_reward[idx * 9 + u] = r;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      if (m[i] && i != 4) { tp[4] = add_ftz(tp[4], tp[i]); tp[i] = 0.0f; }
+    }
+    if (m[4]) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) tp[i] = 0.0f;
+      tp[4] = 1.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) trans_prob[idx * 81 + u * 9 + i] = tp[i];
+  }
+  // model_gen:235-263: 0.98 / 0.02 are double literals rounded to float.
+  const float hit = (float)0.98, miss = (float)0.02;
+  const uint8_t mm[4] = {m[1], m[3], m[5], m[7]};
+  for (int z = 0; z < 16; ++z) {
+    const float l0 = ((z >> 0) & 1) == mm[0] ? hit : miss;
+    const float l1 = ((z >> 1) & 1) == mm[1] ? hit : miss;
+    const float l2 = ((z >> 2) & 1) == mm[2] ? hit : miss;
+    const float l3 = ((z >> 3) & 1) == mm[3] ? hit : miss;
+    meas_prob[idx * 16 + z] = mul_ftz(mul_ftz(mul_ftz(l0, l1), l2), l3);
+  }
+}
+
+// ---------------------------------------------------------------- B2 -------
+// pbvi:88-133 cudaBayesBeliefUpdate, batched: child c is made from belief
+// column src[c] with action act[c] and observation obs[c] and written,
+// un-normalised, to column dst[c].  threadIdx.x runs over children so that
+// siblings (same source column) read the same addresses.
+struct BayesItem { int src, dst; uint8_t act, obs; };
+
+__global__ void __launch_bounds__(256)
+pomdp_bayes_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
+                   const float* __restrict__ meas_prob,
+                   const BayesItem* __restrict__ items, int n_items,
+                   const float* bel_in, float* bel_out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int cell = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (c >= n_items || cell >= H * W) return;
+  const BayesItem it = items[c];
+  const int x = cell % W, y = cell / W;
+  // Arithmetic of the reference kernel as nvcc 12.9 compiles it for sm_100a
+  // with --use_fast_math: FFMA.FTZ chain over slots 0..7, the last slot as a
+  // rounded FMUL.FTZ product added with FADD.FTZ, then FMUL.FTZ by L.
+  float p = 0.0f;
+#pragma unroll
+  for (int s = 0; s < 9; ++s) {
+    const int sx = x + s % 3 - 1, sy = y + s / 3 - 1;
+    if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
+    const size_t sidx = (size_t)sy * W + sx;
+    const float tp = __ldg(trans_prob + 81 * sidx + 9 * it.act + (8 - s));
+    const float b = bel_in[sidx * cap + it.src];
+    if (s < 8) p = fma_ftz(tp, b, p);
+    else p = add_ftz(p, mul_ftz(tp, b));
+  }
+  p = mul_ftz(p, __ldg(meas_prob + 16 * (size_t)cell + it.obs));
+  bel_out[(size_t)cell * cap + it.dst] = p;
+}
+
+// ---------------------------------------------------------------- B3 -------
+// tree:226-229: sum = accumulate(b, 0.0f) sequentially, then b /= sum (IEEE
+// division).  One thread per belief column.
+__global__ void __launch_bounds__(128)
+pomdp_normalize_kernel(int HW, int cap, const int* __restrict__ slots, int n,
+                       float* __restrict__ bel, float* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = slots[i];
+  float sum = 0.0f;
+  for (int s = 0; s < HW; ++s) sum = __fadd_rn(sum, bel[(size_t)s * cap + c]);
+  for (int s = 0; s < HW; ++s) {
+    const size_t q = (size_t)s * cap + c;
+    bel[q] = __fdiv_rn(bel[q], sum);
+  }
+  if (sums) sums[i] = sum;
+}
+
+// ---------------------------------------------------------------- B7 -------
+// tree:326-328: distribution = partial_sum(belief) (sequential float adds).
+// One thread per expanded V node; prefix[s * n + i].
+__global__ void __launch_bounds__(128)
+pomdp_prefix_kernel(int HW, int cap, const int* __restrict__ slots, int n,
+                    const float* __restrict__ bel, float* __restrict__ prefix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = slots[i];
+  float acc = 0.0f;
+  for (int s = 0; s < HW; ++s) {
+    acc = __fadd_rn(acc, bel[(size_t)s * cap + c]);
+    prefix[(size_t)s * n + i] = acc;
+  }
+}
+
+// The 2*n uniforms cudaForwardSampling consumes (tree:84-92, 117, 134):
+// XORWOW, curand_init(1234, idx, 0), two curand_uniform draws.  The reference
+// re-creates the states for every Q node, so these numbers never change.
+__global__ void pomdp_uniforms_kernel(int n, float* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  curandState st;
+  curand_init(1234, idx, 0, &st);
+  out[2 * idx] = curand_uniform(&st);
+  out[2 * idx + 1] = curand_uniform(&st);
+}
+
+// tree:331-337 (state sample by inverse CDF: first prefix >= draw; the prefix
+// is non-decreasing, so a binary search finds the same element) followed by
+// tree:94-147 cudaForwardSampling.  One thread per (expanded node i, action
+// a, sample k); draws[(i*9+a)*S + k] are the host rand() values already
+// divided by RAND_MAX+1.  A draw beyond the last prefix sum is clamped to the
+// last cell (the reference indexes one past the belief there).
+__global__ void __launch_bounds__(128)
+pomdp_sample_kernel(int H, int W, int n, int S,
+                    const float* __restrict__ trans_prob,
+                    const float* __restrict__ meas_prob,
+                    const float* __restrict__ prefix,
+                    const float* __restrict__ draws,
+                    const float* __restrict__ uniforms,
+                    uint8_t* __restrict__ observations) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 9 * S) return;
+  const int k = t % S, a = (t / S) % 9, i = t / (9 * S);
+  const int HW = H * W;
+  const float r = draws[t];
+  int lo = 0, hi = HW;                       // first s with prefix[s] >= r
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (prefix[(size_t)mid * n + i] >= r) hi = mid; else lo = mid + 1;
+  }
+  int s1 = lo < HW ? lo : HW - 1;
+  float cum = 0.0f;
+  const float r2 = uniforms[2 * k];
+  int s2 = 0;
+  bool found = false;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const float tp = trans_prob[(size_t)s1 * 81 + a * 9 + j];
+    cum = j == 0 ? tp : add_ftz(tp, cum);
+    if (!found && r2 <= cum) { s2 = j; found = true; }
+  }
+  long long nxt = (long long)s1 + (long long)(s2 / 3 - 1) * W + (s2 % 3 - 1);
+  if (nxt < 0) nxt = 0;
+  if (nxt >= HW) nxt = HW - 1;
+  const float r3 = uniforms[2 * k + 1];
+  int z = 0;
+  found = false;
+  cum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float mp = meas_prob[(size_t)nxt * 16 + j];
+    cum = j == 0 ? mp : add_ftz(mp, cum);
+    if (!found && r3 <= cum) { z = j; found = true; }
+  }
+  observations[t] = (uint8_t)z;
+}
+
+// ------------------------------------------------------------ B4 / B5 ------
+// Values of many beliefs against many alpha vectors:
+//   out[i][j] = sum_s bel[s][slots[i]] * alpha[s][j]     (j < ncol)
+// evaluated exactly like std::inner_product(b, b+HW, alpha, 0.0f) on the
+// reference's host (fib:289-292, pbvi:689-694, tree:172): one accumulator per
+// (i, j), cells in ascending order, float multiply rounded, then float add
+// rounded (no FMA).  alpha is [HW][ld] with the columns
+//   0..8 FIB, 9..17 stage reward, 18..18+N-1 PBVI.
+// CTA tile 64 beliefs x 64 columns, 256 threads, 4x4 accumulators each.
+constexpr int kEvM = 64, kEvN = 64, kEvK = 32;
+
+__global__ void __launch_bounds__(256)
+pomdp_values_kernel(int HW, int cap, int ld, int ncol,
+                    const int* __restrict__ slots, int n,
+                    const float* __restrict__ bel,
+                    const float* __restrict__ alpha, float* __restrict__ out) {
+  __shared__ float sb[kEvK][kEvM + 4];
+  __shared__ float sa[kEvK][kEvN + 4];
+  __shared__ int sslot[kEvM];
+  const int m0 = blockIdx.x * kEvM, n0 = blockIdx.y * kEvN;
+  const int tid = threadIdx.x;
+  if (tid < kEvM) sslot[tid] = (m0 + tid < n) ? slots[m0 + tid] : -1;
+  __syncthreads();
+  const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < HW; k0 += kEvK) {
+    for (int e = tid; e < kEvK * kEvM; e += 256) {
+      const int kk = e / kEvM, mm = e % kEvM;
+      const int s = k0 + kk, sl = sslot[mm];
+      sb[kk][mm] = (s < HW && sl >= 0) ? bel[(size_t)s * cap + sl] : 0.0f;
+    }
+    for (int e = tid; e < kEvK * kEvN; e += 256) {
+      const int kk = e / kEvN, nn = e % kEvN;
+      const int s = k0 + kk, j = n0 + nn;
+      sa[kk][nn] = (s < HW && j < ncol) ? alpha[(size_t)s * ld + j] : 0.0f;
+    }
+    __syncthreads();
+    const int kend = min(kEvK, HW - k0);
+    for (int kk = 0; kk < kend; ++kk) {
+      const float4 b = *reinterpret_cast<const float4*>(&sb[kk][tm]);
+      const float4 a = *reinterpret_cast<const float4*>(&sa[kk][tn]);
+      const float bv[4] = {b.x, b.y, b.z, b.w}, av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(bv[i], av[j]));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + tm + i;
+    if (m >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tn + j;
+      if (col < ncol) out[(size_t)m * ncol + col] = acc[i][j];
+    }
+  }
+}
+
+// Bounds of every evaluated belief from its row of values: first maximum over
+// the FIB columns (upper, fib:294-296) and over the PBVI columns (lower,
+// pbvi:696-698), as std::max_element does.  res[i] = {upper, lower},
+// idx[i] = {fib index, pbvi index}.
+__global__ void pomdp_bounds_kernel(int n, int ncol, int n_pbvi,
+                                    const float* __restrict__ vals,
+                                    float2* __restrict__ res,
+                                    int2* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* v = vals + (size_t)i * ncol;
+  int bu = 0;
+  for (int a = 1; a < 9; ++a) if (v[bu] < v[a]) bu = a;
+  int bl = 0;
+  for (int j = 1; j < n_pbvi; ++j) if (v[18 + bl] < v[18 + j]) bl = j;
+  res[i] = make_float2(v[bu], n_pbvi > 0 ? v[18 + bl] : 0.0f);
+  idx[i] = make_int2(bu, bl);
+}
+
+// Gather host-provided beliefs ([n][HW] row major) into belief columns.
+__global__ void pomdp_scatter_kernel(int HW, int cap, const int* __restrict__ slots,
+                                     int n, const float* __restrict__ rows,
+                                     float* __restrict__ bel) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (s >= HW || i >= n) return;
+  bel[(size_t)s * cap + slots[i]] = rows[(size_t)i * HW + s];
+}
+
+// Belief columns back to [n][HW] rows.
+__global__ void pomdp_gather_kernel(int HW, int cap, const int* __restrict__ slots,
+                                    int n, const float* __restrict__ bel,
+                                    float* __restrict__ rows) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (s >= HW || i >= n) return;
+  rows[(size_t)i * HW + s] = bel[(size_t)s * cap + slots[i]];
+}
+
+}  // namespace pp2d

@@ -101,9 +101,65 @@ def make_ref(outdir):
         print(name, grid.shape, "sweeps", n, "residuals", res)
 
 
+def make_pomdp(outdir):
+    """POMDP half: outputs of the reference kernels (oracle/_ref, GPU box)."""
+    import pomdp_oracle_py as po
+    os.makedirs(outdir, exist_ok=True)
+    R = po.ref()
+    un = np.zeros(100, np.float32)
+    R.ref_pomdp_uniforms(50, un.ctypes.data)
+    np.save(os.path.join(outdir, "curand_xorwow_1234.npy"), un)
+    print("uniforms", un[:4])
+    rng = np.random.default_rng(5)
+    for name, goal in [("map_3x3", (1, 1)), ("map_10x10", (8, 7)),
+                       ("sparse_map_100x40", (95, 34))]:
+        grid = cases.load_bundled(name)
+        h, w = grid.shape
+        hw = h * w
+        tp = np.zeros(hw * 81, np.float32); mp = np.zeros(hw * 16, np.float32)
+        sr = np.zeros(hw * 9, np.float32)
+        R.ref_pomdp_model(h, w, grid.ctypes.data, goal[0], goal[1], tp.ctypes.data,
+                          mp.ctypes.data, sr.ctypes.data)
+        # beliefs: uniform over free cells, and a product of tiny numbers that
+        # reaches the subnormal range (exercises flush-to-zero)
+        b0 = ((1 - grid.astype(np.float32)) / (1 - grid.astype(np.float32)).sum()).reshape(-1)
+        b1 = (rng.random(hw, dtype=np.float32) ** 24 * 1e-30).astype(np.float32)
+        b1[rng.integers(hw, size=hw // 4)] = 0
+        us = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 2, 7], np.uint8)
+        zs = np.array([0, 15, 3, 5, 9, 6, 10, 12, 1, 7, 14], np.uint8)
+        outs = {}
+        for tag, b in (("uniform", b0), ("tiny", b1)):
+            o = np.zeros((len(us), hw), np.float32)
+            R.ref_pomdp_bayes(h, w, grid.ctypes.data, goal[0], goal[1], b.ctypes.data,
+                              len(us), us.ctypes.data, zs.ctypes.data, o.ctypes.data)
+            outs["bayes_" + tag] = o
+        fib = np.zeros(hw * 9, np.float32)
+        n_fib = R.ref_pomdp_fib(h, w, grid.ctypes.data, goal[0], goal[1], cases.GAMMA,
+                                fib.ctypes.data, 20)
+        samples = rng.integers(hw, size=50).astype(np.uint32)
+        # only free cells are valid state samples
+        free = np.flatnonzero(grid.reshape(-1) == 0)
+        samples = free[rng.integers(len(free), size=50)].astype(np.uint32)
+        obs = np.zeros((9, 50), np.uint8)
+        for a in range(9):
+            R.ref_pomdp_forward_sampling(h, w, grid.ctypes.data, goal[0], goal[1], 50,
+                                         samples.ctypes.data, a, obs[a].ctypes.data)
+        data = dict(grid=grid, goal=np.array(goal), b_uniform=b0, b_tiny=b1, us=us,
+                    zs=zs, fib=fib.reshape(hw, 9), fib_sweeps=np.int32(n_fib),
+                    samples=samples, obs=obs, meas_prob=mp.reshape(hw, 16),
+                    stage_reward=sr.reshape(hw, 9), **outs)
+        if hw <= 4096:
+            data["trans_prob"] = tp.reshape(hw, 9, 9)
+        np.savez_compressed(os.path.join(outdir, f"pomdp_{name}.npz"), **data)
+        print(name, "fib sweeps", n_fib, "obs sample", obs[0][:8])
+
+
 if __name__ == "__main__":
     if len(sys.argv) >= 2 and sys.argv[1] == "maps":
         make_maps()
+    elif len(sys.argv) >= 2 and sys.argv[1] == "pomdp":
+        make_pomdp(sys.argv[2] if len(sys.argv) > 2 else
+                   os.path.join(ROOT, "gpurun_out", "golden_ref"))
     elif len(sys.argv) >= 2 and sys.argv[1] == "ref":
         make_ref(sys.argv[2] if len(sys.argv) > 2 else
                  os.path.join(ROOT, "gpurun_out", "golden_ref"))

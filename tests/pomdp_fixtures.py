@@ -1,0 +1,60 @@
+"""Inputs for the POMDP tests and bench: beliefs and alpha vectors.
+
+The alpha vectors the tree consumes come from the FIB and PBVI offline
+solvers in the reference ("next" rows of SURVEY.md section 8f).  Here FIB
+alphas are produced by the oracle's restatement of the FIB solver and the
+PBVI set is replaced by blind-policy value vectors (valid lower bounds) and
+convex mixtures of them; the tree code only needs *some* alpha set."""
+import os
+
+import numpy as np
+
+import cases
+import pomdp_oracle_py as po
+
+_cache = {}
+
+
+def alphas(name_or_grid, goal, gamma=cases.GAMMA, n_pbvi=24, fib_sweeps=0, seed=0):
+    key = (name_or_grid if isinstance(name_or_grid, str) else id(name_or_grid),
+           goal, gamma, n_pbvi, fib_sweeps)
+    if key in _cache:
+        return _cache[key]
+    grid = cases.load_bundled(name_or_grid) if isinstance(name_or_grid, str) else name_or_grid
+    m = po.Model(grid, goal)
+    fib, _ = m.fib(gamma, fib_sweeps)
+    blind = np.stack([m.blind(gamma, a, 120) for a in range(9)])
+    rng = np.random.default_rng(seed)
+    rows = [blind[a] for a in range(9)]
+    acts = list(range(9))
+    while len(rows) < n_pbvi:
+        w = rng.dirichlet(np.ones(9)).astype(np.float32)
+        rows.append((w[:, None] * blind).sum(0).astype(np.float32))
+        acts.append(int(np.argmax(w)))
+    pbvi = np.ascontiguousarray(np.stack(rows[:n_pbvi]), dtype=np.float32)
+    out = (m, np.ascontiguousarray(fib, np.float32), pbvi,
+           np.arange(9, dtype=np.uint8), np.array(acts[:n_pbvi], np.uint8))
+    _cache[key] = out
+    return out
+
+
+def gaussian_beliefs(grid, n, sigma=2.0, seed=0):
+    """isotropic Gaussian bump on a seeded free
+    cell, zeroed on occupied cells, normalised (float32)."""
+    h, w = grid.shape
+    rng = np.random.default_rng(seed)
+    free = np.argwhere(grid == 0)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    out = np.empty((n, h * w), np.float32)
+    for i in range(n):
+        cy, cx = free[rng.integers(len(free))]
+        b = np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / np.float32(2 * sigma * sigma))
+        b = (b * (grid == 0)).astype(np.float32)
+        out[i] = (b / b.sum(dtype=np.float32)).reshape(-1)
+    return out
+
+
+def uniforms():
+    """The 100 cuRAND numbers (tests/golden/curand_xorwow_1234.npy, produced on
+    a B200 by make_golden.py pomdp)."""
+    return np.load(os.path.join(cases.GOLDEN, "curand_xorwow_1234.npy"))

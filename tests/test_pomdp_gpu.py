@@ -1,0 +1,203 @@
+"""GPU tier, QV-tree half through the C ABI.
+
+Bar: bit-exact everywhere.  The device-side arithmetic of the reference
+(FFMA / flush-to-zero) and its host-side arithmetic (sequential float mul+add,
+IEEE division) are both reproduced exactly, so tables, beliefs, bounds, chosen
+actions and tree sizes must be identical to the oracle's."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import pomdp_fixtures as pf
+import pomdp_oracle_py as po
+from path_planning_2d_b200 import PomdpPathPlanning2d, SearchTree, _lib
+
+pytestmark = pytest.mark.gpu
+bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def same(a, b):
+    """Bit-equal, except that any NaN equals any NaN (0/0 has a different sign
+    and payload on x86 and on the GPU)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    return bool(np.all((bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))))
+
+
+@pytest.mark.parametrize("name,goal", [("map_3x3", (1, 1)), ("map_10x10", (8, 7)),
+                                       ("sparse_map_100x40", (95, 34))])
+def test_model_tables_bit_exact(name, goal):
+    grid = cases.load_bundled(name)
+    m = po.Model(grid, goal)
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        tp, mp, sr = p.model_tables()
+    hw = grid.size
+    assert np.array_equal(bits(tp), bits(m.tp.reshape(hw, 9, 9)))
+    assert np.array_equal(bits(mp), bits(m.mp.reshape(hw, 16)))
+    assert np.array_equal(bits(sr), bits(m.sr.reshape(hw, 9)))
+
+
+def test_goal_occupied_is_rejected():
+    grid = np.zeros((6, 6), np.uint8)
+    grid[2, 2] = 1
+    with pytest.raises(_lib.Pp2dError) as e:
+        PomdpPathPlanning2d(grid, (2, 2), cases.GAMMA)
+    assert e.value.code == _lib.PP2D_ERR_GOAL_OCCUPIED
+
+
+def test_sampling_uniforms_match_the_fixture():
+    grid = cases.load_bundled("map_3x3")
+    with PomdpPathPlanning2d(grid, (1, 1), cases.GAMMA) as p:
+        un = p.sampling_uniforms()
+    assert np.array_equal(bits(un), bits(pf.uniforms()))
+    assert np.all(un > 0) and np.all(un <= 1)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (9, 1), (7, 5), (40, 100), (33, 65)])
+def test_bayes_update_batch_bit_exact(shape):
+    h, w = shape
+    grid, goal = cases.synthetic_map(h, w, 0.25, seed=h * 131 + w)
+    m = po.Model(grid, goal)
+    rng = np.random.default_rng(1)
+    n = 37
+    beliefs = rng.random((n, h * w), dtype=np.float32)
+    beliefs[::3] = (beliefs[::3] ** 20 * 1e-32).astype(np.float32)   # subnormals
+    beliefs[1::5, ::2] = 0
+    acts = rng.integers(9, size=n).astype(np.uint8)
+    obs = rng.integers(16, size=n).astype(np.uint8)
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        out = p.bayes_update(beliefs, acts, obs)
+        outn, sums = p.bayes_update(beliefs, acts, obs, normalize=True)
+    for i in range(n):
+        want, _ = m.bayes(beliefs[i], int(acts[i]), int(obs[i]))
+        assert np.array_equal(bits(out[i]), bits(want)), i
+        wantn, s = m.bayes(beliefs[i], int(acts[i]), int(obs[i]), normalize=True)
+        assert bits(np.float32(sums[i])) == bits(np.float32(s)), i
+        assert same(outn[i], wantn), i
+
+
+def test_evaluate_bounds_bit_exact():
+    name, goal = "map_10x10", (8, 7)
+    grid = cases.load_bundled(name)
+    m, fib, pbvi, fa, pa = pf.alphas(name, goal, n_pbvi=70)
+    beliefs = np.concatenate([pf.gaussian_beliefs(grid, 90, seed=2),
+                              np.random.default_rng(3).random((45, grid.size), dtype=np.float32)])
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        p.set_alphas(fib, pbvi, fa, pa)
+        up, ua, lo, la = p.evaluate(beliefs)
+    for i, b in enumerate(beliefs):
+        wu, wua, wl, wla = po.evaluate(b, fib, pbvi, fa, pa)
+        assert bits(np.float32(up[i])) == bits(np.float32(wu)), i
+        assert bits(np.float32(lo[i])) == bits(np.float32(wl)), i
+        assert (ua[i], la[i]) == (wua, wla), i
+
+
+def _tree_pair(name, goal, n_pbvi, seed):
+    grid = cases.load_bundled(name)
+    m, fib, pbvi, fa, pa = pf.alphas(name, goal, n_pbvi=n_pbvi)
+    b = pf.gaussian_beliefs(grid, 1, seed=seed)[0]
+    p = PomdpPathPlanning2d(grid, goal, cases.GAMMA)
+    p.set_alphas(fib, pbvi, fa, pa)
+    ot = po.Tree(m, cases.GAMMA, fib, pbvi, pf.uniforms(), b, fa, pa)
+    return p, ot, b
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_search_tree_expand_step_by_step(seed):
+    p, ot, b = _tree_pair("map_10x10", (8, 7), 20, seed)
+    try:
+        st = SearchTree(p, b)
+        assert tuple(bits(np.float32(v)) for v in st.rootBounds()) == \
+            tuple(bits(np.float32(v)) for v in ot.root_bounds())
+        for step in range(6):
+            st.expand()
+            assert ot.expand() == 0
+            assert st.getDepth() == ot.depth
+            a, r = st.getOptimalAction()
+            oa, orr = ot.best()
+            assert a == oa and bits(np.float32(r)) == bits(np.float32(orr)), step
+            assert tuple(bits(np.float32(v)) for v in st.rootBounds()) == \
+                tuple(bits(np.float32(v)) for v in ot.root_bounds())
+        # re-root on the chosen action and an observation, three times
+        for z in (0, 5, 15):
+            a, _ = st.getOptimalAction()
+            st.update(a, z)
+            assert ot.update(a, z) == 0
+            assert st.getDepth() == ot.depth
+            assert tuple(bits(np.float32(v)) for v in st.rootBounds()) == \
+                tuple(bits(np.float32(v)) for v in ot.root_bounds())
+            st.expand()
+            ot.expand()
+            assert st.getOptimalAction()[0] == ot.best()[0]
+            assert bits(np.float32(st.getOptimalAction()[1])) == bits(np.float32(ot.best()[1]))
+        st.close()
+    finally:
+        ot.close()
+        p.close()
+
+
+def test_belief_callback_on_the_launch_file_map():
+    """BASELINE.json configs[0/1] for the POMDP planner: bundled sparse map,
+    goal (95,34), depth 50, 15 online iterations."""
+    p, ot, b = _tree_pair("sparse_map_100x40", (95, 34), 16, 7)
+    try:
+        a = p.beliefCallback(b)
+        oa, orr, stats, rc = ot.plan(50, 15)
+        assert rc == 0 and a == oa
+        assert p.search_tree.getDepth() == stats[4]
+        assert bits(np.float32(p.search_tree.getOptimalAction()[1])) == bits(np.float32(orr))
+    finally:
+        ot.close()
+        p.close()
+
+
+def test_plan_batch_equals_independent_oracle_plans():
+    name, goal = "map_10x10", (8, 7)
+    grid = cases.load_bundled(name)
+    m, fib, pbvi, fa, pa = pf.alphas(name, goal, n_pbvi=20)
+    beliefs = pf.gaussian_beliefs(grid, 24, seed=11)
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        p.set_alphas(fib, pbvi, fa, pa)
+        acts, vals, stats = p.plan_batch(beliefs, max_depth=50, max_iter=5, with_stats=True)
+    for i, b in enumerate(beliefs):
+        ot = po.Tree(m, cases.GAMMA, fib, pbvi, pf.uniforms(), b, fa, pa)
+        oa, orr, ostats, rc = ot.plan(50, 5)
+        ot.close()
+        assert acts[i] == oa, i
+        assert bits(np.float32(vals[i])) == bits(np.float32(orr)), i
+        assert stats[i, 0] == ostats[0] and stats[i, 1] == ostats[1], i
+        assert stats[i, 2] == ostats[4], i
+
+
+def test_reference_pomdp_kernels_vs_restatement():
+    """Live pin of oracle/pomdp_oracle.c against the reference kernels."""
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                      "oracle", "_ref", "libpp2d_ref_pomdp.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built")
+    R = po.ref()
+    grid, goal = cases.synthetic_map(23, 31, 0.3, seed=4)
+    h, w = grid.shape
+    hw = h * w
+    m = po.Model(grid, goal)
+    tp = np.zeros(hw * 81, np.float32); mp = np.zeros(hw * 16, np.float32)
+    sr = np.zeros(hw * 9, np.float32)
+    R.ref_pomdp_model(h, w, grid.ctypes.data, goal[0], goal[1], tp.ctypes.data,
+                      mp.ctypes.data, sr.ctypes.data)
+    assert np.array_equal(bits(tp), bits(m.tp)) and np.array_equal(bits(mp), bits(m.mp))
+    assert np.array_equal(bits(sr), bits(m.sr))
+    b = (np.random.default_rng(0).random(hw, dtype=np.float32) ** 18 * 1e-30).astype(np.float32)
+    us = np.arange(9, dtype=np.uint8); zs = (np.arange(9) * 7 % 16).astype(np.uint8)
+    out = np.zeros((9, hw), np.float32)
+    R.ref_pomdp_bayes(h, w, grid.ctypes.data, goal[0], goal[1], b.ctypes.data, 9,
+                      us.ctypes.data, zs.ctypes.data, out.ctypes.data)
+    for i in range(9):
+        want, _ = m.bayes(b, int(us[i]), int(zs[i]))
+        assert np.array_equal(bits(out[i]), bits(want)), i
+    fib = np.zeros(hw * 9, np.float32)
+    n = R.ref_pomdp_fib(h, w, grid.ctypes.data, goal[0], goal[1], cases.GAMMA,
+                        fib.ctypes.data, 30)
+    ofib, on = m.fib(cases.GAMMA, 30)
+    assert n == on and np.array_equal(bits(fib), bits(ofib.reshape(-1)))
