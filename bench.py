@@ -209,6 +209,58 @@ def reference_cuda_on_this_gpu(grid, goal, gamma):
         return {"error": str(e)}
 
 
+def qv_tree_section(rank, world, with_cpu):
+    """BASELINE.json configs[4]: batched QV-Tree Search, 1250 queries per GPU
+    (10 000 on 8 GPUs), sharded independently, no collective on the data path."""
+    import torch
+    import torch.distributed as dist
+    import cases
+    import pomdp_fixtures as pf
+    from path_planning_2d_b200 import PomdpPathPlanning2d
+    per_gpu = 1250
+    grid = cases.load_bundled("sparse_map_100x40")
+    goal = (95, 34)
+    fib, pbvi, fa, pa = pf.bundled_alphas(500)
+    beliefs = pf.gaussian_beliefs(grid, per_gpu * world, sigma=2.0, seed=0)
+    mine = beliefs[rank * per_gpu:(rank + 1) * per_gpu]
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        p.set_alphas(fib, pbvi, fa, pa)
+        p.plan_batch(mine[:64])
+        p.plan_batch(mine)                      # warm-up at full size
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        acts, vals, stats = p.plan_batch(mine, with_stats=True)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    out = {"plans_per_sec": per_gpu * world / dt, "queries": per_gpu * world,
+           "seconds": dt, "v_nodes_per_plan": float(stats[:, 0].mean()),
+           "config": "sparse_map_100x40, goal (95,34), Gaussian start beliefs "
+                     "(sigma 2 cells), 9 FIB + 500 lower-bound alpha vectors, depth cap "
+                     "50, 15 expansions, 50 samples per Q node; host beliefs in, "
+                     "actions out; queries sharded per GPU, no data-path collective",
+           "parity": "actions, bounds and tree sizes bit-identical to the oracle "
+                     "(tests/test_pomdp_gpu.py)"}
+    if with_cpu and rank == 0:
+        import pomdp_oracle_py as po
+        m = po.Model(grid, goal)
+        k = 6
+        t0 = time.perf_counter()
+        for i in range(k):
+            t = po.Tree(m, cases.GAMMA, fib, pbvi, pf.uniforms(), mine[i], fa, pa)
+            a, r, st, rc = t.plan(50, 15)
+            t.close()
+            assert a == acts[i], "oracle and GPU disagree on a plan"
+        out["cpu_baseline"] = {"value": k / (time.perf_counter() - t0), "unit": "plans/s",
+                               "cores": 1, "kind": "port",
+                               "sample": f"first {k} queries, oracle/pomdp_oracle.c, 1 thread"}
+    return out
+
+
 def run_main_arm(args):
     import torch
     import torch.distributed as dist
@@ -368,6 +420,10 @@ def run_main_arm(args):
             line["reference_cuda_same_gpu"] = ref_cuda
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_port_throughput(grid, goal, gamma)
+    qv = None if args.no_qv else qv_tree_section(rank, world, world == 1 and not args.no_cpu)
+    if rank == 0:
+        if qv:
+            line["qv_tree"] = qv
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -381,6 +437,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline")
+    ap.add_argument("--no-qv", action="store_true", help="skip the QV-tree section")
     ap.add_argument("--no-ref-cuda", action="store_true",
                     help="skip the reference-kernels-on-this-GPU line")
     args = ap.parse_args()

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <chrono>
 #include <vector>
 
 #include "pomdp_kernels.cuh"
@@ -189,9 +190,10 @@ struct pp2d_pomdp {
   DevBuf<BayesItem> d_items;
   DevBuf<float> d_prefix, d_draws, d_vals, d_rows, d_sums;
   DevBuf<uint8_t> d_obs;
-  DevBuf<float> d_out;               // 11 floats per evaluated belief
+  DevBuf<float> d_out;               // 12 floats per evaluated belief
   cudaStream_t stream = nullptr;
   uint64_t n_bayes = 0, n_vnodes = 0;
+  double t_phase[6] = {0, 0, 0, 0, 0, 0};   // PP2D_POMDP_PROFILE=1: seconds per phase
 };
 
 struct pp2d_tree {
@@ -202,6 +204,9 @@ struct pp2d_tree {
 namespace {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 int pool_reserve(pp2d_pomdp* h, size_t slots_wanted) {
   if ((size_t)h->cap >= slots_wanted && h->d_bel) return PP2D_OK;
@@ -226,15 +231,15 @@ int alloc_slot(pp2d_pomdp* h, int* out) {
   return PP2D_OK;
 }
 
-// Evaluate the beliefs in `slots`: per belief 11 floats
-// {upper, lower, reward[0..8]} into host `out` (B4, B5 and the reward dot of
-// search_tree_cuda.cu:168-173).
+// Evaluate the beliefs in `slots`: per belief 12 floats
+// {upper, lower, reward[0..8], packed indices} into host `out` (B4, B5 and the
+// reward dot of search_tree_cuda.cu:168-173).
 int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
   const int n = (int)slots.size();
   if (n == 0) return PP2D_OK;
   PP2D_TRY(h->d_slots.ensure(n));
   PP2D_TRY(h->d_vals.ensure((size_t)n * h->ncol));
-  PP2D_TRY(h->d_out.ensure((size_t)n * 11));
+  PP2D_TRY(h->d_out.ensure((size_t)n * 12));
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((n + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
@@ -243,27 +248,28 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
       h->d_vals.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
-  // bounds + rewards packed: reuse pomdp_bounds_kernel for the maxima, then
-  // copy the 9 reward columns with a strided memcpy.
-  float2* res = reinterpret_cast<float2*>(h->d_out.p);
-  int2* idx = reinterpret_cast<int2*>(h->d_out.p + (size_t)n * 2);
   pomdp_bounds_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
-      n, h->ncol, h->n_pbvi, h->d_vals.p, res, idx);
+      n, h->ncol, h->n_pbvi, h->d_vals.p, h->d_out.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
-  std::vector<float> hres((size_t)n * 2), hrew((size_t)n * 9);
-  PP2D_CUDA(cudaMemcpyAsync(hres.data(), res, (size_t)n * 2 * sizeof(float),
+  PP2D_CUDA(cudaMemcpyAsync(out, h->d_out.p, (size_t)n * 12 * sizeof(float),
                             cudaMemcpyDeviceToHost, h->stream));
-  PP2D_CUDA(cudaMemcpy2DAsync(hrew.data(), 9 * sizeof(float),
-                              h->d_vals.p + kColReward, h->ncol * sizeof(float),
-                              9 * sizeof(float), n, cudaMemcpyDeviceToHost,
-                              h->stream));
   PP2D_CUDA(cudaStreamSynchronize(h->stream));
-  for (int i = 0; i < n; ++i) {
-    out[i * 11 + 0] = hres[i * 2 + 0];
-    out[i * 11 + 1] = hres[i * 2 + 1];
-    memcpy(out + i * 11 + 2, hrew.data() + (size_t)i * 9, 9 * sizeof(float));
-  }
+  return PP2D_OK;
+}
+
+// tree:226-229 on the listed columns: sequential sum, then divide.
+int normalize_slots(pp2d_pomdp* h, int n, float* sums_out_dev) {
+  PP2D_TRY(h->d_sums.ensure(n));
+  pomdp_colsum_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+      h->HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_sums.p);
+  count_launch();
+  dim3 grid((n + 31) / 32, (h->HW + 7) / 8);
+  pomdp_scale_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n,
+                                                  h->d_sums.p, h->d_bel);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  (void)sums_out_dev;
   return PP2D_OK;
 }
 
@@ -294,13 +300,13 @@ int make_roots(pp2d_pomdp* h, std::vector<Tree*>& trees, const float* beliefs) {
                                                     h->d_rows.p, h->d_bel);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
-  std::vector<float> ev((size_t)n * 11);
+  std::vector<float> ev((size_t)n * 12);
   PP2D_TRY(evaluate_slots(h, slots, ev.data()));
   for (int i = 0; i < n; ++i) {
     Tree& t = *trees[i];
     t.v.emplace_back();
     t.root = (int)t.v.size() - 1;
-    init_vnode(t.v.back(), slots[i], 0, 0.0f, -1, ev.data() + (size_t)i * 11, t.root);
+    init_vnode(t.v.back(), slots[i], 0, 0.0f, -1, ev.data() + (size_t)i * 12, t.root);
     h->n_vnodes++;
   }
   return PP2D_OK;
@@ -335,6 +341,7 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
   const int n = (int)jobs.size();
   if (n == 0) return PP2D_OK;
   const int HW = h->HW;
+  double t0 = now_s();
   // --- forward sampling (search_tree_cuda.cu:311-366) ---
   std::vector<int> slots(n);
   std::vector<float> draws((size_t)n * kActions * kSamples);
@@ -364,7 +371,9 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
   std::vector<uint8_t> obs(draws.size());
   PP2D_CUDA(cudaMemcpyAsync(obs.data(), h->d_obs.p, obs.size(), cudaMemcpyDeviceToHost,
                             h->stream));
+  h->t_phase[0] += now_s() - t0; t0 = now_s();   // host draws + upload (async)
   PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  h->t_phase[1] += now_s() - t0; t0 = now_s();   // prefix + sampling on device
   // --- unique observations per Q node (search_tree_cuda.cu:181-195) ---
   std::vector<BayesItem> items;
   struct Child { int job; uint8_t a, z; float w; int slot; };
@@ -383,6 +392,7 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
       }
     }
   const int nk = (int)kids.size();
+  h->t_phase[2] += now_s() - t0; t0 = now_s();   // host: children lists
   // --- children beliefs: Bayes update + normalise (search_tree_cuda.cu:213-229)
   PP2D_TRY(h->d_items.ensure(nk));
   PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), nk * sizeof(BayesItem),
@@ -398,13 +408,11 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
   PP2D_TRY(h->d_slots.ensure(nk));
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, kslots.data(), nk * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
-  pomdp_normalize_kernel<<<(nk + 127) / 128, 128, 0, h->stream>>>(
-      HW, h->cap, h->d_slots.p, nk, h->d_bel, nullptr);
-  count_launch();
-  PP2D_CUDA(cudaGetLastError());
+  PP2D_TRY(normalize_slots(h, nk, nullptr));
   // --- bounds of the new V nodes (search_tree_cuda.cu:376-385) ---
-  std::vector<float> ev((size_t)nk * 11);
+  std::vector<float> ev((size_t)nk * 12);
   PP2D_TRY(evaluate_slots(h, kslots, ev.data()));
+  h->t_phase[3] += now_s() - t0; t0 = now_s();   // bayes + normalise + bounds (device, synced)
   // --- host bookkeeping ---
   int kpos = 0;
   for (int i = 0; i < n; ++i) {
@@ -422,7 +430,7 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
         t.v.emplace_back();
         const int ci = (int)t.v.size() - 1;
         init_vnode(t.v[ci], kids[kpos].slot, kids[kpos].z, kids[kpos].w, qi,
-                   ev.data() + (size_t)kpos * 11, ci);
+                   ev.data() + (size_t)kpos * 12, ci);
         t.q[qi].children.push_back(ci);
         h->n_vnodes++;
         ++kpos;
@@ -440,6 +448,7 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
     }
     t.expansions++;
   }
+  h->t_phase[4] += now_s() - t0;                 // host: tree bookkeeping
   return PP2D_OK;
 }
 
@@ -603,11 +612,7 @@ int pp2d_pomdp_bayes_update(pp2d_pomdp* h, const float* beliefs_in, uint32_t n,
     h->n_bayes += n;
     PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, outs.data(), n * sizeof(int),
                               cudaMemcpyHostToDevice, h->stream));
-    if (normalize) {
-      pomdp_normalize_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
-          HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_sums.p);
-      count_launch();
-    }
+    if (normalize) PP2D_TRY(normalize_slots(h, (int)n, nullptr));
     pomdp_gather_kernel<<<grid, 256, 0, h->stream>>>(HW, h->cap, h->d_slots.p, n, h->d_bel,
                                                      h->d_rows.p);
     count_launch();
@@ -643,7 +648,7 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     PP2D_TRY(h->d_slots.ensure(n));
     PP2D_TRY(h->d_rows.ensure((size_t)n * HW));
     PP2D_TRY(h->d_vals.ensure((size_t)n * h->ncol));
-    PP2D_TRY(h->d_out.ensure((size_t)n * 11));
+    PP2D_TRY(h->d_out.ensure((size_t)n * 12));
     PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, beliefs, (size_t)n * HW * sizeof(float),
                               cudaMemcpyHostToDevice, h->stream));
     PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
@@ -657,25 +662,21 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
                                                       h->d_slots.p, n, h->d_bel,
                                                       h->d_alpha, h->d_vals.p);
     count_launch();
-    float2* res = reinterpret_cast<float2*>(h->d_out.p);
-    int2* idx = reinterpret_cast<int2*>(h->d_out.p + (size_t)n * 2);
     pomdp_bounds_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(n, h->ncol, h->n_pbvi,
-                                                                h->d_vals.p, res, idx);
+                                                                h->d_vals.p, h->d_out.p);
     count_launch();
     PP2D_CUDA(cudaGetLastError());
-    std::vector<float> hres((size_t)n * 2);
-    std::vector<int> hidx((size_t)n * 2);
-    PP2D_CUDA(cudaMemcpyAsync(hres.data(), res, hres.size() * sizeof(float),
-                              cudaMemcpyDeviceToHost, h->stream));
-    PP2D_CUDA(cudaMemcpyAsync(hidx.data(), idx, hidx.size() * sizeof(int),
+    std::vector<float> hres((size_t)n * 12);
+    PP2D_CUDA(cudaMemcpyAsync(hres.data(), h->d_out.p, hres.size() * sizeof(float),
                               cudaMemcpyDeviceToHost, h->stream));
     PP2D_CUDA(cudaStreamSynchronize(h->stream));
     for (uint32_t i = 0; i < n; ++i) {
-      if (upper) upper[i] = hres[i * 2];
-      if (lower) lower[i] = hres[i * 2 + 1];
-      if (upper_action) upper_action[i] = h->fib_actions[hidx[i * 2]];
-      if (lower_action)
-        lower_action[i] = h->n_pbvi ? h->pbvi_actions[hidx[i * 2 + 1]] : 0;
+      int packed;
+      memcpy(&packed, &hres[(size_t)i * 12 + 11], sizeof(int));
+      if (upper) upper[i] = hres[(size_t)i * 12];
+      if (lower) lower[i] = hres[(size_t)i * 12 + 1];
+      if (upper_action) upper_action[i] = h->fib_actions[packed & 0xff];
+      if (lower_action) lower_action[i] = h->n_pbvi ? h->pbvi_actions[packed >> 8] : 0;
     }
     return PP2D_OK;
   }();
@@ -728,6 +729,12 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
       }
       free_subtree_v(h, store[i], store[i].root);
     }
+  }
+  if (getenv("PP2D_POMDP_PROFILE")) {
+    fprintf(stderr, "pp2d pomdp phases [s]: draws %.4f  sample(dev) %.4f  kids %.4f  "
+            "bayes+norm+bounds(dev) %.4f  bookkeeping %.4f\n", h->t_phase[0], h->t_phase[1],
+            h->t_phase[2], h->t_phase[3], h->t_phase[4]);
+    for (double& t : h->t_phase) t = 0;
   }
   return PP2D_OK;
 }
@@ -815,12 +822,9 @@ int pp2d_tree_update(pp2d_tree* tt, uint8_t a, uint8_t z) {
     count_launch();
     h->n_bayes++;
     PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, &slot, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    pomdp_normalize_kernel<<<1, 128, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, 1, h->d_bel,
-                                                     nullptr);
-    count_launch();
-    PP2D_CUDA(cudaGetLastError());
+    PP2D_TRY(normalize_slots(h, 1, nullptr));
     std::vector<int> s1{slot};
-    float ev[11];
+    float ev[12];
     PP2D_TRY(evaluate_slots(h, s1, ev));
     t.v.emplace_back();
     root_v = (int)t.v.size() - 1;

@@ -145,19 +145,36 @@ pomdp_bayes_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
 // ---------------------------------------------------------------- B3 -------
 // tree:226-229: sum = accumulate(b, 0.0f) sequentially, then b /= sum (IEEE
 // division).  One thread per belief column.
+// The sum is a serial chain of float adds by construction; the loads are
+// issued 16 at a time so that memory latency overlaps.
 __global__ void __launch_bounds__(128)
-pomdp_normalize_kernel(int HW, int cap, const int* __restrict__ slots, int n,
-                       float* __restrict__ bel, float* __restrict__ sums) {
+pomdp_colsum_kernel(int HW, int cap, const int* __restrict__ slots, int n,
+                    const float* __restrict__ bel, float* __restrict__ sums) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int c = slots[i];
+  const float* col = bel + slots[i];
   float sum = 0.0f;
-  for (int s = 0; s < HW; ++s) sum = __fadd_rn(sum, bel[(size_t)s * cap + c]);
-  for (int s = 0; s < HW; ++s) {
-    const size_t q = (size_t)s * cap + c;
-    bel[q] = __fdiv_rn(bel[q], sum);
+  int s = 0;
+  for (; s + 16 <= HW; s += 16) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = col[(size_t)(s + j) * cap];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sum = __fadd_rn(sum, v[j]);
   }
-  if (sums) sums[i] = sum;
+  for (; s < HW; ++s) sum = __fadd_rn(sum, col[(size_t)s * cap]);
+  sums[i] = sum;
+}
+
+// b /= sum for every cell of every listed column (tree:228-229), IEEE division.
+__global__ void __launch_bounds__(256)
+pomdp_scale_kernel(int HW, int cap, const int* __restrict__ slots, int n,
+                   const float* __restrict__ sums, float* __restrict__ bel) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int s = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (i >= n || s >= HW) return;
+  const size_t q = (size_t)s * cap + slots[i];
+  bel[q] = __fdiv_rn(bel[q], sums[i]);
 }
 
 // ---------------------------------------------------------------- B7 -------
@@ -168,10 +185,21 @@ pomdp_prefix_kernel(int HW, int cap, const int* __restrict__ slots, int n,
                     const float* __restrict__ bel, float* __restrict__ prefix) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int c = slots[i];
+  const float* col = bel + slots[i];
   float acc = 0.0f;
-  for (int s = 0; s < HW; ++s) {
-    acc = __fadd_rn(acc, bel[(size_t)s * cap + c]);
+  int s = 0;
+  for (; s + 16 <= HW; s += 16) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = col[(size_t)(s + j) * cap];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      acc = __fadd_rn(acc, v[j]);
+      prefix[(size_t)(s + j) * n + i] = acc;
+    }
+  }
+  for (; s < HW; ++s) {
+    acc = __fadd_rn(acc, col[(size_t)s * cap]);
     prefix[(size_t)s * n + i] = acc;
   }
 }
@@ -307,12 +335,12 @@ pomdp_values_kernel(int HW, int cap, int ld, int ncol,
 
 // Bounds of every evaluated belief from its row of values: first maximum over
 // the FIB columns (upper, fib:294-296) and over the PBVI columns (lower,
-// pbvi:696-698), as std::max_element does.  res[i] = {upper, lower},
-// idx[i] = {fib index, pbvi index}.
+// pbvi:696-698), as std::max_element does.  Packed per belief:
+//   out[i*12 + 0] upper, [1] lower, [2..10] <b, R(:,a)>, [11] = fib index |
+//   pbvi index << 8 (as int bits).
 __global__ void pomdp_bounds_kernel(int n, int ncol, int n_pbvi,
                                     const float* __restrict__ vals,
-                                    float2* __restrict__ res,
-                                    int2* __restrict__ idx) {
+                                    float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* v = vals + (size_t)i * ncol;
@@ -320,8 +348,12 @@ __global__ void pomdp_bounds_kernel(int n, int ncol, int n_pbvi,
   for (int a = 1; a < 9; ++a) if (v[bu] < v[a]) bu = a;
   int bl = 0;
   for (int j = 1; j < n_pbvi; ++j) if (v[18 + bl] < v[18 + j]) bl = j;
-  res[i] = make_float2(v[bu], n_pbvi > 0 ? v[18 + bl] : 0.0f);
-  idx[i] = make_int2(bu, bl);
+  float* o = out + (size_t)i * 12;
+  o[0] = v[bu];
+  o[1] = n_pbvi > 0 ? v[18 + bl] : 0.0f;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) o[2 + a] = v[9 + a];
+  o[11] = __int_as_float(bu | (bl << 8));
 }
 
 // Gather host-provided beliefs ([n][HW] row major) into belief columns.

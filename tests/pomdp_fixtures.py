@@ -58,3 +58,19 @@ def uniforms():
     """The 100 cuRAND numbers (tests/golden/curand_xorwow_1234.npy, produced on
     a B200 by make_golden.py pomdp)."""
     return np.load(os.path.join(cases.GOLDEN, "curand_xorwow_1234.npy"))
+
+
+def bundled_alphas(n_pbvi=500, seed=0):
+    """Config 5 inputs: sparse_map_100x40, goal (95,34):
+    9 FIB alpha vectors (oracle FIB solver run to its stopping rule, committed
+    as tests/golden/alphas_sparse_map_100x40.npz) and n_pbvi lower-bound
+    vectors = the 9 blind-policy values plus seeded convex mixtures of them
+    (stand-in for the PBVI set, which is a "next" row)."""
+    g = np.load(os.path.join(cases.GOLDEN, "alphas_sparse_map_100x40.npz"))
+    fib, blind = g["fib"], g["blind"]
+    rng = np.random.default_rng(seed)
+    w = rng.dirichlet(np.ones(9), size=max(n_pbvi - 9, 0)).astype(np.float32)
+    pbvi = np.concatenate([blind, w @ blind]).astype(np.float32)[:n_pbvi]
+    acts = np.concatenate([np.arange(9), w.argmax(1)]).astype(np.uint8)[:n_pbvi]
+    return (np.ascontiguousarray(fib), np.ascontiguousarray(pbvi),
+            np.arange(9, dtype=np.uint8), acts)
