@@ -184,7 +184,7 @@ def run_reference_arm(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args.emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------
@@ -424,10 +424,31 @@ def run_main_arm(args):
     if rank == 0:
         if qv:
             line["qv_tree"] = qv
-        print(json.dumps(line))
+        args.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+class StdoutGuard:
+    """Only the final JSON line may reach stdout: anything libraries print to
+    fd 1 meanwhile (NCCL's version banner, the reference's printf) goes to
+    stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -441,10 +462,12 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true",
                     help="skip the reference-kernels-on-this-GPU line")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_main_arm(args)
+    with StdoutGuard() as out:
+        args.emit = out.emit
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_main_arm(args)
 
 
 if __name__ == "__main__":

@@ -184,6 +184,24 @@ typedef struct pp2d_halo {
 } pp2d_halo;
 int pp2d_mdp_halo(pp2d_mdp* h, pp2d_halo* out);
 
+/*
+ * Peer-to-peer ghost rows over NVLink (same node, one process per GPU).
+ * Each rank exports a descriptor (CUDA IPC handles of its two J planes and
+ * its flag block), the ranks swap descriptors (any transport; distributed.py
+ * uses all_gather_object) and connect to their upper / lower neighbour (NULL
+ * where there is none) before the first sweep.  From then on every fused
+ * 2-sweep launch (pp2d_mdp_sweeps_ex(h, 2, 0)) writes its first / last two
+ * rows straight into the neighbours' ghost rows and synchronises with them
+ * through flags in device memory: no exchange call, no collective.  Single
+ * sweeps and arg-min sweeps still need the pp2d_mdp_halo exchange, preceded by
+ * a stream-ordered cross-rank barrier (any NCCL collective).
+ */
+#define PP2D_IPC_DESC_BYTES 256
+int pp2d_mdp_ipc_export(pp2d_mdp* h, void* desc /* PP2D_IPC_DESC_BYTES */);
+int pp2d_mdp_ipc_connect(pp2d_mdp* h, const void* up_desc, const void* down_desc);
+/* timed_out != 0: a flag wait gave up (neighbour missing); results invalid. */
+int pp2d_mdp_p2p_status(pp2d_mdp* h, int* timed_out);
+
 /* Device-side residual for shards: enqueue the reduction, then read it. */
 int pp2d_mdp_residual_device(pp2d_mdp* h, void** dev_float_out);
 

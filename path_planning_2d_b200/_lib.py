@@ -14,6 +14,7 @@ PP2D_ERR_INVALID = -1
 PP2D_ERR_GOAL_OCCUPIED = -2
 PP2D_ERR_CUDA = -3
 PP2D_ERR_STATE = -4
+IPC_DESC_BYTES = 256
 
 _vp = ctypes.c_void_p
 _u32 = ctypes.c_uint32
@@ -50,6 +51,9 @@ SIGNATURES = {
                                 ctypes.POINTER(_u32)]),
     "pp2d_mdp_sweep_count": (_u32, [_vp]),
     "pp2d_mdp_halo": (_i, [_vp, ctypes.POINTER(Halo)]),
+    "pp2d_mdp_ipc_export": (_i, [_vp, _vp]),
+    "pp2d_mdp_ipc_connect": (_i, [_vp, _vp, _vp]),
+    "pp2d_mdp_p2p_status": (_i, [_vp, ctypes.POINTER(_i)]),
     "pp2d_pomdp_create": (_i, [_u32, _u32, _vp, _u32, _u32, ctypes.c_float,
                                ctypes.POINTER(_vp)]),
     "pp2d_pomdp_destroy": (None, [_vp]),

@@ -10,6 +10,7 @@
 // point fails with PP2D_ERR_CUDA.
 #include "../../include/pp2d.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -130,6 +131,17 @@ struct pp2d_mdp {
   cudaStream_t stream = nullptr;
   bool async = false;
   int sm_count = 148;
+  // peer-to-peer ghost rows (pp2d_mdp_ipc_connect)
+  unsigned int* flags = nullptr;   // kFlagWords, IPC-shared
+  bool p2p = false;
+  float* up_j[2] = {nullptr, nullptr};     // mapped neighbour planes
+  float* down_j[2] = {nullptr, nullptr};
+  unsigned int* up_flags = nullptr;
+  unsigned int* down_flags = nullptr;
+  uint32_t up_H = 0;
+  void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned int p2p_iter = 0, p2p_expect_top = 0, p2p_expect_bot = 0;
+  int p2p_debug = 0, p2p_edge_rows = 16;
   // tuning knobs (environment overridable, see mdp_config)
   int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6, waves = 1;
 };
@@ -144,10 +156,11 @@ static float trapped_cost(pp2d_mdp* h, uint32_t n) {
   return h->trapped[n];
 }
 
-template <int T, int CW, bool POLICY>
+template <int T, int CW, bool POLICY, bool P2P = false>
 static int launch_sweep(pp2d_mdp* h) {
   using G = StripGeom<T, CW>;
   SweepParams p;
+  memset(&p, 0, sizeof(p));
   p.jin = h->j[h->cur];
   p.jout = h->j[h->cur ^ 1];
   p.code = h->code;
@@ -171,7 +184,7 @@ static int launch_sweep(pp2d_mdp* h) {
     // more CTA than that would run alone in an extra wave.
     int ctas_per_sm = 0;
     PP2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY>, 256, 0));
+        &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY, P2P>, 256, 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     const long slots = (long)h->sm_count * ctas_per_sm * 8;   // resident warps
     long rb = slots * h->waves / p.n_strips;                  // floor
@@ -186,9 +199,37 @@ static int launch_sweep(pp2d_mdp* h) {
   p.gamma = h->gamma * 1.0f;
   p.ga = h->gamma * 0.7f;
   p.gb = h->gamma * 0.1f;
+  if (P2P) {
+    // Boundary units of this launch: those whose rows touch the first / last
+    // two owned rows (they wait for and signal the neighbours).
+    int top_blocks = 0, bot_blocks = 0;
+    for (int rb = 0; rb < n_rb; ++rb) {
+      const int y0 = rb * rpu, y1 = std::min(y0 + rpu, (int)h->H);
+      if (y0 < kPadRows) ++top_blocks;
+      if (y1 > (int)h->H - kPadRows) ++bot_blocks;
+    }
+    h->p2p_iter += 1;
+    const int nxt = h->cur ^ 1;
+    if (h->up_j[nxt]) {
+      h->p2p_expect_top += (unsigned int)(top_blocks * p.n_strips);
+      p.peer_up_out = h->up_j[nxt] + (size_t)(h->up_H + kPadRows) * h->pitch;
+      p.up_flag_remote = h->up_flags + kFlagFromDown;
+    }
+    if (h->down_j[nxt]) {
+      h->p2p_expect_bot += (unsigned int)(bot_blocks * p.n_strips);
+      p.peer_down_out = h->down_j[nxt];
+      p.down_flag_remote = h->down_flags + kFlagFromUp;
+    }
+    p.flags = h->flags;
+    p.iter = h->p2p_iter;
+    p.expect_top = h->p2p_expect_top;
+    p.expect_bot = h->p2p_expect_bot;
+    p.p2p_debug = (unsigned int)h->p2p_debug;
+    p.edge_rows = h->p2p_edge_rows;
+  }
   const int warps_per_cta = 8;
   const int grid = (p.n_units + warps_per_cta - 1) / warps_per_cta;
-  mdp_sweep_kernel<T, CW, POLICY><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+  mdp_sweep_kernel<T, CW, POLICY, P2P><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   PP2D_CUDA(cudaGetLastError());
   h->cur ^= 1;
@@ -198,6 +239,9 @@ static int launch_sweep(pp2d_mdp* h) {
 
 template <int T, bool POLICY>
 static int launch_sweep_cw(pp2d_mdp* h, int cw) {
+  if (T == 2 && !POLICY && h->p2p)
+    return cw == 4 ? launch_sweep<2, 4, false, true>(h)
+                   : launch_sweep<2, 2, false, true>(h);
   switch (cw) {
     case 1: return launch_sweep<T, 1, POLICY>(h);
     case 2: return launch_sweep<T, 2, POLICY>(h);
@@ -295,6 +339,9 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->rows_per_unit = env_int("PP2D_MDP_ROWS_PER_UNIT", 0);
   h->prefetch_rows = env_int("PP2D_MDP_PREFETCH_ROWS", 6);
   h->waves = env_int("PP2D_MDP_WAVES", 1);
+  h->p2p_debug = env_int("PP2D_P2P_DEBUG", 0);
+  h->p2p_edge_rows = env_int("PP2D_P2P_EDGE_ROWS", 16);
+  if (h->p2p_edge_rows < kPadRows) h->p2p_edge_rows = kPadRows;
   if (h->waves < 1) h->waves = 1;
   if (h->prefetch_rows < kPrefetch) h->prefetch_rows = kPrefetch;
   if (h->prefetch_rows > kSlackRows) h->prefetch_rows = kSlackRows;
@@ -311,6 +358,8 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
     PP2D_CUDA(cudaMalloc(&h->occ, (size_t)occ_rows * width));
     PP2D_CUDA(cudaMalloc(&h->lut, kLutFloat4 * sizeof(float4)));
     PP2D_CUDA(cudaMalloc(&h->resid, sizeof(uint32_t)));
+    PP2D_CUDA(cudaMalloc(&h->flags, kFlagWords * sizeof(unsigned int)));
+    PP2D_CUDA(cudaMemset(h->flags, 0, kFlagWords * sizeof(unsigned int)));
     PP2D_CUDA(cudaMallocHost(&h->resid_host, sizeof(uint32_t)));
     std::vector<float4> lut;
     build_lut(gamma, lut);
@@ -366,6 +415,8 @@ void pp2d_mdp_destroy(pp2d_mdp* h) {
   cudaFree(h->j[0]); cudaFree(h->j[1]); cudaFree(h->jchk); cudaFree(h->code);
   cudaFree(h->action); cudaFree(h->occ); cudaFree(h->dense); cudaFree(h->lut);
   cudaFree(h->resid);
+  for (void* q : h->ipc_opened) if (q) cudaIpcCloseMemHandle(q);
+  cudaFree(h->flags);
   if (h->resid_host) cudaFreeHost(h->resid_host);
   delete h;
 }
@@ -551,6 +602,74 @@ int pp2d_mdp_waypoints(pp2d_mdp* h, uint32_t sx, uint32_t sy, uint32_t* cells,
     y += (int)(u / 3) - 1;
   }
   *n_out = n;
+  return PP2D_OK;
+}
+
+namespace {
+struct IpcDesc {
+  cudaIpcMemHandle_t j[2];
+  cudaIpcMemHandle_t flags;
+  uint32_t H, pitch, W, magic;
+};
+static_assert(sizeof(IpcDesc) <= PP2D_IPC_DESC_BYTES, "IPC descriptor too large");
+}  // namespace
+
+int pp2d_mdp_ipc_export(pp2d_mdp* h, void* desc) {
+  if (!h || !desc) return fail(PP2D_ERR_INVALID, "NULL argument");
+  IpcDesc d;
+  memset(&d, 0, sizeof(d));
+  PP2D_CUDA(cudaIpcGetMemHandle(&d.j[0], h->j[0]));
+  PP2D_CUDA(cudaIpcGetMemHandle(&d.j[1], h->j[1]));
+  PP2D_CUDA(cudaIpcGetMemHandle(&d.flags, h->flags));
+  d.H = h->H; d.pitch = (uint32_t)h->pitch; d.W = h->W; d.magic = 0x70703264u;
+  memset(desc, 0, PP2D_IPC_DESC_BYTES);
+  memcpy(desc, &d, sizeof(d));
+  return PP2D_OK;
+}
+
+int pp2d_mdp_ipc_connect(pp2d_mdp* h, const void* up_desc, const void* down_desc) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (!h->sharded) return fail(PP2D_ERR_STATE, "peer-to-peer needs a shard handle");
+  if (h->p2p) return fail(PP2D_ERR_STATE, "already connected");
+  if (h->n_sweeps != 0) return fail(PP2D_ERR_STATE, "connect before the first sweep");
+  int slot = 0;
+  auto open = [&](const void* src, float** j, unsigned int** flags, uint32_t* H) -> int {
+    IpcDesc d;
+    memcpy(&d, src, sizeof(d));
+    if (d.magic != 0x70703264u || d.pitch != (uint32_t)h->pitch || d.W != h->W)
+      return fail(PP2D_ERR_INVALID, "neighbour descriptor does not match this shard");
+    for (int b = 0; b < 2; ++b) {
+      void* q = nullptr;
+      PP2D_CUDA(cudaIpcOpenMemHandle(&q, d.j[b], cudaIpcMemLazyEnablePeerAccess));
+      h->ipc_opened[slot++] = q;
+      j[b] = static_cast<float*>(q);
+    }
+    void* q = nullptr;
+    PP2D_CUDA(cudaIpcOpenMemHandle(&q, d.flags, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened[slot++] = q;
+    *flags = static_cast<unsigned int*>(q);
+    if (H) *H = d.H;
+    return PP2D_OK;
+  };
+  if (up_desc) {
+    int rc = open(up_desc, h->up_j, &h->up_flags, &h->up_H);
+    if (rc != PP2D_OK) return rc;
+  }
+  if (down_desc) {
+    int rc = open(down_desc, h->down_j, &h->down_flags, nullptr);
+    if (rc != PP2D_OK) return rc;
+  }
+  h->p2p = (up_desc != nullptr) || (down_desc != nullptr);
+  return PP2D_OK;
+}
+
+int pp2d_mdp_p2p_status(pp2d_mdp* h, int* timed_out) {
+  if (!h || !timed_out) return fail(PP2D_ERR_INVALID, "NULL argument");
+  unsigned int e = 0;
+  PP2D_CUDA(cudaMemcpyAsync(&e, h->flags + kFlagError, sizeof(e), cudaMemcpyDeviceToHost,
+                            h->stream));
+  PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  *timed_out = (int)e;
   return PP2D_OK;
 }
 

@@ -68,7 +68,34 @@ struct SweepParams {
   int y_begin, y_end;    // rows to produce (may extend 1 row into the ghosts)
   int prefetch_rows;     // rows ahead touched with prefetch.global.L1 (>= kPrefetch)
   float gamma, ga, gb;   // gamma*1.0f, gamma*0.7f, gamma*0.1f
+  // --- peer-to-peer ghost rows (P2P kernels only, see P2pParams) ---
+  float* peer_up_out;    // up neighbour's jout plane at ITS ghost row H_up, col 0
+  float* peer_down_out;  // down neighbour's jout plane at ITS ghost row -2, col 0
+  unsigned int* flags;   // this shard's flag block (kFlag*)
+  unsigned int* up_flag_remote;    // &up.flags[kFlagFromDown]
+  unsigned int* down_flag_remote;  // &down.flags[kFlagFromUp]
+  unsigned int iter;               // 1-based count of fused P2P launches
+  unsigned int expect_top, expect_bot;  // cumulative boundary-unit counts
+  unsigned int p2p_debug;               // bit0 no waits, bit1 no peer stores, bit2 no signals
+  int edge_rows;                        // rows of a boundary unit processed first
 };
+
+// Flag block of a shard (uint32 each, cudaMalloc'ed, IPC-shared).
+constexpr int kFlagFromUp = 0;     // written by the up neighbour: its launch #
+constexpr int kFlagFromDown = 1;   // written by the down neighbour
+constexpr int kFlagCountTop = 2;   // local: finished top-boundary units
+constexpr int kFlagCountBot = 3;   // local: finished bottom-boundary units
+constexpr int kFlagError = 4;      // local: a wait timed out
+constexpr int kFlagWords = 8;
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ float min3(float a, float b, float c) {
   float d;
@@ -257,7 +284,7 @@ struct StripGeom {
   static constexpr int kRingBytesPerWarp = (CW >= 2) ? kRing * kSlotBytes : 0;
 };
 
-template <int T, int CW, bool POLICY>
+template <int T, int CW, bool POLICY, bool P2P = false>
 struct Sweeper {
   using G = StripGeom<T, CW>;
   float A[3][CW + 2];        // J^0 rows y-1, y, y+1 (rotating)
@@ -273,6 +300,8 @@ struct Sweeper {
   const uint16_t* pcode;     // next code row to prefetch (row y+kPrefetch)
   float* pout;               // row written at step y (y for T=1, y-1 for T=2)
   uint8_t* pact;             // action row y (POLICY)
+  float *pup, *pdn;          // P2P: this lane's column in the neighbours' ghost rows
+  int yout;                  // P2P: row index of pout
   size_t l1_ahead;           // CW == 1: rows ahead for prefetch.global.L1
   uint32_t ring_j, ring_c;   // CW >= 2: shared addresses of this lane's ring slots
   int x0;                    // map x of the lane's first cell
@@ -284,7 +313,7 @@ struct Sweeper {
 
   // One marching step on row y.  I: rotation index (compile time).  J2: also
   // produce the second sweep of row y-1 (steady state of T == 2).
-  template <int I, bool J2>
+  template <int I, bool J2, bool PEER = false>
   __device__ __forceinline__ void step() {
     constexpr int a0 = I % 3, a1 = (I + 1) % 3, a2 = (I + 2) % 3;
     constexpr int lc = I % 2, lp = (I + 1) % 2;
@@ -357,25 +386,32 @@ struct Sweeper {
                                 L[lp][j], G4[lp][j], p.gamma, p.ga, p.gb,
                                 act[j]);
         }
-        if (valid) store_own<CW>(pout, v2);
+        if (valid) {
+          store_own<CW>(pout, v2);
+          if constexpr (PEER) {
+            // The first / last two owned rows are also the neighbours' ghost
+            // rows: written straight into their HBM over NVLink.
+            if (pup != nullptr && yout < kPadRows && !(p.p2p_debug & 2u))
+              store_own<CW>(pup + (size_t)yout * p.pitch, v2);
+            if (pdn != nullptr && yout >= p.H - kPadRows && !(p.p2p_debug & 2u))
+              store_own<CW>(pdn + (size_t)(yout - (p.H - kPadRows)) * p.pitch, v2);
+          }
+        }
+        if constexpr (PEER) ++yout;
         pout += p.pitch;
       }
     }
   }
 
-  __device__ __forceinline__ void run(int unit, int lane) {
-    const int k = unit % p.n_strips;
-    const int rb = unit / p.n_strips;
-    const int y0 = p.y_begin + rb * p.rows_per_unit;      // rows [y0, y1)
-    const int y1 = min(y0 + p.rows_per_unit, p.y_end);
-    x0 = k * G::S + G::XOFF + lane * CW;
-    valid = (lane >= G::HL) && (lane < 32 - G::HL) && (x0 < p.W);
-    const size_t col = (size_t)(x0 + kPadLeft);
+  // March over rows [y0, y1) of this lane's columns.  PEER: rows 0,1 / H-2,H-1
+  // are also stored into the neighbours' ghost rows.
+  template <bool PEER>
+  __device__ __forceinline__ void march(int y0, int y1, size_t col) {
     const size_t pitch = (size_t)p.pitch;
-    l1_ahead = (size_t)(p.prefetch_rows - kPrefetch) * pitch;
     // First row stepped on: y0-1 for T=2 (J^1 of the row above), y0 for T=1.
     const int ys = (T == 2) ? y0 - 1 : y0;
     int steps = y1 - ys + (T == 2 ? 1 : 0);               // rows ys .. ye
+    if constexpr (PEER) yout = y0;
     const float* jin = p.jin + col + (size_t)(ys - 1 + kPadRows) * pitch;
     {
       float r[CW];
@@ -387,8 +423,6 @@ struct Sweeper {
     pin = jin + 2 * pitch;                                  // row ys+1
     pcode = p.code + col + (size_t)(ys + kPadRows) * pitch; // row ys
     if constexpr (CW >= 2) {
-      ring_j += lane * (CW * 4);
-      ring_c += lane * (CW * 2);
 #pragma unroll
       for (int d = 0; d < kRing; ++d) {
         cp_async<CW * 4>(ring_j + d * G::kSlotBytes, pin);
@@ -410,16 +444,16 @@ struct Sweeper {
     if constexpr (POLICY) pact = p.action + (size_t)y0 * p.W + x0;
     if constexpr (T == 2) {
       // Two priming steps (rows y0-1 and y0) produce J^1 only.
-      step<0, false>();
-      step<1, false>();
+      step<0, false, PEER>();
+      step<1, false, PEER>();
       steps -= 2;
       while (true) {
-        step<2, true>(); if (--steps == 0) break;
-        step<3, true>(); if (--steps == 0) break;
-        step<4, true>(); if (--steps == 0) break;
-        step<5, true>(); if (--steps == 0) break;
-        step<0, true>(); if (--steps == 0) break;
-        step<1, true>(); if (--steps == 0) break;
+        step<2, true, PEER>(); if (--steps == 0) break;
+        step<3, true, PEER>(); if (--steps == 0) break;
+        step<4, true, PEER>(); if (--steps == 0) break;
+        step<5, true, PEER>(); if (--steps == 0) break;
+        step<0, true, PEER>(); if (--steps == 0) break;
+        step<1, true, PEER>(); if (--steps == 0) break;
       }
     } else {
       while (true) {
@@ -431,14 +465,90 @@ struct Sweeper {
         step<5, false>(); if (--steps == 0) break;
       }
     }
-    // Do not leave the CTA with copies in flight into its shared memory.
+    // Do not leave the slot ring with copies in flight.
     if constexpr (CW >= 2) cp_async_wait<0>();
+  }
+
+  __device__ __forceinline__ void run(int unit, int lane) {
+    const int k = unit % p.n_strips;
+    const int rb = unit / p.n_strips;
+    const int y0 = p.y_begin + rb * p.rows_per_unit;      // rows [y0, y1)
+    const int y1 = min(y0 + p.rows_per_unit, p.y_end);
+    x0 = k * G::S + G::XOFF + lane * CW;
+    valid = (lane >= G::HL) && (lane < 32 - G::HL) && (x0 < p.W);
+    const size_t col = (size_t)(x0 + kPadLeft);
+    l1_ahead = (size_t)(p.prefetch_rows - kPrefetch) * (size_t)p.pitch;
+    if constexpr (CW >= 2) {
+      ring_j += lane * (CW * 4);
+      ring_c += lane * (CW * 2);
+    }
+    int r0 = y0, r1 = y1;            // rows marched without peer stores
+    if constexpr (P2P) {
+      // Units that touch the first / last two owned rows read ghost rows and
+      // write the neighbours' ghost rows.  They process the `edge_rows` rows
+      // next to the boundary FIRST and publish their flag right after, so the
+      // hand-shake is off the critical path of the launch.
+      const bool top = p.peer_up_out != nullptr && y0 < kPadRows;
+      const bool bot = p.peer_down_out != nullptr && y1 > p.H - kPadRows;
+      if (top || bot) {
+        pup = top ? p.peer_up_out + col : nullptr;
+        pdn = bot ? p.peer_down_out + col : nullptr;
+        int e0 = y0, e1 = y1;
+        const int e = p.edge_rows;
+        if (top != bot && y1 - y0 > e) {
+          if (top) { e1 = y0 + e; r0 = e1; }
+          else     { e0 = y1 - e; r1 = e0; }
+        } else {
+          r1 = r0;                     // the whole unit is the edge segment
+        }
+        if (lane == 0 && !(p.p2p_debug & 1u)) {
+          // Wait until the neighbour's previous launch has (a) written my
+          // ghost rows of this buffer parity and (b) finished reading its own
+          // ghost rows that I am about to overwrite; both are implied by its
+          // flag, published after ALL its edge segments facing me are done.
+          const unsigned int want = p.iter - 1;
+          for (int side = 0; side < 2; ++side) {
+            if (!(side == 0 ? top : bot)) continue;
+            const unsigned int* f = p.flags + (side == 0 ? kFlagFromUp : kFlagFromDown);
+            long long spins = 0;
+            while ((int)(ld_acquire_sys(f) - want) < 0) {
+              if (++spins > (1ll << 20)) { atomicExch(p.flags + kFlagError, 1u); break; }
+              __nanosleep(64);
+            }
+          }
+        }
+        __syncwarp();
+        march<true>(e0, e1, col);
+        // Publish: the last edge segment on each side to finish writes this
+        // launch's number into the neighbour's flag.
+        __syncwarp();
+        if (lane == 0 && !(p.p2p_debug & 4u)) {
+          __threadfence_system();
+          if (top) {
+            const unsigned int c = atomicAdd(p.flags + kFlagCountTop, 1u) + 1u;
+            if (c == p.expect_top) {
+              __threadfence_system();
+              st_release_sys(p.up_flag_remote, p.iter);
+            }
+          }
+          if (bot) {
+            const unsigned int c = atomicAdd(p.flags + kFlagCountBot, 1u) + 1u;
+            if (c == p.expect_bot) {
+              __threadfence_system();
+              st_release_sys(p.down_flag_remote, p.iter);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (r1 > r0) march<false>(r0, r1, col);
   }
 };
 
 // One warp per (column strip, row block) unit; 8 warps per CTA.
-template <int T, int CW, bool POLICY>
-__global__ void __launch_bounds__(256)
+template <int T, int CW, bool POLICY, bool P2P = false>
+__global__ void __launch_bounds__(256, (T == 2 && CW == 2) ? 2 : 1)
 mdp_sweep_kernel(const SweepParams p) {
   // The table must start on a 2 KB boundary of the shared window so that the
   // row offset (bits 7..10) and the lane replica (bits 4..6) can be OR-ed
@@ -463,7 +573,7 @@ mdp_sweep_kernel(const SweepParams p) {
                : "=r"(lane_base) : "r"(lut_addr), "r"((lane & 7) << 4) : "memory");
   const uint32_t ring_warp =
       lut_addr + kLutFloat4 * 16 + (threadIdx.x >> 5) * G::kRingBytesPerWarp;
-  Sweeper<T, CW, POLICY> s(p, lane_base, ring_warp);
+  Sweeper<T, CW, POLICY, P2P> s(p, lane_base, ring_warp);
   s.run(unit, lane);
 }
 

@@ -3,9 +3,13 @@
 The reference is single-GPU; this is the new
 multi-GPU driver of section 8e.  The H x W grid is cut into contiguous row
 blocks, one per rank.  Jacobi sweeps only need the neighbours' boundary rows:
-every shard keeps 2 ghost rows of J above and below, advances 2 sweeps per
-fused kernel launch and then swaps 2 rows with each neighbour
-(NCCL send/recv over NVLink; gloo in the CPU tests).  Every 100 sweeps the
+every shard keeps 2 ghost rows of J above and below and advances 2 sweeps per
+fused kernel launch.  On GPUs of one node the fused kernel itself writes its
+first / last two rows into the neighbours' ghost rows through CUDA-IPC peer
+mappings (NVLink stores) and synchronises with them through flags in device
+memory: no exchange call and no collective between fused launches.  Single
+sweeps, arg-min sweeps and the CPU tests swap the 2 rows with
+send/recv (NCCL / gloo) instead.  Every 100 sweeps the
 per-rank inf-norm is combined with a one-float MAX all-reduce and compared
 with the reference's threshold (src/mdp/path_planning_2d.cu:221,263).
 Jacobi iteration is partition invariant, so the result is bit-identical to
@@ -14,6 +18,8 @@ the single-GPU run.
 The shard itself is pluggable (`shard_factory`) so the orchestration can be
 tested on CPU with the oracle standing in for the GPU shard (tests/ only).
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -70,6 +76,16 @@ class GpuShard:
         torch.cuda.current_stream().synchronize()
         self.mdp.reset(grid, goal)
 
+    # peer-to-peer ghost rows (same node): descriptor = CUDA IPC handles
+    def p2p_descriptor(self):
+        return self.mdp.ipc_export()
+
+    def p2p_connect(self, up_desc, down_desc):
+        self.mdp.ipc_connect(up_desc, down_desc)
+
+    def p2p_timed_out(self):
+        return self.mdp.p2p_timed_out()
+
     def halo_tensors(self):
         h = self.mdp.halo()
         t = lambda p: device_tensor(p, h.bytes)
@@ -88,7 +104,7 @@ class GpuShard:
 
 class ShardedValueIteration:
     def __init__(self, grid, goal, gamma, rank=None, world_size=None,
-                 group=None, shard_factory=GpuShard):
+                 group=None, shard_factory=GpuShard, p2p=None):
         self.group = group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world_size is None else world_size
@@ -98,10 +114,28 @@ class ShardedValueIteration:
         self.rows = self.bounds[self.rank]
         self.shard = shard_factory(grid, goal, gamma, self.rows)
         self.n_sweeps = 0
+        # Peer-to-peer ghost rows: default on when the shard supports it.
+        if p2p is None:
+            p2p = (self.world > 1 and hasattr(self.shard, "p2p_descriptor")
+                   and os.environ.get("PP2D_P2P", "1") != "0")
+        self.p2p = bool(p2p) and self.world > 1
+        self._fused_pending = False     # fused P2P launches since the last barrier
+        if self.p2p:
+            descs = [None] * self.world
+            dist.all_gather_object(descs, self.shard.p2p_descriptor(), group=self.group)
+            up = descs[self.rank - 1] if self.rank > 0 else None
+            down = descs[self.rank + 1] if self.rank + 1 < self.world else None
+            self.shard.p2p_connect(up, down)
+            self._token = torch.zeros(1, device="cuda")
 
     def reset(self, grid=None, goal=None):
         """Re-solve from J = 0 with a new map (same shape) and/or goal."""
+        if self.p2p:
+            self._cross_rank_barrier()
         self.shard.reset(grid, goal)
+        if self.p2p:                 # nobody starts over before everyone reset
+            dist.all_reduce(self._token, group=self.group)
+            torch.cuda.current_stream().synchronize()
         self.n_sweeps = 0
 
     # -- ghost rows --------------------------------------------------------
@@ -126,14 +160,27 @@ class ShardedValueIteration:
         return dist.get_global_rank(self.group, group_rank)
 
     # -- sweeps ------------------------------------------------------------
+    def _cross_rank_barrier(self):
+        """Stream-ordered: completes on a rank only after every rank's earlier
+        kernels (and their peer stores) have completed."""
+        if self._fused_pending:
+            dist.all_reduce(self._token, group=self.group)
+            self._fused_pending = False
+
     def sweeps(self, n, want_action=True):
         """n Jacobi sweeps of the whole grid; ghost rows refreshed every 2."""
         left = n
         while left > 0:
             k = min(HALO_ROWS, left)
             last = (left - k == 0)
-            self.shard.sweeps(k, want_action and last)
-            self.exchange()
+            if self.p2p and k == 2 and not (want_action and last):
+                self.shard.sweeps(2, False)      # ghost rows travel inside the kernel
+                self._fused_pending = True
+            else:
+                if self.p2p:
+                    self._cross_rank_barrier()
+                self.shard.sweeps(k, want_action and last)
+                self.exchange()
             left -= k
         self.n_sweeps += n
 
@@ -157,6 +204,10 @@ class ShardedValueIteration:
         return self.n_sweeps, residuals
 
     def download(self):
+        if self.p2p:
+            self._cross_rank_barrier()
+            if self.shard.p2p_timed_out():
+                raise RuntimeError("peer-to-peer ghost-row exchange timed out")
         return self.shard.download()
 
     def gather(self):

@@ -162,6 +162,19 @@ class MdpPathPlanning2d:
             ctypes.byref(n)))
         return cells[:n.value].copy()
 
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(_lib.IPC_DESC_BYTES)
+        _lib.check(self._lib.pp2d_mdp_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_connect(self, up_desc, down_desc):
+        _lib.check(self._lib.pp2d_mdp_ipc_connect(self._h, up_desc, down_desc))
+
+    def p2p_timed_out(self):
+        e = ctypes.c_int()
+        _lib.check(self._lib.pp2d_mdp_p2p_status(self._h, ctypes.byref(e)))
+        return bool(e.value)
+
     def halo(self):
         h = _lib.Halo()
         _lib.check(self._lib.pp2d_mdp_halo(self._h, ctypes.byref(h)))

@@ -22,7 +22,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, p2p):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from path_planning_2d_b200.distributed import ShardedValueIteration
@@ -33,7 +33,8 @@ def _worker(rank, world, port, out_dir):
                             device_id=torch.device("cuda", rank))
     try:
         grid, goal = cases.synthetic_map(301, 517, 0.2, seed=77)
-        vi = ShardedValueIteration(grid, goal, cases.GAMMA)
+        vi = ShardedValueIteration(grid, goal, cases.GAMMA, p2p=p2p)
+        assert vi.p2p == p2p
         vi.sweeps(5, want_action=False)
         sweeps, residuals = vi.value_iteration(max_batches=2)
         cost, action = vi.gather()
@@ -45,12 +46,15 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_nccl_sharded_solve_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("p2p", [True, False])
+def test_nccl_sharded_solve_matches_single_gpu(tmp_path, p2p):
+    """p2p=True: ghost rows written by the fused kernel into the neighbours'
+    HBM (CUDA IPC + device flags); p2p=False: NCCL send/recv after every launch."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world,
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), p2p), nprocs=world,
              join=True)
     got = np.load(tmp_path / "out.npz")
     grid, goal = cases.synthetic_map(301, 517, 0.2, seed=77)
