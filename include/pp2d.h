@@ -244,6 +244,15 @@ int pp2d_pomdp_sampling_uniforms(pp2d_pomdp* h, float* out100);
 int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
                           const uint8_t* fib_actions, const float* pbvi_alphas,
                           const uint8_t* pbvi_actions, uint32_t n_pbvi);
+/*
+ * fastInformedBound (fast_informed_bound_cuda.cu:97-276): value iteration on
+ * the 9 FIB alpha vectors, 10 sweeps per convergence check, stop when the
+ * inf-norm of the change is <= 0.01 (or after max_sweeps > 0).  alphas:
+ * f32[HW][9] (host), actions: u8[9] = identity (may be NULL).  The result is
+ * what pp2d_pomdp_set_alphas takes as fib_alphas.
+ */
+int pp2d_pomdp_solve_fib(pp2d_pomdp* h, float* alphas, uint8_t* actions,
+                         uint32_t* sweeps_out, uint32_t max_sweeps);
 /* Size the device belief pool for n_beliefs resident beliefs (optional). */
 int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs);
 /*

@@ -1,0 +1,354 @@
+// pp2d/planners.hpp -- C++ host side above the C ABI: ROS-free mirrors of the
+// reference's planner classes, same names, members and error behaviour.
+//
+//   reference                                           here
+//   include/path_planning_2d/path_planning_2d_base.h    PathPlanning2dBase
+//   include/path_planning_2d/mdp_path_planning_2d.h     MdpPathPlanning2d
+//   include/path_planning_2d/pomdp_path_planning_2d.h   PomdpPathPlanning2d
+//   include/path_planning_2d/search_tree.h              SearchTree
+//
+// What changes against the reference: ros::NodeHandle parameters become a
+// string map (`Params`), dummy_simulator::Belief becomes the plain struct
+// `Belief`, publishers become return values, cv::imread becomes
+// pp2d/map_io.hpp, and every device-side call goes through include/pp2d.h.
+// CUDA failures keep the reference's print-and-exit behaviour
+// (helper_cuda.h:984-999) through PP2D_CHECK.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../pp2d.h"
+#include "map_io.hpp"
+
+#define PP2D_CHECK(call)                                                    \
+  do {                                                                      \
+    int rc_ = (call);                                                       \
+    if (rc_ != PP2D_OK) {                                                   \
+      std::fprintf(stderr, "pp2d error at %s:%d code=%d \"%s\" : %s\n",    \
+                   __FILE__, __LINE__, rc_, #call, pp2d_last_error());      \
+      std::exit(EXIT_FAILURE);                                              \
+    }                                                                       \
+  } while (0)
+
+namespace path_planning_2d {
+
+typedef std::map<std::string, std::string> Params;   // ~ private ROS params
+
+struct Belief {                       // dummy_simulator/msg/Belief.msg
+  uint8_t action = 0;
+  uint8_t measurement[4] = {0, 0, 0, 0};
+  std::vector<float> belief;
+};
+
+class PathPlanning2dBase {            // path_planning_2d_base.h:29-79
+ public:
+  explicit PathPlanning2dBase(const Params& n) : nh(n) {}
+  virtual ~PathPlanning2dBase() {}
+  virtual bool initialize() = 0;
+
+ protected:
+  virtual bool loadParameters() = 0;
+  bool getParam(const std::string& k, std::string& v) const {
+    auto it = nh.find(k);
+    if (it == nh.end()) return false;
+    v = it->second;
+    return true;
+  }
+  bool getParam(const std::string& k, int32_t& v) const {
+    std::string s;
+    if (!getParam(k, s)) return false;
+    v = (int32_t)std::strtol(s.c_str(), nullptr, 10);
+    return true;
+  }
+  bool getParam(const std::string& k, float& v) const {
+    std::string s;
+    if (!getParam(k, s)) return false;
+    v = (float)std::strtod(s.c_str(), nullptr);   // double param -> float member
+    return true;
+  }
+  bool getParam(const std::string& k, bool& v) const {
+    std::string s;
+    if (!getParam(k, s)) return false;
+    v = (s == "true" || s == "1");
+    return true;
+  }
+  // loadMapFromFile (src/mdp/path_planning_2d.cu:191-205)
+  virtual bool loadMapFromFile() {
+    return pp2d::load_occupancy(map_path, map_width, map_height, grid_map);
+  }
+
+  Params nh;
+  std::string map_path;
+  uint32_t map_width = 0, map_height = 0;
+  double map_resolution = 0.0;
+  std::vector<uint8_t> grid_map;
+  int32_t goal[2] = {0, 0};
+  float discount_factor = 0.0f;
+
+ public:
+  uint32_t width() const { return map_width; }
+  uint32_t height() const { return map_height; }
+  const std::vector<uint8_t>& map() const { return grid_map; }
+};
+
+// ---------------------------------------------------------------------------
+class MdpPathPlanning2d : public PathPlanning2dBase {
+ public:
+  explicit MdpPathPlanning2d(const Params& n) : PathPlanning2dBase(n) {}
+  ~MdpPathPlanning2d() override { pp2d_mdp_destroy(mdp_); }
+
+  // src/mdp/path_planning_2d.cu:72-140
+  bool initialize() override {
+    if (!loadParameters()) {
+      std::fprintf(stderr, "Cannot load all required parameters...\n");
+      return false;
+    }
+    if (!loadMapFromFile()) {
+      std::fprintf(stderr, "Cannot load the map %s\n", map_path.c_str());
+      return false;
+    }
+    int rc = pp2d_mdp_create(map_height, map_width, grid_map.data(), goal[0], goal[1],
+                             discount_factor, &mdp_);
+    if (rc == PP2D_ERR_GOAL_OCCUPIED || rc == PP2D_ERR_INVALID) {
+      std::fprintf(stderr, "The assigned goal (%d %d) is at a occupied cell...\n", goal[0],
+                   goal[1]);
+      return false;
+    }
+    PP2D_CHECK(rc);
+    std::printf("Solve MDP with value iteration...\n");
+    valueIteration();
+    optimal_cost.resize((size_t)map_height * map_width);
+    optimal_action.resize((size_t)map_height * map_width);
+    PP2D_CHECK(pp2d_mdp_download(mdp_, optimal_cost.data(), optimal_action.data()));
+    std::printf("Initialization finished...\n");
+    return true;
+  }
+
+  // src/mdp/path_planning_2d.cu:168-189: the action at the belief mode.
+  uint8_t beliefCallback(const Belief& belief) const {
+    float belief_mode = 0.0f;
+    int32_t belief_mode_idx = 0;
+    for (size_t i = 0; i < belief.belief.size(); ++i)
+      if (belief.belief[i] > belief_mode) {
+        belief_mode_idx = (int32_t)i;
+        belief_mode = belief.belief[i];
+      }
+    return optimal_action[belief_mode_idx];
+  }
+
+  // Way-points of the greedy policy (row W of SURVEY.md section 8a).
+  std::vector<uint32_t> waypoints(uint32_t sx, uint32_t sy) const {
+    std::vector<uint32_t> cells((size_t)map_height * map_width);
+    uint32_t n = 0;
+    PP2D_CHECK(pp2d_mdp_waypoints(mdp_, sx, sy, cells.data(), (uint32_t)cells.size(), &n));
+    cells.resize(n);
+    return cells;
+  }
+
+  std::vector<float> optimal_cost;
+  std::vector<uint8_t> optimal_action;
+  int total_iterations = 0;
+  std::vector<double> residuals;
+
+ private:
+  bool loadParameters() override {          // src/mdp/path_planning_2d.cu:142-154
+    if (!getParam("map_path", map_path)) return false;
+    if (!getParam("goal_x", goal[0])) return false;
+    if (!getParam("goal_y", goal[1])) return false;
+    if (!getParam("discount_factor", discount_factor)) return false;
+    float res = 0.f;
+    if (!getParam("map_resolution", res)) return false;
+    map_resolution = res;
+    return true;
+  }
+
+  // src/mdp/path_planning_2d.cu:207-269 (imshow windows dropped)
+  void valueIteration() {
+    float cost_inf_norm = 0.0f;
+    const double max_optimal_cost = 5.0 / (1.0 - discount_factor);
+    do {
+      PP2D_CHECK(pp2d_mdp_sweeps(mdp_, 100));
+      total_iterations += 100;
+      PP2D_CHECK(pp2d_mdp_residual(mdp_, &cost_inf_norm));
+      residuals.push_back(cost_inf_norm);
+      std::printf("Inf-norm: %f\n", cost_inf_norm);
+    } while (cost_inf_norm > max_optimal_cost * 1e-3);
+  }
+
+  pp2d_mdp* mdp_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+class SearchTree {                     // search_tree.h:130-165
+ public:
+  SearchTree(pp2d_pomdp* h, const float* b) { PP2D_CHECK(pp2d_tree_create(h, b, &t_)); }
+  SearchTree(const SearchTree&) = delete;
+  SearchTree& operator=(const SearchTree&) = delete;
+  ~SearchTree() { pp2d_tree_destroy(t_); }
+  void expand() { PP2D_CHECK(pp2d_tree_expand(t_)); }
+  void getOptimalAction(uint8_t& a, float& r) { PP2D_CHECK(pp2d_tree_best_action(t_, &a, &r)); }
+  void update(const uint8_t a, const uint8_t z) { PP2D_CHECK(pp2d_tree_update(t_, a, z)); }
+  uint32_t getDepth() { return pp2d_tree_depth(t_); }
+
+ private:
+  pp2d_tree* t_ = nullptr;
+};
+
+class PomdpPathPlanning2d : public PathPlanning2dBase {
+ public:
+  explicit PomdpPathPlanning2d(const Params& n) : PathPlanning2dBase(n) {}
+  ~PomdpPathPlanning2d() override {
+    delete search_tree;
+    pp2d_pomdp_destroy(pomdp_);
+  }
+
+  // src/pomdp/path_planning_2d.cu:80-166, read_data_from_file = true path:
+  // the alpha vectors come from the text files the reference's save_data
+  // service writes (fib_alphas, fib_actions, pbvi_alphas, pbvi_actions) in
+  // `data_dir`.
+  bool initialize() override {
+    if (!loadParameters()) {
+      std::fprintf(stderr, "Cannot load all required parameters...\n");
+      return false;
+    }
+    if (!loadMapFromFile()) return false;
+    int rc = pp2d_pomdp_create(map_height, map_width, grid_map.data(), goal[0], goal[1],
+                               discount_factor, &pomdp_);
+    if (rc == PP2D_ERR_GOAL_OCCUPIED || rc == PP2D_ERR_INVALID) {
+      std::fprintf(stderr, "The assigned goal (%d %d) is at a occupied cell...\n", goal[0],
+                   goal[1]);
+      return false;
+    }
+    PP2D_CHECK(rc);
+    // uniform initial belief over the free cells (path_planning_2d.cu:99-107)
+    float sum = 0.0f;
+    for (size_t i = 0; i < grid_map.size(); ++i) sum += 1.0f - grid_map[i];
+    initial_belief.resize(grid_map.size());
+    for (size_t i = 0; i < grid_map.size(); ++i) initial_belief[i] = (1.0f - grid_map[i]) / sum;
+    if (!read_from_file) {
+      std::fprintf(stderr, "the FIB / PBVI solvers are not part of this build; "
+                           "set read_data_from_file\n");
+      return false;
+    }
+    if (!loadFibDataFromFile() || !loadPbviDataFromFile()) return false;
+    PP2D_CHECK(pp2d_pomdp_set_alphas(pomdp_, fib_alphas.data(), fib_actions.data(),
+                                     pbvi_alphas.data(), pbvi_actions.data(),
+                                     belief_set_size));
+    return true;
+  }
+
+  // src/pomdp/path_planning_2d.cu:199-241
+  uint8_t beliefCallback(const Belief& msg) {
+    const uint8_t action = msg.action;
+    const uint8_t observation = (uint8_t)((msg.measurement[3] << 3) + (msg.measurement[2] << 2) +
+                                          (msg.measurement[1] << 1) + msg.measurement[0]);
+    if (search_tree == nullptr) search_tree = new SearchTree(pomdp_, msg.belief.data());
+    else search_tree->update(action, observation);
+    uint8_t update_counter = 0;
+    while (search_tree->getDepth() < (uint32_t)max_search_tree_depth &&
+           update_counter++ < max_online_iteration)
+      search_tree->expand();
+    uint8_t new_action = 0;
+    float new_reward = 0.0f;
+    search_tree->getOptimalAction(new_action, new_reward);
+    last_reward = new_reward;
+    return new_action;
+  }
+
+  void resetSearchTreeCallback() { delete search_tree; search_tree = nullptr; }
+
+  // saveDataCallback's model half (model_generation_cuda.cu:74-115), "%15.8f".
+  bool saveModelDataToFile(const std::string& dir) {
+    const size_t n = (size_t)map_height * map_width;
+    std::vector<float> tp(n * 81), mp(n * 16), sr(n * 9);
+    PP2D_CHECK(pp2d_pomdp_model_tables(pomdp_, tp.data(), mp.data(), sr.data()));
+    return saveRows(dir + "/model_data_trans_prob", tp, 9) &&
+           saveRows(dir + "/model_data_meas_prob", mp, 16) &&
+           saveRows(dir + "/model_data_stage_reward", sr, 9);
+  }
+
+  std::vector<float> initial_belief;
+  float last_reward = 0.0f;
+  pp2d_pomdp* handle() { return pomdp_; }
+
+ private:
+  bool loadParameters() override {          // src/pomdp/path_planning_2d.cu:168-184
+    if (!getParam("map_path", map_path)) return false;
+    if (!getParam("goal_x", goal[0])) return false;
+    if (!getParam("goal_y", goal[1])) return false;
+    if (!getParam("discount_factor", discount_factor)) return false;
+    float res = 0.f;
+    if (!getParam("map_resolution", res)) return false;
+    map_resolution = res;
+    if (!getParam("read_data_from_file", read_from_file)) return false;
+    if (!getParam("max_search_tree_depth", max_search_tree_depth)) return false;
+    if (!getParam("max_online_iteration", max_online_iteration)) return false;
+    getParam("data_dir", data_dir);
+    int32_t n = 500;                        // belief_set_size, path_planning_2d.cu:122
+    if (getParam("belief_set_size", n)) belief_set_size = (uint32_t)n;
+    return true;
+  }
+
+  static bool readFloats(const std::string& path, std::vector<float>& v) {
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) { std::fprintf(stderr, "cannot open %s\n", path.c_str()); return false; }
+    for (float& x : v)
+      if (std::fscanf(f, "%f", &x) != 1) {
+        std::fprintf(stderr, "Data dimension is not set properly\n");
+        std::fclose(f);
+        return false;
+      }
+    std::fclose(f);
+    return true;
+  }
+  static bool readBytes(const std::string& path, std::vector<uint8_t>& v) {
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) { std::fprintf(stderr, "cannot open %s\n", path.c_str()); return false; }
+    for (uint8_t& x : v) {
+      unsigned u = 0;
+      if (std::fscanf(f, "%u", &u) != 1) { std::fclose(f); return false; }
+      x = (uint8_t)u;
+    }
+    std::fclose(f);
+    return true;
+  }
+  static bool saveRows(const std::string& path, const std::vector<float>& v, int per_row) {
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return false;
+    for (size_t i = 0; i < v.size(); ++i) {
+      std::fprintf(f, "%15.8f", v[i]);
+      if ((i + 1) % per_row == 0) std::fprintf(f, "\n");
+    }
+    std::fclose(f);
+    return true;
+  }
+  // fast_informed_bound_cuda.cu:361-394
+  bool loadFibDataFromFile() {
+    fib_alphas.resize((size_t)map_height * map_width * 9);
+    fib_actions.resize(9);
+    return readFloats(data_dir + "/fib_alphas", fib_alphas) &&
+           readBytes(data_dir + "/fib_actions", fib_actions);
+  }
+  // point_based_value_iteration_cuda.cu:768-800
+  bool loadPbviDataFromFile() {
+    pbvi_alphas.resize((size_t)belief_set_size * map_height * map_width);
+    pbvi_actions.resize(belief_set_size);
+    return readFloats(data_dir + "/pbvi_alphas", pbvi_alphas) &&
+           readBytes(data_dir + "/pbvi_actions", pbvi_actions);
+  }
+
+  pp2d_pomdp* pomdp_ = nullptr;
+  SearchTree* search_tree = nullptr;
+  bool read_from_file = true;
+  int32_t max_search_tree_depth = 50, max_online_iteration = 15;
+  uint32_t belief_set_size = 500;
+  std::string data_dir = ".";
+  std::vector<float> fib_alphas, pbvi_alphas;
+  std::vector<uint8_t> fib_actions, pbvi_actions;
+};
+
+}  // namespace path_planning_2d

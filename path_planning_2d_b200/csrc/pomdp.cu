@@ -568,6 +568,51 @@ int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
   return PP2D_OK;
 }
 
+int pp2d_pomdp_solve_fib(pp2d_pomdp* h, float* alphas, uint8_t* actions,
+                         uint32_t* sweeps_out, uint32_t max_sweeps) {
+  if (!h || !alphas) return fail(PP2D_ERR_INVALID, "NULL argument");
+  const size_t n = (size_t)h->HW * 9;
+  float *a1 = nullptr, *a2 = nullptr, *prev = nullptr;
+  unsigned int* d_res = nullptr;
+  int rc = [&]() -> int {
+    PP2D_CUDA(cudaMalloc(&a1, n * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&a2, n * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&prev, n * sizeof(float)));
+    PP2D_CUDA(cudaMalloc(&d_res, sizeof(unsigned int)));
+    PP2D_CUDA(cudaMemsetAsync(a1, 0, n * sizeof(float), h->stream));
+    PP2D_CUDA(cudaMemsetAsync(a2, 0, n * sizeof(float), h->stream));
+    PP2D_CUDA(cudaMemsetAsync(prev, 0, n * sizeof(float), h->stream));
+    const int blocks = (int)((n + 127) / 128);
+    uint32_t total = 0;
+    float inf_norm = 0.0f;
+    do {                                  // fast_informed_bound_cuda.cu:223-262
+      for (int i = 0; i < 5; ++i) {
+        pomdp_fib_kernel<<<blocks, 128, 0, h->stream>>>(h->H, h->W, h->gamma, h->d_tp,
+                                                        h->d_mp, h->d_sr, a1, a2);
+        count_launch();
+        pomdp_fib_kernel<<<blocks, 128, 0, h->stream>>>(h->H, h->W, h->gamma, h->d_tp,
+                                                        h->d_mp, h->d_sr, a2, a1);
+        count_launch();
+      }
+      total += 10;
+      PP2D_CUDA(cudaMemsetAsync(d_res, 0, sizeof(unsigned int), h->stream));
+      pomdp_maxdiff_kernel<<<64, 256, 0, h->stream>>>(a1, prev, n, d_res);
+      count_launch();
+      PP2D_CUDA(cudaGetLastError());
+      unsigned int bits = 0;
+      PP2D_CUDA(cudaMemcpyAsync(&bits, d_res, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+      PP2D_CUDA(cudaStreamSynchronize(h->stream));
+      memcpy(&inf_norm, &bits, sizeof(float));
+    } while (inf_norm > 0.01f && (max_sweeps == 0 || total < max_sweeps));
+    PP2D_CUDA(cudaMemcpy(alphas, a1, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (actions) for (int a = 0; a < 9; ++a) actions[a] = (uint8_t)a;  // fib:75-77
+    if (sweeps_out) *sweeps_out = total;
+    return PP2D_OK;
+  }();
+  cudaFree(a1); cudaFree(a2); cudaFree(prev); cudaFree(d_res);
+  return rc;
+}
+
 int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
   return pool_reserve(h, n_beliefs);

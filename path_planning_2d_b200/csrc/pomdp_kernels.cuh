@@ -356,6 +356,67 @@ __global__ void pomdp_bounds_kernel(int n, int ncol, int n_pbvi,
   o[11] = __int_as_float(bu | (bl << 8));
 }
 
+// ------------------------------------------------ FIB solver ("next" #1) ----
+// fib:97-204 cudaFIBValueIteration: one sweep of the Fast Informed Bound
+// backup on the 9 alpha vectors, alpha[s][a] layout.  One thread per
+// (cell, action); same operation order as the reference kernel: per
+// observation o, trans*meas (FMUL.FTZ), per next action an FFMA.FTZ chain over
+// the 9 next states from 0, running max, FADD.FTZ into reward-to-go, and
+// finally fma(gamma, reward_to_go, reward).
+__global__ void __launch_bounds__(128)
+pomdp_fib_kernel(int H, int W, float gamma, const float* __restrict__ trans_prob,
+                 const float* __restrict__ meas_prob,
+                 const float* __restrict__ stage_reward,
+                 const float* __restrict__ prev, float* __restrict__ curr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * W * 9) return;
+  const int a = t % 9, cell = t / 9;
+  const int x = cell % W, y = cell / W;
+  float tp[9];
+  int nidx[9];
+#pragma unroll
+  for (int sp = 0; sp < 9; ++sp) {
+    const int nx = x + sp % 3 - 1, ny = y + sp / 3 - 1;
+    nidx[sp] = (nx < 0 || nx >= W || ny < 0 || ny >= H) ? -1 : ny * W + nx;
+    tp[sp] = __ldg(trans_prob + 81 * (size_t)cell + 9 * a + sp);
+  }
+  float rtg = 0.0f;
+  for (int o = 0; o < 16; ++o) {
+    float ltm[9];
+#pragma unroll
+    for (int sp = 0; sp < 9; ++sp)
+      ltm[sp] = mul_ftz(tp[sp], nidx[sp] >= 0 ? __ldg(meas_prob + 16 * (size_t)nidx[sp] + o)
+                                              : 0.0f);
+    float best = -3.402823466e+38f;
+    for (int ap = 0; ap < 9; ++ap) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int sp = 0; sp < 9; ++sp)
+        acc = fma_ftz(ltm[sp], nidx[sp] >= 0 ? __ldg(prev + 9 * (size_t)nidx[sp] + ap) : 0.0f,
+                      acc);
+      if (best < acc) best = acc;
+    }
+    rtg = add_ftz(rtg, best);
+  }
+  curr[(size_t)cell * 9 + a] = fma_ftz(gamma, rtg, __ldg(stage_reward + (size_t)cell * 9 + a));
+}
+
+// max |a - b| over n floats (fib:245-251), atomicMax on the float bits.
+__global__ void __launch_bounds__(256)
+pomdp_maxdiff_kernel(const float* __restrict__ a, float* __restrict__ b_and_copy,
+                     size_t n, unsigned int* result) {
+  float m = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float v = a[i];
+    m = fmaxf(m, fabsf(b_and_copy[i] - v));
+    b_and_copy[i] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(result, __float_as_uint(m));
+}
+
 // Gather host-provided beliefs ([n][HW] row major) into belief columns.
 __global__ void pomdp_scatter_kernel(int HW, int cap, const int* __restrict__ slots,
                                      int n, const float* __restrict__ rows,

@@ -123,6 +123,17 @@ class PomdpPathPlanning2d:
         _lib.check(self._lib.pp2d_pomdp_sampling_uniforms(self._h, out.ctypes.data))
         return out
 
+    def fastInformedBound(self, max_sweeps=0):
+        """fast_informed_bound_cuda.cu:206-276 on the GPU; returns
+        (alphas [HW][9], actions [9], sweeps)."""
+        n = self.map_height * self.map_width
+        al = np.empty((n, 9), np.float32)
+        ac = np.empty(9, np.uint8)
+        sw = ctypes.c_uint32()
+        _lib.check(self._lib.pp2d_pomdp_solve_fib(self._h, al.ctypes.data, ac.ctypes.data,
+                                                  ctypes.byref(sw), max_sweeps))
+        return al, ac, sw.value
+
     def set_alphas(self, fib_alphas, pbvi_alphas, fib_actions=None, pbvi_actions=None):
         fa = np.ascontiguousarray(fib_alphas, dtype=np.float32)
         pa = np.ascontiguousarray(pbvi_alphas, dtype=np.float32)

@@ -36,6 +36,19 @@ def make_maps():
         grid = np.ascontiguousarray(grid, dtype=np.uint8)
         np.save(os.path.join(HERE, "maps", name + ".npy"), grid)
         print(name, grid.shape, int(grid.sum()), "occupied")
+        # PNG fixtures for the C++ map loader (our own encodings of the grids,
+        # not copies of the reference files): gray, and RGB with near-threshold
+        # colours to exercise the BGR->gray weights.
+        gray = np.where(grid == 1, 0, 255).astype(np.uint8)
+        rng = np.random.default_rng(len(name))
+        noisy = gray.copy()
+        sel = rng.random(gray.shape) < 0.3
+        noisy[sel] = rng.integers(240, 256, size=int(sel.sum()))
+        cv2.imwrite(os.path.join(HERE, "maps", name + "_gray.png"), noisy)
+        rgb = np.stack([noisy] * 3, -1).astype(np.int32)
+        rgb += rng.integers(-4, 5, size=rgb.shape)
+        cv2.imwrite(os.path.join(HERE, "maps", name + "_rgb.png"),
+                    np.clip(rgb, 0, 255).astype(np.uint8))
 
 
 def ref_lib():

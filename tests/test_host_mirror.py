@@ -1,0 +1,128 @@
+"""The C++ host mirror (include/pp2d/planners.hpp, map_io.hpp): compiled with
+g++ against libpp2d.so and driven through tests/cpp/host_mirror_main.cpp.
+CPU tier: the map loader against cv2.  GPU tier: MdpPathPlanning2d and
+PomdpPathPlanning2d against the oracle."""
+import glob
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "host_mirror")
+
+
+def fnv(data):
+    h = 1469598103934665603
+    for b in np.frombuffer(bytes(data), np.uint8).tolist():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+@pytest.fixture(scope="module")
+def exe():
+    libdir = os.path.join(ROOT, "path_planning_2d_b200")
+    src = os.path.join(ROOT, "tests", "cpp", "host_mirror_main.cpp")
+    cmd = ["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", EXE, src,
+           "-L", libdir, "-lpp2d", "-lz", f"-Wl,-rpath,{libdir}"]
+    subprocess.run(cmd, check=True)
+    return EXE
+
+
+@pytest.mark.parametrize("png", sorted(glob.glob(os.path.join(cases.GOLDEN, "maps", "*.png"))))
+def test_map_loader_matches_opencv(exe, png):
+    import cv2
+    img = cv2.imread(png, cv2.IMREAD_GRAYSCALE)
+    _, grid = cv2.threshold(img, 250.0, 1.0, cv2.THRESH_BINARY_INV)
+    out = subprocess.run([exe, "maps", png], capture_output=True, text=True).stdout.split()
+    assert out[:3] == [str(img.shape[1]), str(img.shape[0]), str(int(grid.sum()))]
+    assert out[3] == fnv(np.ascontiguousarray(grid, np.uint8).tobytes())
+
+
+def test_map_loader_rejects_garbage(exe, tmp_path):
+    bad = tmp_path / "bad.png"
+    bad.write_bytes(b"not a png at all")
+    assert subprocess.run([exe, "maps", str(bad)], capture_output=True,
+                          text=True).stdout.strip() == "FAIL"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["map_10x10", "sparse_map_100x40"])
+def test_cpp_mdp_planner_matches_oracle(exe, name):
+    import cv2
+    import oracle_py
+    goal, start = cases.BUNDLED[name]
+    png = os.path.join(cases.GOLDEN, "maps", name + "_rgb.png")
+    img = cv2.imread(png, cv2.IMREAD_GRAYSCALE)
+    _, grid = cv2.threshold(img, 250.0, 1.0, cv2.THRESH_BINARY_INV)
+    grid = np.ascontiguousarray(grid, np.uint8)
+    if grid[goal[1], goal[0]] or grid[start[1], start[0]]:
+        pytest.skip("noise fixture blocked the goal/start")
+    J, A, n, res = oracle_py.value_iteration(grid, goal, cases.GAMMA)
+    path = oracle_py.waypoints(A, start)
+    out = subprocess.run([exe, "mdp", png, str(goal[0]), str(goal[1]), "0.95",
+                          str(start[0]), str(start[1])], capture_output=True, text=True)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0]
+    kv = dict(t.split("=") for t in line.split()[1:])
+    assert int(kv["sweeps"]) == n
+    assert kv["cost"] == fnv(J.astype(np.float32).tobytes())
+    assert kv["action"] == fnv(A.tobytes())
+    assert int(kv["path_len"]) == len(path)
+    assert kv["path"] == fnv(path.astype(np.uint32).tobytes())
+    assert int(kv["cb"]) == A[start[1], start[0]]
+
+
+@pytest.mark.gpu
+def test_cpp_mdp_planner_rejects_occupied_goal(exe):
+    png = os.path.join(cases.GOLDEN, "maps", "map_10x10_gray.png")
+    out = subprocess.run([exe, "mdp", png, "0", "0", "0.95", "1", "1"],
+                         capture_output=True, text=True)
+    assert "INIT_FAILED" in out.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_pomdp_planner_matches_oracle(exe, tmp_path):
+    """read_data_from_file=true path: alpha vectors in the reference's text
+    format ("%15.8f"), two belief callbacks (fresh tree, then re-root)."""
+    import cv2
+    import pomdp_fixtures as pf
+    import pomdp_oracle_py as po
+    name, goal = "map_10x10", (8, 7)
+    png = os.path.join(cases.GOLDEN, "maps", name + "_gray.png")
+    img = cv2.imread(png, cv2.IMREAD_GRAYSCALE)
+    _, grid = cv2.threshold(img, 250.0, 1.0, cv2.THRESH_BINARY_INV)
+    grid = np.ascontiguousarray(grid, np.uint8)
+    if grid[goal[1], goal[0]]:
+        pytest.skip("noise fixture blocked the goal")
+    m, fib, pbvi, fa, pa = pf.alphas(grid, goal, n_pbvi=12)
+    # the text round trip is lossy by format: the oracle gets the SAME rounded
+    # numbers the C++ planner reads back
+    def dump(path, arr):
+        with open(path, "w") as f:
+            for row in arr:
+                f.write("".join("%15.8f" % v for v in row) + "\n")
+        return np.array([[np.float32(float("%15.8f" % v)) for v in row] for row in arr],
+                        np.float32)
+    fib_r = dump(tmp_path / "fib_alphas", fib)
+    pbvi_r = dump(tmp_path / "pbvi_alphas", pbvi)
+    (tmp_path / "fib_actions").write_text("".join("%10u\n" % a for a in fa))
+    (tmp_path / "pbvi_actions").write_text("".join("%10u\n" % a for a in pa))
+    b = pf.gaussian_beliefs(grid, 1, seed=5)[0]
+    (tmp_path / "belief.bin").write_bytes(b.tobytes())
+    out = subprocess.run([exe, "pomdp", png, str(goal[0]), str(goal[1]), "0.95",
+                          str(tmp_path), str(tmp_path / "belief.bin"), "12", "6"],
+                         capture_output=True, text=True)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0]
+    kv = dict(t.split("=") for t in line.split()[1:])
+    t = po.Tree(m, cases.GAMMA, fib_r, pbvi_r, pf.uniforms(), b, fa, pa)
+    a0, r0, _, _ = t.plan(50, 6)
+    assert t.update(a0, 0) == 0
+    a1, r1, _, _ = t.plan(50, 6)
+    t.close()
+    assert int(kv["a0"]) == a0 and int(kv["a1"]) == a1
+    assert kv["r0"] == "%08x" % np.float32(r0).view(np.uint32)
+    assert kv["r1"] == "%08x" % np.float32(r1).view(np.uint32)

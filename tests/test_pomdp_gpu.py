@@ -201,3 +201,17 @@ def test_reference_pomdp_kernels_vs_restatement():
                         fib.ctypes.data, 30)
     ofib, on = m.fib(cases.GAMMA, 30)
     assert n == on and np.array_equal(bits(fib), bits(ofib.reshape(-1)))
+
+
+@pytest.mark.parametrize("name,goal", [("map_10x10", (8, 7)), ("sparse_map_100x40", (95, 34))])
+def test_fib_solver_bit_exact(name, goal):
+    """"next" row 1: the FIB offline solver, same sweeps and bits as the
+    oracle (itself pinned to the reference kernel by the golden vectors)."""
+    grid = cases.load_bundled(name)
+    m = po.Model(grid, goal)
+    want, n = m.fib(cases.GAMMA)
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        got, acts, sweeps = p.fastInformedBound()
+    assert sweeps == n
+    assert acts.tolist() == list(range(9))
+    assert np.array_equal(bits(got), bits(want))
