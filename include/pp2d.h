@@ -298,6 +298,13 @@ int pp2d_tree_root_bounds(const pp2d_tree* t, float* upper, float* lower);
 /* beliefCallback's loop + getOptimalAction on an existing tree. */
 int pp2d_tree_plan(pp2d_tree* t, uint32_t max_depth, uint32_t max_iter,
                    uint8_t* action, float* value);
+/* SearchTree::print (search_tree_cuda.cu:288-309, 452-473, 628-633) into a
+ * buffer instead of stdout: pre-order walk from the root, 9 floats per node =
+ * kind (0 = V node, 1 = Q node), observation | action, weight | reward,
+ * upper bound, lower bound, heuristic, depth, number of children, pre-order
+ * id of vnode_to_expand (-1 = nullptr).  Writes at most cap_nodes nodes,
+ * returns the number of nodes in the tree (negative on error). */
+int64_t pp2d_tree_dump(const pp2d_tree* t, float* out, uint64_t cap_nodes);
 
 #ifdef __cplusplus
 }

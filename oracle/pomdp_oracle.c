@@ -715,6 +715,72 @@ int oracle_pomdp_tree_root_q(const pomdp_tree* t, float* upper, float* lower,
   return t->root->n_children;
 }
 
+/* Pre-order dump of the whole tree (the information SearchTree::print shows,
+ * tree:288-309, 452-473, 628-633): 9 floats per node = kind (0 = V, 1 = Q),
+ * observation | action, weight | reward, upper, lower, heuristic, depth,
+ * #children, pre-order id of vnode_to_expand (-1 = NULL or not in the tree).
+ * Same format as oracle/ref_pomdp_full_driver.cu:ref_full_tree_dump and
+ * pp2d_tree_dump.  Returns the node count. */
+typedef struct { const void** key; int n, cap; } idmap_t;
+static void idmap_add(idmap_t* m, const void* k) {
+  if (m->n == m->cap) {
+    m->cap = m->cap ? 2 * m->cap : 256;
+    m->key = (const void**)realloc((void*)m->key, (size_t)m->cap * sizeof(void*));
+  }
+  m->key[m->n++] = k;
+}
+static float idmap_find(const idmap_t* m, const void* k) {
+  if (!k) return -1.0f;
+  for (int i = 0; i < m->n; ++i) if (m->key[i] == k) return (float)i;
+  return -1.0f;
+}
+static void number_v(const VNode* v, idmap_t* m);
+static void number_q(const QNode* q, idmap_t* m) {
+  idmap_add(m, q);
+  for (int i = 0; i < q->n_children; ++i) number_v(q->children[i], m);
+}
+static void number_v(const VNode* v, idmap_t* m) {
+  idmap_add(m, v);
+  for (int i = 0; i < v->n_children; ++i) number_q(v->children[i], m);
+}
+int64_t oracle_pomdp_tree_dump(const pomdp_tree* t, float* out, uint64_t cap_nodes) {
+  idmap_t m = {NULL, 0, 0};
+  number_v(t->root, &m);
+  /* pre-order: entry i of the map is node i; V and Q alternate by level, so
+   * the kind is recovered by walking again in the same order */
+  int64_t n = m.n;
+  if (out) {
+    /* iterative re-walk with an explicit stack of (node, kind) */
+    const void** stack = (const void**)malloc((size_t)(n + 1) * sizeof(void*));
+    uint8_t* kind = (uint8_t*)malloc((size_t)n + 1);
+    int sp = 0;
+    uint64_t row = 0;
+    stack[sp] = t->root; kind[sp] = 0; ++sp;
+    while (sp > 0 && row < cap_nodes) {
+      --sp;
+      float* o = out + 9 * row++;
+      if (kind[sp] == 0) {
+        const VNode* v = (const VNode*)stack[sp];
+        o[0] = 0.0f; o[1] = (float)v->observation; o[2] = v->weight;
+        o[3] = v->upper_bound; o[4] = v->lower_bound; o[5] = v->heuristic;
+        o[6] = (float)v->depth; o[7] = (float)v->n_children;
+        o[8] = idmap_find(&m, v->vnode_to_expand);
+        for (int i = v->n_children - 1; i >= 0; --i) { stack[sp] = v->children[i]; kind[sp] = 1; ++sp; }
+      } else {
+        const QNode* q = (const QNode*)stack[sp];
+        o[0] = 1.0f; o[1] = (float)q->action; o[2] = q->reward;
+        o[3] = q->upper_bound; o[4] = q->lower_bound; o[5] = q->heuristic;
+        o[6] = (float)q->depth; o[7] = (float)q->n_children;
+        o[8] = idmap_find(&m, q->vnode_to_expand);
+        for (int i = q->n_children - 1; i >= 0; --i) { stack[sp] = q->children[i]; kind[sp] = 0; ++sp; }
+      }
+    }
+    free(stack); free(kind);
+  }
+  free((void*)m.key);
+  return n;
+}
+
 /* ---- helpers for fixtures (not in the reference) ------------------------ */
 /* Value of the blind policy "always action a": V <- R(:,a) + gamma * P_a V,
  * `sweeps` Jacobi iterations from V = R(:,a)/(1-gamma) lower estimate 0.

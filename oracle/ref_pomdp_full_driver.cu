@@ -1,0 +1,309 @@
+/*
+ * oracle/ref_pomdp_full_driver.cu -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * C entry points around the reference's COMPLETE POMDP stack.  The four
+ * reference translation units
+ *     src/pomdp/model_generation_cuda.cu
+ *     src/pomdp/fast_informed_bound_cuda.cu
+ *     src/pomdp/point_based_value_iteration_cuda.cu
+ *     src/pomdp/search_tree_cuda.cu
+ * are compiled UNMODIFIED, where they lie under /root/reference, by
+ * oracle/Makefile (target ref_pomdp_full: nvcc -rdc=true, the reference's
+ * --use_fast_math, arch sm_100a) and linked with this file into
+ * oracle/_ref/libpp2d_ref_pomdp_full.so.  Their non-CUDA dependencies are
+ * replaced by the stand-in headers under oracle/stubs/ (ROS, std_srvs,
+ * dummy_simulator message, boost::shared_ptr, and the subset of
+ * Boost.MultiArray those files use -- see stubs/boost/multi_array.hpp).
+ *
+ * This file only does what PomdpPathPlanning2d::initialize / beliefCallback
+ * (src/pomdp/path_planning_2d.cu:98-155, 199-241) do around those functions,
+ * and walks the resulting tree to dump it.  No arithmetic of the path is
+ * restated here.
+ *
+ * The reference keeps all state in process globals: one planner per process.
+ */
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+/* SearchTree::root is private; the dump below needs to walk the tree. */
+#define private public
+#include <path_planning_2d/search_tree.h>
+#undef private
+
+using namespace path_planning_2d;
+
+/* reference symbols (declared as in src/pomdp/path_planning_2d.cu:33-56) */
+void allocateDeviceMemoryOfModel(const uint32_t, const uint32_t);
+void freeDeviceMemoryOfModel();
+void generateModelData(const uint32_t, const uint32_t, const uint8_t* const,
+                       const int32_t* const);
+void allocateDeviceMemoryOfFIB(const uint32_t, const uint32_t);
+void freeDeviceMemoryOfFIB();
+void fastInformedBound(const uint32_t, const uint32_t, const float);
+void allocateDeviceMemoryOfPBVI(const uint32_t, const uint32_t, const uint32_t);
+void freeDeviceMemoryOfPBVI();
+/* point_based_value_iteration_cuda.cu:165-169, 344-350 */
+void generateBeliefSet(const uint32_t height, const uint32_t width,
+                       const uint32_t max_size, const float* const __restrict__ b0,
+                       float* const __restrict__ b_set_out);
+void backupAlphaVectors(const uint32_t height, const uint32_t width, const float gamma,
+                        const uint32_t set_size, const float* const __restrict__ b_set_in,
+                        float* const __restrict__ alphas_out,
+                        uint8_t* const __restrict__ actions_out);
+void evaluateFibCpu(const uint32_t, const uint32_t, const float* const, float&, uint8_t&);
+void evaluatePbviCpu(const uint32_t, const uint32_t, const float* const, float&, uint8_t&);
+
+extern float* host_trans_prob;
+extern float* host_meas_prob;
+extern float* host_stage_reward;
+extern float* host_fib_alphas;
+extern uint8_t* host_fib_actions;
+extern float* host_pbvi_alphas;
+extern uint8_t* host_pbvi_actions;
+extern float* dev_pbvi_alphas;
+extern uint8_t* dev_pbvi_actions;
+extern uint32_t belief_set_size;
+
+namespace {
+uint32_t g_h = 0, g_w = 0, g_npbvi = 0;
+float g_gamma = 0.f;
+bool g_ready = false;
+SearchTree* g_tree = nullptr;
+
+void count_nodes(const VNode* v, uint64_t* nv, uint64_t* nq);
+void count_nodes(const QNode* q, uint64_t* nv, uint64_t* nq) {
+  ++*nq;
+  for (const VNode* c : q->children) if (c) count_nodes(c, nv, nq);
+}
+void count_nodes(const VNode* v, uint64_t* nv, uint64_t* nq) {
+  ++*nv;
+  for (const QNode* c : v->children) if (c) count_nodes(c, nv, nq);
+}
+
+/* pre-order numbering of every node, V and Q nodes sharing one counter */
+void number_nodes(const VNode* v, std::map<const void*, int>& id);
+void number_nodes(const QNode* q, std::map<const void*, int>& id) {
+  const int k = (int)id.size();
+  id[q] = k;
+  for (const VNode* c : q->children) if (c) number_nodes(c, id);
+}
+void number_nodes(const VNode* v, std::map<const void*, int>& id) {
+  const int k = (int)id.size();
+  id[v] = k;
+  for (const QNode* c : v->children) if (c) number_nodes(c, id);
+}
+/* 9 floats per node: kind (0 = V, 1 = Q), observation | action,
+ * weight | reward, upper, lower, heuristic, depth, #children, pre-order id of
+ * vnode_to_expand (-1 = nullptr) */
+void dump_nodes(const VNode* v, const std::map<const void*, int>& id, std::vector<float>& o);
+void dump_nodes(const QNode* q, const std::map<const void*, int>& id, std::vector<float>& o) {
+  const float te = q->vnode_to_expand && id.count(q->vnode_to_expand)
+                       ? (float)id.at(q->vnode_to_expand) : -1.0f;
+  const float row[9] = {1.0f, (float)q->action, q->reward, q->upper_bound, q->lower_bound,
+                        q->heuristic, (float)q->depth, (float)q->children.size(), te};
+  o.insert(o.end(), row, row + 9);
+  for (const VNode* c : q->children) if (c) dump_nodes(c, id, o);
+}
+void dump_nodes(const VNode* v, const std::map<const void*, int>& id, std::vector<float>& o) {
+  const float te = v->vnode_to_expand && id.count(v->vnode_to_expand)
+                       ? (float)id.at(v->vnode_to_expand) : -1.0f;
+  const float row[9] = {0.0f, (float)v->observation, v->weight, v->upper_bound, v->lower_bound,
+                        v->heuristic, (float)v->depth, (float)v->children.size(), te};
+  o.insert(o.end(), row, row + 9);
+  for (const QNode* c : v->children) if (c) dump_nodes(c, id, o);
+}
+}  // namespace
+
+extern "C" {
+
+/* initialize() up to the offline solvers: model tables, buffers, statics
+ * (src/pomdp/path_planning_2d.cu:109-155 without the solver calls). */
+int ref_full_init(uint32_t h, uint32_t w, const uint8_t* map, int32_t gx, int32_t gy,
+                  float gamma, uint32_t n_pbvi) {
+  if (g_ready) return -1;
+  int32_t goal[2] = {gx, gy};
+  allocateDeviceMemoryOfModel(h, w);
+  generateModelData(h, w, map, goal);
+  allocateDeviceMemoryOfFIB(h, w);
+  allocateDeviceMemoryOfPBVI(h, w, n_pbvi);
+  QNode::height = h; QNode::width = w; QNode::gamma = gamma;
+  VNode::height = h; VNode::width = w; VNode::gamma = gamma;
+  SearchTree::height = h; SearchTree::width = w;
+  g_h = h; g_w = w; g_gamma = gamma; g_npbvi = n_pbvi;
+  g_ready = true;
+  return 0;
+}
+
+int ref_full_shutdown(void) {
+  if (!g_ready) return -1;
+  delete g_tree; g_tree = nullptr;
+  freeDeviceMemoryOfPBVI();
+  freeDeviceMemoryOfFIB();
+  freeDeviceMemoryOfModel();
+  g_ready = false;
+  return 0;
+}
+
+int ref_full_model(float* trans_prob, float* meas_prob, float* stage_reward) {
+  const size_t n = (size_t)g_h * g_w;
+  if (trans_prob) memcpy(trans_prob, host_trans_prob, n * 81 * sizeof(float));
+  if (meas_prob) memcpy(meas_prob, host_meas_prob, n * 16 * sizeof(float));
+  if (stage_reward) memcpy(stage_reward, host_stage_reward, n * 9 * sizeof(float));
+  return 0;
+}
+
+/* The read_data_from_file=true path without the text round trip: the tree
+ * reads host_fib_alphas [HW][9], host_fib_actions, host_pbvi_alphas [N][HW],
+ * host_pbvi_actions (fast_informed_bound_cuda.cu:278-297,
+ * point_based_value_iteration_cuda.cu:678-699). */
+int ref_full_set_alphas(const float* fib, const uint8_t* fib_actions, const float* pbvi,
+                        const uint8_t* pbvi_actions) {
+  const size_t n = (size_t)g_h * g_w;
+  memcpy(host_fib_alphas, fib, n * 9 * sizeof(float));
+  for (int a = 0; a < 9; ++a) host_fib_actions[a] = fib_actions ? fib_actions[a] : (uint8_t)a;
+  memcpy(host_pbvi_alphas, pbvi, n * g_npbvi * sizeof(float));
+  if (pbvi_actions) memcpy(host_pbvi_actions, pbvi_actions, g_npbvi);
+  else memset(host_pbvi_actions, 0, g_npbvi);
+  return 0;
+}
+
+/* fastInformedBound (fast_informed_bound_cuda.cu:206-276). */
+int ref_full_solve_fib(float* alphas_out, uint8_t* actions_out) {
+  fastInformedBound(g_h, g_w, g_gamma);
+  const size_t n = (size_t)g_h * g_w;
+  if (alphas_out) memcpy(alphas_out, host_fib_alphas, n * 9 * sizeof(float));
+  if (actions_out) memcpy(actions_out, host_fib_actions, 9);
+  return 0;
+}
+
+/* pointBasedValueIteration (point_based_value_iteration_cuda.cu:643-676),
+ * with the belief set kept so that it can be returned.  rand_seed > 0 calls
+ * srand(rand_seed) first (1 = the state of a fresh process, the planner never
+ * calls srand). */
+int ref_full_solve_pbvi(const float* initial_belief, uint32_t rand_seed,
+                        float* belief_set_out, float* alphas_out, uint8_t* actions_out) {
+  const size_t n = (size_t)g_h * g_w;
+  if (rand_seed) srand(rand_seed);
+  float* belief_set = (float*)malloc(sizeof(float) * n * belief_set_size);
+  generateBeliefSet(g_h, g_w, belief_set_size, initial_belief, belief_set);
+  for (size_t i = 0; i < belief_set_size * n; ++i) host_pbvi_alphas[i] = 0.0f;
+  backupAlphaVectors(g_h, g_w, g_gamma, belief_set_size, belief_set, host_pbvi_alphas,
+                     host_pbvi_actions);
+  cudaMemcpy(dev_pbvi_alphas, host_pbvi_alphas, sizeof(float) * belief_set_size * n,
+             cudaMemcpyHostToDevice);
+  cudaMemcpy(dev_pbvi_actions, host_pbvi_actions, belief_set_size, cudaMemcpyHostToDevice);
+  if (belief_set_out) memcpy(belief_set_out, belief_set, sizeof(float) * n * belief_set_size);
+  if (alphas_out) memcpy(alphas_out, host_pbvi_alphas, sizeof(float) * n * belief_set_size);
+  if (actions_out) memcpy(actions_out, host_pbvi_actions, belief_set_size);
+  free(belief_set);
+  return 0;
+}
+
+/* generateBeliefSet alone (point_based_value_iteration_cuda.cu:165-293). */
+int ref_full_belief_set(const float* initial_belief, uint32_t rand_seed, float* belief_set_out) {
+  if (rand_seed) srand(rand_seed);
+  generateBeliefSet(g_h, g_w, belief_set_size, initial_belief, belief_set_out);
+  return 0;
+}
+
+/* backupAlphaVectors alone on a given belief set, alphas start at 0. */
+int ref_full_backup(const float* belief_set, float* alphas_out, uint8_t* actions_out) {
+  const size_t n = (size_t)g_h * g_w;
+  for (size_t i = 0; i < belief_set_size * n; ++i) host_pbvi_alphas[i] = 0.0f;
+  backupAlphaVectors(g_h, g_w, g_gamma, belief_set_size, belief_set, host_pbvi_alphas,
+                     host_pbvi_actions);
+  if (alphas_out) memcpy(alphas_out, host_pbvi_alphas, sizeof(float) * n * belief_set_size);
+  if (actions_out) memcpy(actions_out, host_pbvi_actions, belief_set_size);
+  return 0;
+}
+
+int ref_full_evaluate(const float* belief, float* upper, uint8_t* upper_action, float* lower,
+                      uint8_t* lower_action) {
+  float u, l; uint8_t ua, la;
+  evaluateFibCpu(g_h, g_w, belief, u, ua);
+  evaluatePbviCpu(g_h, g_w, belief, l, la);
+  if (upper) *upper = u;
+  if (upper_action) *upper_action = ua;
+  if (lower) *lower = l;
+  if (lower_action) *lower_action = la;
+  return 0;
+}
+
+/* ---- SearchTree (search_tree.h:130-165) ---------------------------------- */
+/* rand_seed > 0: srand(rand_seed) before the tree is built (1 = fresh process). */
+int ref_full_tree_create(const float* belief, uint32_t rand_seed) {
+  delete g_tree; g_tree = nullptr;
+  if (rand_seed) srand(rand_seed);
+  g_tree = new SearchTree(belief);
+  return 0;
+}
+int ref_full_tree_destroy(void) { delete g_tree; g_tree = nullptr; return 0; }
+int ref_full_tree_expand(void) {
+  if (!g_tree || !g_tree->root->vnode_to_expand) return -1;   /* reference would crash */
+  g_tree->expand();
+  return 0;
+}
+uint32_t ref_full_tree_depth(void) { return g_tree ? g_tree->getDepth() : 0; }
+int ref_full_tree_best_action(uint8_t* a, float* r) {
+  uint8_t aa = 0; float rr = 0.f;
+  g_tree->getOptimalAction(aa, rr);
+  if (a) *a = aa;
+  if (r) *r = rr;
+  return 0;
+}
+int ref_full_tree_update(uint8_t a, uint8_t z) {
+  if (!g_tree || g_tree->root->children.empty()) return -1;   /* reference would crash */
+  g_tree->update(a, z);
+  return 0;
+}
+int ref_full_tree_root_bounds(float* upper, float* lower) {
+  if (upper) *upper = g_tree->root->upper_bound;
+  if (lower) *lower = g_tree->root->lower_bound;
+  return 0;
+}
+/* beliefCallback's expansion loop (src/pomdp/path_planning_2d.cu:217-228);
+ * stats = {#V nodes, #Q nodes, root depth, expansions done}. */
+int ref_full_tree_plan(uint32_t max_depth, uint32_t max_iter, uint8_t* action, float* value,
+                       uint64_t* stats) {
+  uint8_t update_counter = 0;
+  uint64_t done = 0;
+  while (g_tree->getDepth() < max_depth && update_counter++ < max_iter) {
+    if (!g_tree->root->vnode_to_expand) break;
+    g_tree->expand();
+    ++done;
+  }
+  ref_full_tree_best_action(action, value);
+  if (stats) {
+    stats[0] = stats[1] = 0;
+    count_nodes(g_tree->root, &stats[0], &stats[1]);
+    stats[2] = g_tree->getDepth();
+    stats[3] = done;
+  }
+  return 0;
+}
+/* pre-order dump, 9 floats per node; returns the number of nodes (writes at
+ * most cap_nodes of them). */
+int64_t ref_full_tree_dump(float* out, uint64_t cap_nodes) {
+  std::map<const void*, int> id;
+  number_nodes(g_tree->root, id);
+  std::vector<float> rows;
+  dump_nodes(g_tree->root, id, rows);
+  const uint64_t n = rows.size() / 9;
+  if (out) memcpy(out, rows.data(), sizeof(float) * 9 * (n < cap_nodes ? n : cap_nodes));
+  return (int64_t)n;
+}
+/* belief of the root V node */
+int ref_full_tree_root_belief(float* out) {
+  memcpy(out, g_tree->root->belief, sizeof(float) * g_h * g_w);
+  return 0;
+}
+
+}  /* extern "C" */

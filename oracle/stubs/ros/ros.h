@@ -2,6 +2,9 @@
 // declarations for the reference's POMDP headers to parse when only its
 // CUDA translation units are compiled for the oracle.  Nothing is linked.
 #pragma once
+#include <cmath>
+#include <cstdio>
+#include <iostream>
 #include <string>
 namespace ros {
 class Publisher {};

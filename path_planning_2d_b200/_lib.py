@@ -73,6 +73,7 @@ SIGNATURES = {
     "pp2d_tree_update": (_i, [_vp, ctypes.c_uint8, ctypes.c_uint8]),
     "pp2d_tree_root_bounds": (_i, [_vp, _vp, _vp]),
     "pp2d_tree_plan": (_i, [_vp, _u32, _u32, _vp, _vp]),
+    "pp2d_tree_dump": (ctypes.c_int64, [_vp, _vp, ctypes.c_uint64]),
 }
 
 _lib = None

@@ -40,6 +40,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "async_copy.cuh"
+
 namespace pp2d {
 
 constexpr int kPadRows = 2;   // ghost rows above and below the owned rows
@@ -238,18 +240,6 @@ __device__ __forceinline__ void lut_fetch(uint32_t lane_base, uint32_t word,
 // their first use, sharing a scoreboard with younger loads) the copies are
 // issued where they are written and waited for with a counting barrier
 // (LDGDEPBAR / DEPBAR.LE in SASS).
-template <int BYTES>
-__device__ __forceinline__ void cp_async(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;"
-               :: "r"(saddr), "l"(g), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
-}
 template <int CW, int OFF>
 __device__ __forceinline__ void lds_row(uint32_t saddr, float (&o)[CW]) {
   if constexpr (CW == 2) {

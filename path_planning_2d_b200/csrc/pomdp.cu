@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
+#include <climits>
+#include <cstdint>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -208,24 +210,43 @@ double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Grow the belief pool [HW][cap] to at least slots_wanted columns.  Live
+// beliefs keep their slot numbers: the old matrix is copied row by row into
+// the wider one (the slot index is the fastest dimension).
 int pool_reserve(pp2d_pomdp* h, size_t slots_wanted) {
   if ((size_t)h->cap >= slots_wanted && h->d_bel) return PP2D_OK;
-  if (h->d_bel && h->free_slots.size() != (size_t)h->cap)
-    return fail(PP2D_ERR_STATE, "belief pool is in use (%d slots) and cannot grow to %zu",
-                h->cap, slots_wanted);
+  const size_t cap = (slots_wanted + 31) / 32 * 32;
+  if (cap > (size_t)INT32_MAX)
+    return fail(PP2D_ERR_INVALID, "belief pool of %zu slots is too large", cap);
+  float* nb = nullptr;
+  PP2D_CUDA(cudaMalloc(&nb, cap * (size_t)h->HW * sizeof(float)));
+  const size_t old_cap = h->d_bel ? (size_t)h->cap : 0;
+  if (old_cap && h->free_slots.size() != old_cap) {
+    cudaError_t e = cudaMemcpy2DAsync(nb, cap * sizeof(float), h->d_bel, old_cap * sizeof(float),
+                                      old_cap * sizeof(float), (size_t)h->HW,
+                                      cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+      cudaFree(nb);
+      return fail(PP2D_ERR_CUDA, "CUDA error growing the belief pool: %s", cudaGetErrorName(e));
+    }
+  }
   if (h->d_bel) cudaFree(h->d_bel);
-  h->d_bel = nullptr;
-  size_t cap = (slots_wanted + 31) / 32 * 32;
-  PP2D_CUDA(cudaMalloc(&h->d_bel, cap * (size_t)h->HW * sizeof(float)));
+  h->d_bel = nb;
   h->cap = (int)cap;
-  h->free_slots.resize(cap);
-  for (size_t i = 0; i < cap; ++i) h->free_slots[i] = (int)(cap - 1 - i);
+  // new slots go UNDER the still-free old ones so that allocation order of a
+  // fresh pool stays ascending
+  std::vector<int> fresh;
+  fresh.reserve(cap - old_cap + h->free_slots.size());
+  for (size_t i = cap; i-- > old_cap;) fresh.push_back((int)i);
+  fresh.insert(fresh.end(), h->free_slots.begin(), h->free_slots.end());
+  h->free_slots.swap(fresh);
   return PP2D_OK;
 }
 
 int alloc_slot(pp2d_pomdp* h, int* out) {
   if (h->free_slots.empty())
-    return fail(PP2D_ERR_STATE, "belief pool exhausted (%d slots)", h->cap);
+    PP2D_TRY(pool_reserve(h, std::max<size_t>(4096, 2 * (size_t)h->cap)));
   *out = h->free_slots.back();
   h->free_slots.pop_back();
   return PP2D_OK;
@@ -544,7 +565,7 @@ int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
   if (!h || !fib_alphas) return fail(PP2D_ERR_INVALID, "NULL argument");
   if (n_pbvi > 0 && !pbvi_alphas) return fail(PP2D_ERR_INVALID, "pbvi_alphas is NULL");
   const int ncol = kColPbvi + (int)n_pbvi;
-  const int ld = (ncol + 63) / 64 * 64;
+  const int ld = (ncol + kEvN - 1) / kEvN * kEvN;   // zero-padded to whole column tiles
   const size_t HW = (size_t)h->HW;
   std::vector<float> mat(HW * ld, 0.0f), sr(HW * 9);
   PP2D_CUDA(cudaMemcpy(sr.data(), h->d_sr, HW * 9 * sizeof(float), cudaMemcpyDeviceToHost));
@@ -624,9 +645,7 @@ int pp2d_pomdp_bayes_update(pp2d_pomdp* h, const float* beliefs_in, uint32_t n,
   if (!h || !beliefs_in || !actions || !observations || !beliefs_out)
     return fail(PP2D_ERR_INVALID, "NULL argument");
   if (n == 0) return PP2D_OK;
-  PP2D_TRY(pool_reserve(h, std::max<size_t>(h->cap, 2 * (size_t)n)));
-  if (h->free_slots.size() < 2 * (size_t)n)
-    return fail(PP2D_ERR_STATE, "belief pool too small for %u updates", n);
+  PP2D_TRY(pool_reserve(h, (size_t)h->cap - h->free_slots.size() + 2 * (size_t)n));
   const int HW = h->HW;
   std::vector<int> in(n), outs(n);
   std::vector<BayesItem> items(n);
@@ -683,9 +702,7 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
   if (!h || !beliefs) return fail(PP2D_ERR_INVALID, "NULL argument");
   if (!h->have_alphas) return fail(PP2D_ERR_STATE, "pp2d_pomdp_set_alphas not called");
   if (n == 0) return PP2D_OK;
-  PP2D_TRY(pool_reserve(h, std::max<size_t>(h->cap, n)));
-  if (h->free_slots.size() < n)
-    return fail(PP2D_ERR_STATE, "belief pool too small for %u beliefs", n);
+  PP2D_TRY(pool_reserve(h, (size_t)h->cap - h->free_slots.size() + n));
   const int HW = h->HW;
   std::vector<int> slots(n);
   for (uint32_t i = 0; i < n; ++i) PP2D_TRY(alloc_slot(h, &slots[i]));
@@ -830,6 +847,40 @@ int pp2d_tree_root_bounds(const pp2d_tree* t, float* upper, float* lower) {
   if (upper) *upper = t->t.v[t->t.root].upper;
   if (lower) *lower = t->t.v[t->t.root].lower;
   return PP2D_OK;
+}
+
+/* SearchTree::print (search_tree_cuda.cu:288-309, 452-473, 628-633) */
+int64_t pp2d_tree_dump(const pp2d_tree* tt, float* out, uint64_t cap_nodes) {
+  if (!tt || tt->t.root < 0) { fail(PP2D_ERR_INVALID, "tree is NULL"); return -1; }
+  const Tree& t = tt->t;
+  // pass 1: pre-order ids of the V nodes (V and Q nodes share one counter)
+  std::vector<int> vid(t.v.size(), -1);
+  struct Item { int idx; bool is_q; };
+  std::vector<Item> order, stack{{t.root, false}};
+  while (!stack.empty()) {
+    const Item it = stack.back();
+    stack.pop_back();
+    if (!it.is_q) vid[it.idx] = (int)order.size();
+    order.push_back(it);
+    const std::vector<int>& ch = it.is_q ? t.q[it.idx].children : t.v[it.idx].children;
+    for (size_t i = ch.size(); i-- > 0;) stack.push_back({ch[i], !it.is_q});
+  }
+  auto target = [&](int v) { return v >= 0 ? (float)vid[v] : -1.0f; };
+  for (size_t k = 0; out && k < order.size() && k < cap_nodes; ++k) {
+    float* o = out + 9 * k;
+    if (order[k].is_q) {
+      const QNodeH& q = t.q[order[k].idx];
+      o[0] = 1.0f; o[1] = (float)q.action; o[2] = q.reward; o[3] = q.upper; o[4] = q.lower;
+      o[5] = q.heuristic; o[6] = (float)q.depth; o[7] = (float)q.children.size();
+      o[8] = target(q.to_expand);
+    } else {
+      const VNodeH& v = t.v[order[k].idx];
+      o[0] = 0.0f; o[1] = (float)v.obs; o[2] = v.weight; o[3] = v.upper; o[4] = v.lower;
+      o[5] = v.heuristic; o[6] = (float)v.depth; o[7] = (float)v.children.size();
+      o[8] = target(v.to_expand);
+    }
+  }
+  return (int64_t)order.size();
 }
 
 /* SearchTree::update(a, z), search_tree_cuda.cu:548-626 */

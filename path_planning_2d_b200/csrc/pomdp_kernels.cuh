@@ -22,6 +22,8 @@
 #include <curand_kernel.h>
 #include <stdint.h>
 
+#include "async_copy.cuh"
+
 namespace pp2d {
 
 __device__ __forceinline__ float fma_ftz(float a, float b, float c) {
@@ -275,59 +277,88 @@ pomdp_sample_kernel(int H, int W, int n, int S,
 // (i, j), cells in ascending order, float multiply rounded, then float add
 // rounded (no FMA).  alpha is [HW][ld] with the columns
 //   0..8 FIB, 9..17 stage reward, 18..18+N-1 PBVI.
-// CTA tile 64 beliefs x 64 columns, 256 threads, 4x4 accumulators each.
-constexpr int kEvM = 64, kEvN = 64, kEvK = 32;
+// CTA tile 128 beliefs x 128 columns, 256 threads, 8x8 accumulators each
+// (4 LDS.128 per 128 math instructions: the 4x4 version was bound by the
+// shared-memory pipe), K chunks of 16 cells double-buffered with cp.async.
+constexpr int kEvM = 128, kEvN = 128, kEvK = 16, kEvPad = 4;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 pomdp_values_kernel(int HW, int cap, int ld, int ncol,
                     const int* __restrict__ slots, int n,
                     const float* __restrict__ bel,
                     const float* __restrict__ alpha, float* __restrict__ out) {
-  __shared__ float sb[kEvK][kEvM + 4];
-  __shared__ float sa[kEvK][kEvN + 4];
+  __shared__ __align__(16) float sb[2][kEvK][kEvM + kEvPad];
+  __shared__ __align__(16) float sa[2][kEvK][kEvN + kEvPad];
   __shared__ int sslot[kEvM];
   const int m0 = blockIdx.x * kEvM, n0 = blockIdx.y * kEvN;
   const int tid = threadIdx.x;
-  if (tid < kEvM) sslot[tid] = (m0 + tid < n) ? slots[m0 + tid] : -1;
+  if (tid < kEvM) sslot[tid] = (m0 + tid < n) ? slots[m0 + tid] : slots[0];
   __syncthreads();
-  const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
-  float acc[4][4];
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-  for (int k0 = 0; k0 < HW; k0 += kEvK) {
-    for (int e = tid; e < kEvK * kEvM; e += 256) {
-      const int kk = e / kEvM, mm = e % kEvM;
-      const int s = k0 + kk, sl = sslot[mm];
-      sb[kk][mm] = (s < HW && sl >= 0) ? bel[(size_t)s * cap + sl] : 0.0f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  // Tile loaders.  Rows past HW are clamped to the last row: they are never
+  // accumulated (the k loop stops at HW), only kept in bounds.  Columns past
+  // ncol read the zero padding of alpha (ld is a multiple of 128).
+  auto load_tiles = [&](int buf, int k0) {
+#pragma unroll
+    for (int e = 0; e < (kEvK * kEvM) / 256; ++e) {
+      const int idx = tid + e * 256;
+      const int kk = idx / kEvM, mm = idx % kEvM;
+      const int s = min(k0 + kk, HW - 1);
+      cp_async<4>((uint32_t)__cvta_generic_to_shared(&sb[buf][kk][mm]),
+                  bel + (size_t)s * cap + sslot[mm]);
     }
-    for (int e = tid; e < kEvK * kEvN; e += 256) {
-      const int kk = e / kEvN, nn = e % kEvN;
-      const int s = k0 + kk, j = n0 + nn;
-      sa[kk][nn] = (s < HW && j < ncol) ? alpha[(size_t)s * ld + j] : 0.0f;
+#pragma unroll
+    for (int e = 0; e < (kEvK * kEvN / 4) / 256; ++e) {
+      const int idx = tid + e * 256;
+      const int kk = idx / (kEvN / 4), nn = (idx % (kEvN / 4)) * 4;
+      const int s = min(k0 + kk, HW - 1);
+      cp_async<16>((uint32_t)__cvta_generic_to_shared(&sa[buf][kk][nn]),
+                   alpha + (size_t)s * ld + n0 + nn);
+    }
+    cp_async_commit();
+  };
+
+  const int nchunks = (HW + kEvK - 1) / kEvK;
+  load_tiles(0, 0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunks) {
+      load_tiles(buf ^ 1, (c + 1) * kEvK);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    const int kend = min(kEvK, HW - k0);
+    const int kend = min(kEvK, HW - c * kEvK);
+#pragma unroll 4
     for (int kk = 0; kk < kend; ++kk) {
-      const float4 b = *reinterpret_cast<const float4*>(&sb[kk][tm]);
-      const float4 a = *reinterpret_cast<const float4*>(&sa[kk][tn]);
-      const float bv[4] = {b.x, b.y, b.z, b.w}, av[4] = {a.x, a.y, a.z, a.w};
+      const float4 b0 = *reinterpret_cast<const float4*>(&sb[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sb[buf][kk][64 + tx * 4]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&sa[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sa[buf][kk][64 + ty * 4]);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 8; ++j)
           acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(bv[i], av[j]));
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + tm + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
     if (m >= n) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = n0 + tn + j;
+    for (int j = 0; j < 8; ++j) {
+      const int col = n0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + (j - 4));
       if (col < ncol) out[(size_t)m * ncol + col] = acc[i][j];
     }
   }

@@ -65,6 +65,16 @@ class SearchTree:
                                             ctypes.addressof(a), ctypes.addressof(r)))
         return a.value, r.value
 
+    def dump(self):
+        """print() of search_tree_cuda.cu:628-633 as an array [nodes][9], see
+        pp2d_tree_dump in include/pp2d.h."""
+        n = self._lib.pp2d_tree_dump(self._t, None, 0)
+        if n < 0:
+            raise _lib.Pp2dError(_lib.PP2D_ERR_INVALID, "pp2d_tree_dump failed")
+        out = np.zeros((n, 9), np.float32)
+        self._lib.pp2d_tree_dump(self._t, out.ctypes.data, n)
+        return out
+
 
 class PomdpPathPlanning2d:
     def __init__(self, grid_map, goal, discount_factor, max_search_tree_depth=50,

@@ -5,6 +5,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
+ROOT = os.path.dirname(HERE)
 GAMMA = 0.95  # launch/mdp_path_planning_2d.launch:21 (discount_factor)
 
 # name -> (goal (x, y), start (x, y)).  sparse_map_100x40 with goal (95,34) and

@@ -13,6 +13,14 @@
       count, per-batch residuals (and the model tables for the small maps)
       as <outdir>/ref_<name>.npz.  The files committed in tests/golden/ were
       produced this way on a B200 (see DESIGN.md "Oracle pin").
+
+  python tests/golden/make_golden.py pomdp [outdir]
+      (GPU box)  Reference POMDP kernels: tables, Bayes updates, FIB sweeps,
+      cuRAND uniforms, forward sampling -> pomdp_<name>.npz.
+
+  python tests/golden/make_golden.py tree [outdir]
+      (GPU box)  The reference's own QV-tree host code (SearchTree, VNode,
+      QNode, evaluateFibCpu, evaluatePbviCpu) -> tree_<case>.npz.
 """
 import ctypes
 import os
@@ -167,8 +175,30 @@ def make_pomdp(outdir):
         print(name, "fib sweeps", n_fib, "obs sample", obs[0][:8])
 
 
+def make_tree(outdir, only=None):
+    """QV-tree half: the reference's own SearchTree / VNode / QNode host code
+    (oracle/_ref/libpp2d_ref_pomdp_full.so: four unmodified translation units)
+    run on a GPU box through the scenario of tests/tree_scenario.py; one
+    process per case because the reference keeps its state in globals."""
+    import subprocess
+    import tree_scenario as ts
+    os.makedirs(outdir, exist_ok=True)
+    if only is not None:
+        out = ts.run_reference_case(only)
+        np.savez_compressed(os.path.join(outdir, f"tree_{only}.npz"), **out)
+        print(only, "nodes", [int(v.shape[0]) for k, v in out.items() if "dump" in k])
+        return
+    for case in ts.CASES:
+        subprocess.run([sys.executable, os.path.abspath(__file__), "tree", outdir, case],
+                       check=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) >= 2 and sys.argv[1] == "maps":
+    if len(sys.argv) >= 2 and sys.argv[1] == "tree":
+        make_tree(sys.argv[2] if len(sys.argv) > 2 else
+                  os.path.join(ROOT, "gpurun_out", "golden_ref"),
+                  sys.argv[3] if len(sys.argv) > 3 else None)
+    elif len(sys.argv) >= 2 and sys.argv[1] == "maps":
         make_maps()
     elif len(sys.argv) >= 2 and sys.argv[1] == "pomdp":
         make_pomdp(sys.argv[2] if len(sys.argv) > 2 else

@@ -43,6 +43,8 @@ def lib():
         L.oracle_pomdp_tree_root_q.restype = ctypes.c_int
         L.oracle_pomdp_tree_root_q.argtypes = [_vp, _vp, _vp, _vp]
         L.oracle_pomdp_forward_sampling.restype = ctypes.c_int
+        L.oracle_pomdp_tree_dump.restype = ctypes.c_int64
+        L.oracle_pomdp_tree_dump.argtypes = [_vp, _vp, ctypes.c_uint64]
         _lib = L
     return _lib
 
@@ -152,6 +154,12 @@ class Tree:
         lib().oracle_pomdp_tree_root_bounds(self.t, ctypes.addressof(u), ctypes.addressof(l))
         return u.value, l.value
 
+    def dump(self):
+        n = lib().oracle_pomdp_tree_dump(self.t, None, 0)
+        out = np.zeros((n, 9), np.float32)
+        lib().oracle_pomdp_tree_dump(self.t, out.ctypes.data, n)
+        return out
+
     def root_q(self):
         u = np.zeros(9, np.float32); l = np.zeros(9, np.float32); r = np.zeros(9, np.float32)
         n = lib().oracle_pomdp_tree_root_q(self.t, u.ctypes.data, l.ctypes.data, r.ctypes.data)
@@ -177,3 +185,131 @@ def ref():
         R.ref_pomdp_forward_sampling.argtypes = [_u32, _u32, _vp, _i32, _i32, _u32, _vp, _u8, _vp]
         _ref = R
     return _ref
+
+
+class RefFull:
+    """The reference's complete POMDP stack (oracle/_ref/libpp2d_ref_pomdp_full.so:
+    the four unmodified translation units + oracle/ref_pomdp_full_driver.cu).
+    The reference keeps its state in process globals: ONE instance per process
+    (tests run it in a subprocess).  GPU box only."""
+
+    def __init__(self, grid, goal, gamma, n_pbvi):
+        R = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libpp2d_ref_pomdp_full.so"))
+        R.ref_full_init.argtypes = [_u32, _u32, _vp, _i32, _i32, _f, _u32]
+        R.ref_full_model.argtypes = [_vp, _vp, _vp]
+        R.ref_full_set_alphas.argtypes = [_vp, _vp, _vp, _vp]
+        R.ref_full_solve_fib.argtypes = [_vp, _vp]
+        R.ref_full_solve_pbvi.argtypes = [_vp, _u32, _vp, _vp, _vp]
+        R.ref_full_belief_set.argtypes = [_vp, _u32, _vp]
+        R.ref_full_backup.argtypes = [_vp, _vp, _vp]
+        R.ref_full_evaluate.argtypes = [_vp, _vp, _vp, _vp, _vp]
+        R.ref_full_tree_create.argtypes = [_vp, _u32]
+        R.ref_full_tree_depth.restype = _u32
+        R.ref_full_tree_best_action.argtypes = [_vp, _vp]
+        R.ref_full_tree_update.argtypes = [_u8, _u8]
+        R.ref_full_tree_root_bounds.argtypes = [_vp, _vp]
+        R.ref_full_tree_plan.argtypes = [_u32, _u32, _vp, _vp, _vp]
+        R.ref_full_tree_dump.restype = ctypes.c_int64
+        R.ref_full_tree_dump.argtypes = [_vp, ctypes.c_uint64]
+        R.ref_full_tree_root_belief.argtypes = [_vp]
+        self.R = R
+        self.grid = np.ascontiguousarray(grid, np.uint8)
+        self.h, self.w = self.grid.shape
+        self.hw = self.h * self.w
+        self.n_pbvi = n_pbvi
+        rc = R.ref_full_init(self.h, self.w, self.grid.ctypes.data, goal[0], goal[1],
+                             gamma, n_pbvi)
+        assert rc == 0, "the reference planner is one-per-process"
+
+    def close(self):
+        self.R.ref_full_shutdown()
+
+    def model(self):
+        tp = np.zeros((self.hw, 9, 9), np.float32)
+        mp = np.zeros((self.hw, 16), np.float32)
+        sr = np.zeros((self.hw, 9), np.float32)
+        self.R.ref_full_model(tp.ctypes.data, mp.ctypes.data, sr.ctypes.data)
+        return tp, mp, sr
+
+    def set_alphas(self, fib, pbvi, fa=None, pa=None):
+        fib = np.ascontiguousarray(fib, np.float32)
+        pbvi = np.ascontiguousarray(pbvi, np.float32)
+        assert fib.shape == (self.hw, 9) and pbvi.shape == (self.n_pbvi, self.hw)
+        fa = None if fa is None else np.ascontiguousarray(fa, np.uint8)
+        pa = None if pa is None else np.ascontiguousarray(pa, np.uint8)
+        self.R.ref_full_set_alphas(fib.ctypes.data, fa.ctypes.data if fa is not None else None,
+                                   pbvi.ctypes.data, pa.ctypes.data if pa is not None else None)
+
+    def solve_fib(self):
+        al = np.zeros((self.hw, 9), np.float32)
+        ac = np.zeros(9, np.uint8)
+        self.R.ref_full_solve_fib(al.ctypes.data, ac.ctypes.data)
+        return al, ac
+
+    def belief_set(self, b0, seed=1):
+        b0 = np.ascontiguousarray(b0, np.float32).reshape(-1)
+        out = np.zeros((self.n_pbvi, self.hw), np.float32)
+        self.R.ref_full_belief_set(b0.ctypes.data, seed, out.ctypes.data)
+        return out
+
+    def backup(self, belief_set):
+        bs = np.ascontiguousarray(belief_set, np.float32)
+        al = np.zeros((self.n_pbvi, self.hw), np.float32)
+        ac = np.zeros(self.n_pbvi, np.uint8)
+        self.R.ref_full_backup(bs.ctypes.data, al.ctypes.data, ac.ctypes.data)
+        return al, ac
+
+    def solve_pbvi(self, b0, seed=1):
+        b0 = np.ascontiguousarray(b0, np.float32).reshape(-1)
+        bs = np.zeros((self.n_pbvi, self.hw), np.float32)
+        al = np.zeros((self.n_pbvi, self.hw), np.float32)
+        ac = np.zeros(self.n_pbvi, np.uint8)
+        self.R.ref_full_solve_pbvi(b0.ctypes.data, seed, bs.ctypes.data, al.ctypes.data,
+                                   ac.ctypes.data)
+        return bs, al, ac
+
+    def evaluate(self, belief):
+        b = np.ascontiguousarray(belief, np.float32).reshape(-1)
+        up, lo = _f(), _f()
+        ua, la = _u8(), _u8()
+        self.R.ref_full_evaluate(b.ctypes.data, ctypes.addressof(up), ctypes.addressof(ua),
+                                 ctypes.addressof(lo), ctypes.addressof(la))
+        return up.value, ua.value, lo.value, la.value
+
+    # SearchTree -- same method names as Tree above
+    def create(self, belief, seed=1):
+        b = np.ascontiguousarray(belief, np.float32).reshape(-1)
+        self.R.ref_full_tree_create(b.ctypes.data, seed)
+
+    def expand(self):
+        return self.R.ref_full_tree_expand()
+
+    def update(self, a, z):
+        return self.R.ref_full_tree_update(a, z)
+
+    @property
+    def depth(self):
+        return self.R.ref_full_tree_depth()
+
+    def best(self):
+        a, r = _u8(), _f()
+        self.R.ref_full_tree_best_action(ctypes.addressof(a), ctypes.addressof(r))
+        return a.value, r.value
+
+    def root_bounds(self):
+        u, l = _f(), _f()
+        self.R.ref_full_tree_root_bounds(ctypes.addressof(u), ctypes.addressof(l))
+        return u.value, l.value
+
+    def plan(self, max_depth=50, max_iter=15):
+        a, r = _u8(), _f()
+        stats = np.zeros(4, np.uint64)
+        self.R.ref_full_tree_plan(max_depth, max_iter, ctypes.addressof(a),
+                                  ctypes.addressof(r), stats.ctypes.data)
+        return a.value, r.value, stats
+
+    def dump(self):
+        n = self.R.ref_full_tree_dump(None, 0)
+        out = np.zeros((n, 9), np.float32)
+        self.R.ref_full_tree_dump(out.ctypes.data, n)
+        return out
