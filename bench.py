@@ -220,10 +220,18 @@ def qv_tree_section(rank, world, with_cpu):
     per_gpu = 1250
     grid = cases.load_bundled("sparse_map_100x40")
     goal = (95, 34)
-    fib, pbvi, fa, pa = pf.bundled_alphas(500)
     beliefs = pf.gaussian_beliefs(grid, per_gpu * world, sigma=2.0, seed=0)
     mine = beliefs[rank * per_gpu:(rank + 1) * per_gpu]
     with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        # offline part of PomdpPathPlanning2d::initialize (untimed, as in the
+        # reference where it runs once at start-up): FIB upper-bound and PBVI
+        # lower-bound alpha vectors from the GPU solvers, replicated per rank
+        free = (grid.reshape(-1) == 0).astype(np.float32)
+        b0 = free / free.sum(dtype=np.float32)
+        t0 = time.perf_counter()
+        fib, fa, fib_sweeps = p.fastInformedBound()
+        _, pbvi, pa = p.pointBasedValueIteration(b0, 500, rand_seed=1)
+        offline_s = time.perf_counter() - t0
         p.set_alphas(fib, pbvi, fa, pa)
         p.plan_batch(mine[:64])
         p.plan_batch(mine)                      # warm-up at full size
@@ -239,12 +247,16 @@ def qv_tree_section(rank, world, with_cpu):
     dt = float(dt.item())
     out = {"plans_per_sec": per_gpu * world / dt, "queries": per_gpu * world,
            "seconds": dt, "v_nodes_per_plan": float(stats[:, 0].mean()),
+           "offline_solve_seconds": offline_s,
            "config": "sparse_map_100x40, goal (95,34), Gaussian start beliefs "
-                     "(sigma 2 cells), 9 FIB + 500 lower-bound alpha vectors, depth cap "
-                     "50, 15 expansions, 50 samples per Q node; host beliefs in, "
-                     "actions out; queries sharded per GPU, no data-path collective",
-           "parity": "actions, bounds and tree sizes bit-identical to the oracle "
-                     "(tests/test_pomdp_gpu.py)"}
+                     "(sigma 2 cells), 9 FIB + 500 PBVI alpha vectors from the GPU "
+                     "offline solvers (untimed; bit-identical to the reference's, "
+                     "tests/test_pbvi_gpu.py), depth cap 50, 15 expansions, 50 samples "
+                     "per Q node; host beliefs in, actions out; queries sharded per "
+                     "GPU, no data-path collective",
+           "parity": "actions, bounds and tree shapes bit-identical to the oracle and to "
+                     "the reference's own SearchTree (tests/test_pomdp_gpu.py, "
+                     "tests/test_tree_pin_gpu.py)"}
     if with_cpu and rank == 0:
         import pomdp_oracle_py as po
         m = po.Model(grid, goal)

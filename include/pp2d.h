@@ -254,6 +254,23 @@ int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
 int pp2d_pomdp_solve_fib(pp2d_pomdp* h, float* alphas, uint8_t* actions,
                          uint32_t* sweeps_out, uint32_t max_sweeps);
 /* Size the device belief pool for n_beliefs resident beliefs (optional). */
+/* ---- offline PBVI solver (point_based_value_iteration_cuda.cu) ----------- */
+/* generateBeliefSet (pbvi:165-293): expands {initial_belief} to n beliefs
+ * (rand() stream seeded with rand_seed, 1 = a fresh process; 0 is taken as 1).
+ * belief_set: [n][HW] host, row-major, in set order. */
+int pp2d_pomdp_generate_belief_set(pp2d_pomdp* h, const float* initial_belief,
+                                   uint32_t n, uint32_t rand_seed, float* belief_set);
+/* backupAlphaVectors (pbvi:344-641) from alpha = 0: `iterations` point-based
+ * backups of all n alpha vectors (0 = the reference's count,
+ * ceil(log(1e-3/5)/log(gamma)), pbvi:427-431).  alphas [n][HW], actions [n]. */
+int pp2d_pomdp_backup_alphas(pp2d_pomdp* h, const float* belief_set, uint32_t n,
+                             uint32_t iterations, float* alphas, uint8_t* actions);
+/* pointBasedValueIteration (pbvi:643-676): both steps without the round trip
+ * through the host; belief_set (optional) and alphas are [n][HW]. */
+int pp2d_pomdp_solve_pbvi(pp2d_pomdp* h, const float* initial_belief, uint32_t n,
+                          uint32_t rand_seed, uint32_t iterations, float* belief_set,
+                          float* alphas, uint8_t* actions);
+
 int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs);
 /*
  * Batched cudaBayesBeliefUpdate (point_based_value_iteration_cuda.cu:88-133;

@@ -65,6 +65,9 @@ SIGNATURES = {
     "pp2d_pomdp_bayes_update": (_i, [_vp, _vp, _u32, _vp, _vp, _i, _vp, _vp]),
     "pp2d_pomdp_evaluate": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "pp2d_pomdp_plan_batch": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "pp2d_pomdp_generate_belief_set": (_i, [_vp, _vp, _u32, _u32, _vp]),
+    "pp2d_pomdp_backup_alphas": (_i, [_vp, _vp, _u32, _u32, _vp, _vp]),
+    "pp2d_pomdp_solve_pbvi": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "pp2d_tree_create": (_i, [_vp, _vp, ctypes.POINTER(_vp)]),
     "pp2d_tree_destroy": (None, [_vp]),
     "pp2d_tree_expand": (_i, [_vp]),

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpp2d.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["mdp.cu", "pomdp.cu"]
+SOURCES = ["mdp.cu", "pomdp.cu", "pbvi.cu"]
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
             and os.path.getmtime(LIB) >= _newest(deps)):
         return LIB
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + srcs
+        ["-o", LIB] + srcs + ["-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

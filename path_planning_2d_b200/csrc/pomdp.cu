@@ -26,79 +26,12 @@
 #include <chrono>
 #include <vector>
 
+#include "pomdp_host.h"
 #include "pomdp_kernels.cuh"
-
-namespace pp2d {
-int fail(int code, const char* fmt, ...);            // mdp.cu
-extern std::atomic<uint64_t> g_launches;
-}  // namespace pp2d
 
 using namespace pp2d;
 
-#define PP2D_CUDA(expr)                                                      \
-  do {                                                                       \
-    cudaError_t e_ = (expr);                                                 \
-    if (e_ != cudaSuccess)                                                   \
-      return fail(PP2D_ERR_CUDA, "CUDA error at %s:%d code=%d(%s) \"%s\"",   \
-                  __FILE__, __LINE__, (int)e_, cudaGetErrorName(e_), #expr); \
-  } while (0)
-#define PP2D_TRY(expr)                 \
-  do {                                 \
-    int rc_ = (expr);                  \
-    if (rc_ != PP2D_OK) return rc_;    \
-  } while (0)
-
 namespace {
-
-constexpr int kSamples = 50;      // search_tree_cuda.cu:176
-constexpr int kActions = 9;
-constexpr int kColFib = 0, kColReward = 9, kColPbvi = 18;
-
-// glibc rand() (TYPE_3 additive feedback, what the planner's rand() is since
-// it never calls srand(): search_tree_cuda.cu:332).  Every query owns one
-// stream seeded like a fresh process.
-struct GlibcRand {
-  int32_t r[34];
-  int k;
-  void seed(uint32_t s) {
-    int32_t t[344];
-    if (s == 0) s = 1;
-    t[0] = (int32_t)s;
-    for (int i = 1; i < 31; ++i) {
-      long long v = (16807LL * t[i - 1]) % 2147483647LL;
-      if (v < 0) v += 2147483647LL;
-      t[i] = (int32_t)v;
-    }
-    for (int i = 31; i < 34; ++i) t[i] = t[i - 31];
-    for (int i = 34; i < 344; ++i)
-      t[i] = (int32_t)((uint32_t)t[i - 31] + (uint32_t)t[i - 3]);
-    for (int i = 0; i < 34; ++i) r[i] = t[310 + i];
-    k = 0;
-  }
-  uint32_t next() {
-    uint32_t v = (uint32_t)r[(k + 3) % 34] + (uint32_t)r[(k + 31) % 34];
-    r[k] = (int32_t)v;
-    k = (k + 1) % 34;
-    return v >> 1;
-  }
-};
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t cap = 0;
-  int ensure(size_t n) {
-    if (n <= cap) return PP2D_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = n + n / 2 + 64;
-    PP2D_CUDA(cudaMalloc(&p, want * sizeof(T)));
-    cap = want;
-    return PP2D_OK;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
 
 // Host-side tree nodes (search_tree.h:30-128), indices instead of pointers.
 struct QNodeH {
@@ -173,42 +106,12 @@ void vnode_update(Tree& t, int vi) {
 
 }  // namespace
 
-struct pp2d_pomdp {
-  int H = 0, W = 0, HW = 0, gx = 0, gy = 0;
-  float gamma = 0.f;
-  uint8_t* d_map = nullptr;
-  float *d_tp = nullptr, *d_mp = nullptr, *d_sr = nullptr, *d_uniforms = nullptr;
-  // alpha matrix [HW][ld]: FIB | stage reward | PBVI
-  float* d_alpha = nullptr;
-  int ld = 0, ncol = 18, n_pbvi = 0;
-  std::vector<uint8_t> fib_actions, pbvi_actions;
-  bool have_alphas = false;
-  // belief pool [HW][cap]
-  float* d_bel = nullptr;
-  int cap = 0;
-  std::vector<int> free_slots;
-  // scratch
-  DevBuf<int> d_slots;
-  DevBuf<BayesItem> d_items;
-  DevBuf<float> d_prefix, d_draws, d_vals, d_rows, d_sums;
-  DevBuf<uint8_t> d_obs;
-  DevBuf<float> d_out;               // 12 floats per evaluated belief
-  cudaStream_t stream = nullptr;
-  uint64_t n_bayes = 0, n_vnodes = 0;
-  double t_phase[6] = {0, 0, 0, 0, 0, 0};   // PP2D_POMDP_PROFILE=1: seconds per phase
-};
-
 struct pp2d_tree {
   pp2d_pomdp* h = nullptr;
   Tree t;
 };
 
-namespace {
-
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-double now_s() {
-  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
+namespace pp2d {
 
 // Grow the belief pool [HW][cap] to at least slots_wanted columns.  Live
 // beliefs keep their slot numbers: the old matrix is copied row by row into
@@ -250,6 +153,94 @@ int alloc_slot(pp2d_pomdp* h, int* out) {
   *out = h->free_slots.back();
   h->free_slots.pop_back();
   return PP2D_OK;
+}
+
+int launch_bayes(pp2d_pomdp* h, const std::vector<BayesItem>& items) {
+  const int n = (int)items.size();
+  if (n == 0) return PP2D_OK;
+  PP2D_TRY(h->d_items.ensure(n));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), n * sizeof(BayesItem),
+                            cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((n + 31) / 32, (h->HW + 7) / 8);
+  pomdp_bayes_kernel<<<grid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+                                                  h->d_items.p, n, h->d_bel, h->d_bel);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  h->n_bayes += n;
+  return PP2D_OK;
+}
+
+// tree:226-229 on the listed columns: sequential sum, then divide.
+int launch_normalize(pp2d_pomdp* h, const std::vector<int>& slots) {
+  const int n = (int)slots.size();
+  if (n == 0) return PP2D_OK;
+  PP2D_TRY(h->d_slots.ensure(n));
+  PP2D_TRY(h->d_sums.ensure(n));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  pomdp_colsum_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+      h->HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_sums.p);
+  count_launch();
+  dim3 grid((n + 31) / 32, (h->HW + 7) / 8);
+  pomdp_scale_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n,
+                                                  h->d_sums.p, h->d_bel);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  return PP2D_OK;
+}
+
+// tree:326-328 for the listed columns into h->d_prefix[s * n + i].
+int launch_prefix(pp2d_pomdp* h, const std::vector<int>& slots) {
+  const int n = (int)slots.size();
+  if (n == 0) return PP2D_OK;
+  PP2D_TRY(h->d_slots.ensure(n));
+  PP2D_TRY(h->d_prefix.ensure((size_t)n * h->HW));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  pomdp_prefix_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+      h->HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_prefix.p);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  return PP2D_OK;
+}
+
+int launch_scatter(pp2d_pomdp* h, const std::vector<int>& slots, const float* host_rows) {
+  const int n = (int)slots.size();
+  if (n == 0) return PP2D_OK;
+  PP2D_TRY(h->d_slots.ensure(n));
+  PP2D_TRY(h->d_rows.ensure((size_t)n * h->HW));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, host_rows, (size_t)n * h->HW * sizeof(float),
+                            cudaMemcpyHostToDevice, h->stream));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((h->HW + 255) / 256, n);
+  pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n,
+                                                    h->d_rows.p, h->d_bel);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  return PP2D_OK;
+}
+
+int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows) {
+  const int n = (int)slots.size();
+  if (n == 0) return PP2D_OK;
+  PP2D_TRY(h->d_slots.ensure(n));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((h->HW + 255) / 256, n);
+  pomdp_gather_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n, h->d_bel,
+                                                   dev_rows);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  return PP2D_OK;
+}
+
+}  // namespace pp2d
+
+namespace {
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 // Evaluate the beliefs in `slots`: per belief 12 floats

@@ -1,0 +1,124 @@
+// pomdp_host.h -- host-side state shared by pomdp.cu (QV-tree) and pbvi.cu
+// (offline PBVI solver): the planner handle behind pp2d_pomdp, the belief
+// pool helpers and the glibc rand() replica.
+#pragma once
+#include "../../include/pp2d.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <vector>
+
+namespace pp2d {
+int fail(int code, const char* fmt, ...);            // mdp.cu
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct BayesItem { int src, dst; uint8_t act, obs; };
+}  // namespace pp2d
+
+#define PP2D_CUDA(expr)                                                      \
+  do {                                                                       \
+    cudaError_t e_ = (expr);                                                 \
+    if (e_ != cudaSuccess)                                                   \
+      return pp2d::fail(PP2D_ERR_CUDA, "CUDA error at %s:%d code=%d(%s) \"%s\"",   \
+                  __FILE__, __LINE__, (int)e_, cudaGetErrorName(e_), #expr); \
+  } while (0)
+#define PP2D_TRY(expr)                 \
+  do {                                 \
+    int rc_ = (expr);                  \
+    if (rc_ != PP2D_OK) return rc_;    \
+  } while (0)
+
+namespace pp2d {
+
+constexpr int kSamples = 50;      // search_tree_cuda.cu:176
+constexpr int kActions = 9;
+constexpr int kColFib = 0, kColReward = 9, kColPbvi = 18;
+
+// glibc rand() (TYPE_3 additive feedback, what the planner's rand() is since
+// it never calls srand(): search_tree_cuda.cu:332).  Every query owns one
+// stream seeded like a fresh process.
+struct GlibcRand {
+  int32_t r[34];
+  int k;
+  void seed(uint32_t s) {
+    int32_t t[344];
+    if (s == 0) s = 1;
+    t[0] = (int32_t)s;
+    for (int i = 1; i < 31; ++i) {
+      long long v = (16807LL * t[i - 1]) % 2147483647LL;
+      if (v < 0) v += 2147483647LL;
+      t[i] = (int32_t)v;
+    }
+    for (int i = 31; i < 34; ++i) t[i] = t[i - 31];
+    for (int i = 34; i < 344; ++i)
+      t[i] = (int32_t)((uint32_t)t[i - 31] + (uint32_t)t[i - 3]);
+    for (int i = 0; i < 34; ++i) r[i] = t[310 + i];
+    k = 0;
+  }
+  uint32_t next() {
+    uint32_t v = (uint32_t)r[(k + 3) % 34] + (uint32_t)r[(k + 31) % 34];
+    r[k] = (int32_t)v;
+    k = (k + 1) % 34;
+    return v >> 1;
+  }
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return PP2D_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 2 + 64;
+    PP2D_CUDA(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+    return PP2D_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace pp2d
+
+struct pp2d_pomdp {
+  int H = 0, W = 0, HW = 0, gx = 0, gy = 0;
+  float gamma = 0.f;
+  uint8_t* d_map = nullptr;
+  float *d_tp = nullptr, *d_mp = nullptr, *d_sr = nullptr, *d_uniforms = nullptr;
+  // alpha matrix [HW][ld]: FIB | stage reward | PBVI
+  float* d_alpha = nullptr;
+  int ld = 0, ncol = 18, n_pbvi = 0;
+  std::vector<uint8_t> fib_actions, pbvi_actions;
+  bool have_alphas = false;
+  // belief pool [HW][cap]
+  float* d_bel = nullptr;
+  int cap = 0;
+  std::vector<int> free_slots;
+  // scratch
+  pp2d::DevBuf<int> d_slots;
+  pp2d::DevBuf<pp2d::BayesItem> d_items;
+  pp2d::DevBuf<float> d_prefix, d_draws, d_vals, d_rows, d_sums;
+  pp2d::DevBuf<uint8_t> d_obs;
+  pp2d::DevBuf<float> d_out;               // 12 floats per evaluated belief
+  cudaStream_t stream = nullptr;
+  uint64_t n_bayes = 0, n_vnodes = 0;
+  double t_phase[6] = {0, 0, 0, 0, 0, 0};   // PP2D_POMDP_PROFILE=1: seconds per phase
+};
+
+
+namespace pp2d {
+// belief pool [HW][cap] (pomdp.cu)
+int pool_reserve(pp2d_pomdp* h, size_t slots_wanted);
+int alloc_slot(pp2d_pomdp* h, int* out);
+// the batched B2 / B3 / B7 launches on pool columns (pomdp.cu)
+int launch_bayes(pp2d_pomdp* h, const std::vector<BayesItem>& items);
+int launch_normalize(pp2d_pomdp* h, const std::vector<int>& slots);
+int launch_prefix(pp2d_pomdp* h, const std::vector<int>& slots);   // -> h->d_prefix [s*n+i]
+int launch_scatter(pp2d_pomdp* h, const std::vector<int>& slots, const float* host_rows);
+int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows);
+}  // namespace pp2d

@@ -23,24 +23,10 @@
 #include <stdint.h>
 
 #include "async_copy.cuh"
+#include "fp_exact.cuh"
+#include "pomdp_host.h"
 
 namespace pp2d {
-
-__device__ __forceinline__ float fma_ftz(float a, float b, float c) {
-  float d;
-  asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-__device__ __forceinline__ float mul_ftz(float a, float b) {
-  float d;
-  asm("mul.rn.ftz.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-  return d;
-}
-__device__ __forceinline__ float add_ftz(float a, float b) {
-  float d;
-  asm("add.rn.ftz.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-  return d;
-}
 
 // ---------------------------------------------------------------- B1 -------
 // model_gen:161-347: per cell trans_prob[9][9] (blocked mass moved to "stay"
@@ -114,7 +100,7 @@ __global__ void pomdp_model_kernel(int H, int W, int gx, int gy,
 // column src[c] with action act[c] and observation obs[c] and written,
 // un-normalised, to column dst[c].  threadIdx.x runs over children so that
 // siblings (same source column) read the same addresses.
-struct BayesItem { int src, dst; uint8_t act, obs; };
+// (BayesItem is declared in pomdp_host.h)
 
 __global__ void __launch_bounds__(256)
 pomdp_bayes_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,

@@ -144,6 +144,44 @@ class PomdpPathPlanning2d:
                                                   ctypes.byref(sw), max_sweeps))
         return al, ac, sw.value
 
+    def generateBeliefSet(self, initial_belief, max_size=500, rand_seed=1):
+        """point_based_value_iteration_cuda.cu:165-293 on the GPU -> [max_size][HW]."""
+        n = self.map_height * self.map_width
+        b0 = np.ascontiguousarray(initial_belief, dtype=np.float32).reshape(-1)
+        if b0.size != n:
+            raise ValueError("belief size != height*width")
+        out = np.empty((max_size, n), np.float32)
+        _lib.check(self._lib.pp2d_pomdp_generate_belief_set(
+            self._h, b0.ctypes.data, max_size, rand_seed, out.ctypes.data))
+        return out
+
+    def backupAlphaVectors(self, belief_set, iterations=0):
+        """point_based_value_iteration_cuda.cu:344-641 -> (alphas [N][HW], actions [N])."""
+        n = self.map_height * self.map_width
+        bs = np.ascontiguousarray(belief_set, dtype=np.float32)
+        if bs.ndim != 2 or bs.shape[1] != n:
+            raise ValueError("belief_set must be [N][HW]")
+        al = np.empty_like(bs)
+        ac = np.empty(bs.shape[0], np.uint8)
+        _lib.check(self._lib.pp2d_pomdp_backup_alphas(
+            self._h, bs.ctypes.data, bs.shape[0], iterations, al.ctypes.data, ac.ctypes.data))
+        return al, ac
+
+    def pointBasedValueIteration(self, initial_belief, belief_set_size=500, rand_seed=1,
+                                 iterations=0):
+        """point_based_value_iteration_cuda.cu:643-676 -> (belief_set, alphas, actions)."""
+        n = self.map_height * self.map_width
+        b0 = np.ascontiguousarray(initial_belief, dtype=np.float32).reshape(-1)
+        if b0.size != n:
+            raise ValueError("belief size != height*width")
+        bs = np.empty((belief_set_size, n), np.float32)
+        al = np.empty((belief_set_size, n), np.float32)
+        ac = np.empty(belief_set_size, np.uint8)
+        _lib.check(self._lib.pp2d_pomdp_solve_pbvi(
+            self._h, b0.ctypes.data, belief_set_size, rand_seed, iterations,
+            bs.ctypes.data, al.ctypes.data, ac.ctypes.data))
+        return bs, al, ac
+
     def set_alphas(self, fib_alphas, pbvi_alphas, fib_actions=None, pbvi_actions=None):
         fa = np.ascontiguousarray(fib_alphas, dtype=np.float32)
         pa = np.ascontiguousarray(pbvi_alphas, dtype=np.float32)

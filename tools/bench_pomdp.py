@@ -19,11 +19,16 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1250
     grid = cases.load_bundled("sparse_map_100x40")
     goal = (95, 34)
-    fib, pbvi, fa, pa = pf.bundled_alphas(500)
+    fib = None
     beliefs = pf.gaussian_beliefs(grid, n, sigma=2.0, seed=0)
     from path_planning_2d_b200 import PomdpPathPlanning2d, _lib
     lib = _lib.load()
     with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        free = (grid.reshape(-1) == 0).astype(np.float32)
+        t0 = time.perf_counter()
+        fib, fa, _ = p.fastInformedBound()
+        _, pbvi, pa = p.pointBasedValueIteration(free / free.sum(dtype=np.float32), 500)
+        print(f"offline FIB + PBVI(500): {time.perf_counter() - t0:.2f} s")
         p.set_alphas(fib, pbvi, fa, pa)
         p.plan_batch(beliefs[:32])                     # warm-up, pool growth
         p.plan_batch(beliefs)
