@@ -18,7 +18,7 @@ SOURCES = ["mdp.cu", "pomdp.cu", "pbvi.cu"]
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared",
     "-I", os.path.join(ROOT, "include"),
 ]
 
@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
             and os.path.getmtime(LIB) >= _newest(deps)):
         return LIB
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + srcs + ["-ldl"]
+        ["-o", LIB] + srcs + ["-ldl", "-lgomp"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

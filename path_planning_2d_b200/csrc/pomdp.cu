@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <sched.h>
 #include <chrono>
 #include <vector>
 
@@ -51,7 +52,6 @@ struct VNodeH {
   float upper = FLT_MAX, lower = -FLT_MAX, heuristic = FLT_MIN;
   int to_expand = -1;
   uint32_t depth = 0;
-  float reward[kActions] = {0};       // <b, R(:,a)> for a later expansion
 };
 
 struct Tree {
@@ -239,19 +239,33 @@ int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows)
 
 namespace {
 
+// Host threads for the per-tree work of a batch: PP2D_HOST_THREADS, else the
+// CPUs this process may run on, at most 16.  (Set explicitly rather than left
+// to OMP_NUM_THREADS, which torchrun forces to 1.)
+int host_threads() {
+  static const int n = [] {
+    const char* e = getenv("PP2D_HOST_THREADS");
+    if (e && atoi(e) > 0) return atoi(e);
+    cpu_set_t set;
+    int c = 1;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) c = CPU_COUNT(&set);
+    return std::max(1, std::min(16, c));
+  }();
+  return n;
+}
+
 double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Evaluate the beliefs in `slots`: per belief 12 floats
-// {upper, lower, reward[0..8], packed indices} into host `out` (B4, B5 and the
-// reward dot of search_tree_cuda.cu:168-173).
+// Evaluate the beliefs in `slots`: per belief 4 floats {upper, lower, packed
+// indices, 0} into host `out` (B4, B5).
 int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
   const int n = (int)slots.size();
   if (n == 0) return PP2D_OK;
   PP2D_TRY(h->d_slots.ensure(n));
   PP2D_TRY(h->d_vals.ensure((size_t)n * h->ncol));
-  PP2D_TRY(h->d_out.ensure((size_t)n * 12));
+  PP2D_TRY(h->d_out.ensure((size_t)n * 4));
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((n + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
@@ -264,9 +278,23 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
       n, h->ncol, h->n_pbvi, h->d_vals.p, h->d_out.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
-  PP2D_CUDA(cudaMemcpyAsync(out, h->d_out.p, (size_t)n * 12 * sizeof(float),
+  PP2D_CUDA(cudaMemcpyAsync(out, h->d_out.p, (size_t)n * 4 * sizeof(float),
                             cudaMemcpyDeviceToHost, h->stream));
   PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  return PP2D_OK;
+}
+
+// <b, R(:,a)> for the 9 actions (tree:168-173) of the beliefs in the device
+// slot list `d_slots` (n entries): asynchronous, [n][9] into host `out`.
+int reward_dots_async(pp2d_pomdp* h, const int* d_slots, int n, float* out) {
+  PP2D_TRY(h->d_rew.ensure((size_t)n * kActions));
+  dim3 grid((n + 127) / 128, kActions);
+  pomdp_rewards_kernel<<<grid, 128, 0, h->stream>>>(h->HW, h->cap, d_slots, n, h->d_bel,
+                                                    h->d_sr, h->d_rew.p);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  PP2D_CUDA(cudaMemcpyAsync(out, h->d_rew.p, (size_t)n * kActions * sizeof(float),
+                            cudaMemcpyDeviceToHost, h->stream));
   return PP2D_OK;
 }
 
@@ -293,7 +321,6 @@ void init_vnode(VNodeH& v, int slot, uint8_t obs, float weight, int parent,
   v.heuristic = v.upper - v.lower;
   v.to_expand = self;
   v.depth = 0;
-  memcpy(v.reward, ev + 2, 9 * sizeof(float));
 }
 
 // Upload host beliefs ([n][HW]) into fresh slots and create the root V nodes.
@@ -312,13 +339,13 @@ int make_roots(pp2d_pomdp* h, std::vector<Tree*>& trees, const float* beliefs) {
                                                     h->d_rows.p, h->d_bel);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
-  std::vector<float> ev((size_t)n * 12);
+  std::vector<float> ev((size_t)n * 4);
   PP2D_TRY(evaluate_slots(h, slots, ev.data()));
   for (int i = 0; i < n; ++i) {
     Tree& t = *trees[i];
     t.v.emplace_back();
     t.root = (int)t.v.size() - 1;
-    init_vnode(t.v.back(), slots[i], 0, 0.0f, -1, ev.data() + (size_t)i * 12, t.root);
+    init_vnode(t.v.back(), slots[i], 0, 0.0f, -1, ev.data() + (size_t)i * 4, t.root);
     h->n_vnodes++;
   }
   return PP2D_OK;
@@ -336,7 +363,8 @@ void free_subtree_v(pp2d_pomdp* h, Tree& t, int vi) {
 }
 
 // One expansion round (SearchTree::expand, search_tree_cuda.cu:490-508) for
-// every tree in `trees`, all device work batched.
+// every tree in `trees`, all device work batched, per-tree host work spread
+// over the host cores (the trees are independent).
 int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
   struct Job { Tree* t; int v; };
   std::vector<Job> jobs;
@@ -357,22 +385,23 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
   // --- forward sampling (search_tree_cuda.cu:311-366) ---
   std::vector<int> slots(n);
   std::vector<float> draws((size_t)n * kActions * kSamples);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= 64)
   for (int i = 0; i < n; ++i) {
     slots[i] = jobs[i].t->v[jobs[i].v].slot;
+    float* d = draws.data() + (size_t)i * kActions * kSamples;
     for (int k = 0; k < kActions * kSamples; ++k)
-      draws[(size_t)i * kActions * kSamples + k] =
-          (float)jobs[i].t->rng.next() / ((float)2147483647 + 1.0f);
+      d[k] = (float)jobs[i].t->rng.next() / ((float)2147483647 + 1.0f);
   }
-  PP2D_TRY(h->d_slots.ensure(n));
+  PP2D_TRY(h->d_jobslots.ensure(n));
   PP2D_TRY(h->d_prefix.ensure((size_t)n * HW));
   PP2D_TRY(h->d_draws.ensure(draws.size()));
   PP2D_TRY(h->d_obs.ensure(draws.size()));
-  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
+  PP2D_CUDA(cudaMemcpyAsync(h->d_jobslots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   PP2D_CUDA(cudaMemcpyAsync(h->d_draws.p, draws.data(), draws.size() * sizeof(float),
                             cudaMemcpyHostToDevice, h->stream));
   pomdp_prefix_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
-      HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_prefix.p);
+      HW, h->cap, h->d_jobslots.p, n, h->d_bel, h->d_prefix.p);
   count_launch();
   const int nt = n * kActions * kSamples;
   pomdp_sample_kernel<<<(nt + 127) / 128, 128, 0, h->stream>>>(
@@ -383,53 +412,66 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
   std::vector<uint8_t> obs(draws.size());
   PP2D_CUDA(cudaMemcpyAsync(obs.data(), h->d_obs.p, obs.size(), cudaMemcpyDeviceToHost,
                             h->stream));
+  // reward of the 9 Q nodes of every expanded node (search_tree_cuda.cu:168-173)
+  std::vector<float> rewards((size_t)n * kActions);
+  PP2D_TRY(reward_dots_async(h, h->d_jobslots.p, n, rewards.data()));
   h->t_phase[0] += now_s() - t0; t0 = now_s();   // host draws + upload (async)
   PP2D_CUDA(cudaStreamSynchronize(h->stream));
-  h->t_phase[1] += now_s() - t0; t0 = now_s();   // prefix + sampling on device
+  h->t_phase[1] += now_s() - t0; t0 = now_s();   // prefix + sampling + rewards on device
   // --- unique observations per Q node (search_tree_cuda.cu:181-195) ---
-  std::vector<BayesItem> items;
-  struct Child { int job; uint8_t a, z; float w; int slot; };
-  std::vector<Child> kids;
-  for (int i = 0; i < n; ++i)
+  struct Child { uint8_t a, z; float w; };
+  std::vector<int> first(n + 1, 0);              // children of job i: [first[i], first[i+1])
+  std::vector<uint16_t> masks((size_t)n * kActions);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= 64)
+  for (int i = 0; i < n; ++i) {
+    int cnt = 0;
     for (int a = 0; a < kActions; ++a) {
-      int count[16] = {0};
       const uint8_t* o = obs.data() + ((size_t)i * kActions + a) * kSamples;
-      for (int k = 0; k < kSamples; ++k) count[o[k] & 15]++;
+      uint16_t m = 0;
+      for (int k = 0; k < kSamples; ++k) m |= (uint16_t)(1u << (o[k] & 15));
+      masks[(size_t)i * kActions + a] = m;
+      cnt += __builtin_popcount(m);
+    }
+    first[i + 1] = cnt;
+  }
+  for (int i = 0; i < n; ++i) first[i + 1] += first[i];
+  const int nk = first[n];
+  std::vector<int> kslots(nk);
+  for (int k = 0; k < nk; ++k) PP2D_TRY(alloc_slot(h, &kslots[k]));
+  std::vector<Child> kids(nk);
+  std::vector<BayesItem> items(nk);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= 64)
+  for (int i = 0; i < n; ++i) {
+    int k = first[i];
+    for (int a = 0; a < kActions; ++a) {
+      const uint8_t* o = obs.data() + ((size_t)i * kActions + a) * kSamples;
+      int count[16] = {0};
+      for (int s = 0; s < kSamples; ++s) count[o[s] & 15]++;
       for (int z = 0; z < 16; ++z) {
         if (!count[z]) continue;
-        Child c{i, (uint8_t)a, (uint8_t)z, (float)count[z] / (float)kSamples, -1};
-        PP2D_TRY(alloc_slot(h, &c.slot));
-        kids.push_back(c);
-        items.push_back(BayesItem{slots[i], c.slot, (uint8_t)a, (uint8_t)z});
+        kids[k] = Child{(uint8_t)a, (uint8_t)z, (float)count[z] / (float)kSamples};
+        items[k] = BayesItem{slots[i], kslots[k], (uint8_t)a, (uint8_t)z};
+        ++k;
       }
     }
-  const int nk = (int)kids.size();
+  }
   h->t_phase[2] += now_s() - t0; t0 = now_s();   // host: children lists
   // --- children beliefs: Bayes update + normalise (search_tree_cuda.cu:213-229)
-  PP2D_TRY(h->d_items.ensure(nk));
-  PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), nk * sizeof(BayesItem),
-                            cudaMemcpyHostToDevice, h->stream));
-  dim3 bgrid((nk + 31) / 32, (HW + 7) / 8);
-  pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
-                                                   h->d_items.p, nk, h->d_bel, h->d_bel);
-  count_launch();
-  PP2D_CUDA(cudaGetLastError());
-  h->n_bayes += nk;
-  std::vector<int> kslots(nk);
-  for (int i = 0; i < nk; ++i) kslots[i] = kids[i].slot;
-  PP2D_TRY(h->d_slots.ensure(nk));
-  PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, kslots.data(), nk * sizeof(int),
-                            cudaMemcpyHostToDevice, h->stream));
-  PP2D_TRY(normalize_slots(h, nk, nullptr));
+  PP2D_TRY(launch_bayes(h, items));
+  PP2D_TRY(launch_normalize(h, kslots));
   // --- bounds of the new V nodes (search_tree_cuda.cu:376-385) ---
-  std::vector<float> ev((size_t)nk * 12);
+  std::vector<float> ev((size_t)nk * 4);
   PP2D_TRY(evaluate_slots(h, kslots, ev.data()));
   h->t_phase[3] += now_s() - t0; t0 = now_s();   // bayes + normalise + bounds (device, synced)
   // --- host bookkeeping ---
-  int kpos = 0;
+#pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads()) if (n >= 64)
   for (int i = 0; i < n; ++i) {
     Tree& t = *jobs[i].t;
     const int vi = jobs[i].v;
+    int kpos = first[i];
+    const int kend = first[i + 1];
+    t.v.reserve(t.v.size() + (size_t)(kend - kpos));
+    t.q.reserve(t.q.size() + kActions);
     t.v[vi].children.resize(kActions);
     for (int a = 0; a < kActions; ++a) {
       t.q.emplace_back();
@@ -437,14 +479,13 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
       t.v[vi].children[a] = qi;
       t.q[qi].action = (uint8_t)a;
       t.q[qi].parent = vi;
-      t.q[qi].reward = t.v[vi].reward[a];
-      while (kpos < nk && kids[kpos].job == i && kids[kpos].a == a) {
+      t.q[qi].reward = rewards[(size_t)i * kActions + a];
+      while (kpos < kend && kids[kpos].a == a) {
         t.v.emplace_back();
         const int ci = (int)t.v.size() - 1;
-        init_vnode(t.v[ci], kids[kpos].slot, kids[kpos].z, kids[kpos].w, qi,
-                   ev.data() + (size_t)kpos * 12, ci);
+        init_vnode(t.v[ci], kslots[kpos], kids[kpos].z, kids[kpos].w, qi,
+                   ev.data() + (size_t)kpos * 4, ci);
         t.q[qi].children.push_back(ci);
-        h->n_vnodes++;
         ++kpos;
       }
       qnode_update(t, qi, h->gamma);
@@ -460,6 +501,7 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
     }
     t.expansions++;
   }
+  h->n_vnodes += (uint64_t)nk;
   h->t_phase[4] += now_s() - t0;                 // host: tree bookkeeping
   return PP2D_OK;
 }
@@ -527,6 +569,7 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();
+  h->d_rew.release(); h->d_jobslots.release();
   delete h;
 }
 
@@ -558,12 +601,10 @@ int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
   const int ncol = kColPbvi + (int)n_pbvi;
   const int ld = (ncol + kEvN - 1) / kEvN * kEvN;   // zero-padded to whole column tiles
   const size_t HW = (size_t)h->HW;
-  std::vector<float> mat(HW * ld, 0.0f), sr(HW * 9);
-  PP2D_CUDA(cudaMemcpy(sr.data(), h->d_sr, HW * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<float> mat(HW * ld, 0.0f);
   for (size_t s = 0; s < HW; ++s) {
     float* row = mat.data() + s * ld;
     memcpy(row + kColFib, fib_alphas + s * 9, 9 * sizeof(float));
-    memcpy(row + kColReward, sr.data() + s * 9, 9 * sizeof(float));
     for (uint32_t i = 0; i < n_pbvi; ++i) row[kColPbvi + i] = pbvi_alphas[(size_t)i * HW + s];
   }
   if (h->d_alpha) cudaFree(h->d_alpha);
@@ -701,7 +742,7 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     PP2D_TRY(h->d_slots.ensure(n));
     PP2D_TRY(h->d_rows.ensure((size_t)n * HW));
     PP2D_TRY(h->d_vals.ensure((size_t)n * h->ncol));
-    PP2D_TRY(h->d_out.ensure((size_t)n * 12));
+    PP2D_TRY(h->d_out.ensure((size_t)n * 4));
     PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, beliefs, (size_t)n * HW * sizeof(float),
                               cudaMemcpyHostToDevice, h->stream));
     PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
@@ -719,15 +760,15 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
                                                                 h->d_vals.p, h->d_out.p);
     count_launch();
     PP2D_CUDA(cudaGetLastError());
-    std::vector<float> hres((size_t)n * 12);
+    std::vector<float> hres((size_t)n * 4);
     PP2D_CUDA(cudaMemcpyAsync(hres.data(), h->d_out.p, hres.size() * sizeof(float),
                               cudaMemcpyDeviceToHost, h->stream));
     PP2D_CUDA(cudaStreamSynchronize(h->stream));
     for (uint32_t i = 0; i < n; ++i) {
       int packed;
-      memcpy(&packed, &hres[(size_t)i * 12 + 11], sizeof(int));
-      if (upper) upper[i] = hres[(size_t)i * 12];
-      if (lower) lower[i] = hres[(size_t)i * 12 + 1];
+      memcpy(&packed, &hres[(size_t)i * 4 + 2], sizeof(int));
+      if (upper) upper[i] = hres[(size_t)i * 4];
+      if (lower) lower[i] = hres[(size_t)i * 4 + 1];
       if (upper_action) upper_action[i] = h->fib_actions[packed & 0xff];
       if (lower_action) lower_action[i] = h->n_pbvi ? h->pbvi_actions[packed >> 8] : 0;
     }
@@ -911,7 +952,7 @@ int pp2d_tree_update(pp2d_tree* tt, uint8_t a, uint8_t z) {
     PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, &slot, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     PP2D_TRY(normalize_slots(h, 1, nullptr));
     std::vector<int> s1{slot};
-    float ev[12];
+    float ev[4];
     PP2D_TRY(evaluate_slots(h, s1, ev));
     t.v.emplace_back();
     root_v = (int)t.v.size() - 1;

@@ -35,7 +35,7 @@ namespace pp2d {
 
 constexpr int kSamples = 50;      // search_tree_cuda.cu:176
 constexpr int kActions = 9;
-constexpr int kColFib = 0, kColReward = 9, kColPbvi = 18;
+constexpr int kColFib = 0, kColPbvi = 9;   // columns of the bound matrix
 
 // glibc rand() (TYPE_3 additive feedback, what the planner's rand() is since
 // it never calls srand(): search_tree_cuda.cu:332).  Every query owns one
@@ -90,9 +90,9 @@ struct pp2d_pomdp {
   float gamma = 0.f;
   uint8_t* d_map = nullptr;
   float *d_tp = nullptr, *d_mp = nullptr, *d_sr = nullptr, *d_uniforms = nullptr;
-  // alpha matrix [HW][ld]: FIB | stage reward | PBVI
+  // bound matrix [HW][ld]: FIB | PBVI (zero padded to whole column tiles)
   float* d_alpha = nullptr;
-  int ld = 0, ncol = 18, n_pbvi = 0;
+  int ld = 0, ncol = 9, n_pbvi = 0;
   std::vector<uint8_t> fib_actions, pbvi_actions;
   bool have_alphas = false;
   // belief pool [HW][cap]
@@ -104,7 +104,9 @@ struct pp2d_pomdp {
   pp2d::DevBuf<pp2d::BayesItem> d_items;
   pp2d::DevBuf<float> d_prefix, d_draws, d_vals, d_rows, d_sums;
   pp2d::DevBuf<uint8_t> d_obs;
-  pp2d::DevBuf<float> d_out;               // 12 floats per evaluated belief
+  pp2d::DevBuf<float> d_out;               // 4 floats per evaluated belief
+  pp2d::DevBuf<float> d_rew;               // [n][9] reward dots of expanded nodes
+  pp2d::DevBuf<int> d_jobslots;            // slots of the nodes being expanded
   cudaStream_t stream = nullptr;
   uint64_t n_bayes = 0, n_vnodes = 0;
   double t_phase[6] = {0, 0, 0, 0, 0, 0};   // PP2D_POMDP_PROFILE=1: seconds per phase

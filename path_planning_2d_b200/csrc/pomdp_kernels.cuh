@@ -261,8 +261,10 @@ pomdp_sample_kernel(int H, int W, int n, int S,
 // evaluated exactly like std::inner_product(b, b+HW, alpha, 0.0f) on the
 // reference's host (fib:289-292, pbvi:689-694, tree:172): one accumulator per
 // (i, j), cells in ascending order, float multiply rounded, then float add
-// rounded (no FMA).  alpha is [HW][ld] with the columns
-//   0..8 FIB, 9..17 stage reward, 18..18+N-1 PBVI.
+// rounded (no FMA).  alpha is [HW][ld]: the bound matrix has the columns
+//   0..8 FIB, 9..9+N-1 PBVI
+// (509 -> 512 = four column tiles for the reference's 500 vectors); ld is a
+// multiple of the column tile and the padding is zero.
 // CTA tile 128 beliefs x 128 columns, 256 threads, 8x8 accumulators each
 // (4 LDS.128 per 128 math instructions: the 4x4 version was bound by the
 // shared-memory pipe), K chunks of 16 cells double-buffered with cp.async.
@@ -350,11 +352,41 @@ pomdp_values_kernel(int HW, int cap, int ld, int ncol,
   }
 }
 
+// tree:168-173: reward[i][a] = inner_product(b_i, R(:,a), 0.0f) for the nodes
+// being expanded: one thread per (belief, action), the same sequential
+// multiply-then-add chain as pomdp_values_kernel; loads issued 8 cells ahead
+// of the chain.  stage_reward is the reference table [HW][9].
+__global__ void __launch_bounds__(128)
+pomdp_rewards_kernel(int HW, int cap, const int* __restrict__ slots, int n,
+                     const float* __restrict__ bel, const float* __restrict__ stage_reward,
+                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y;
+  if (i >= n) return;
+  const float* col = bel + slots[i];
+  const float* r = stage_reward + a;
+  float acc = 0.0f;
+  int s = 0;
+  for (; s + 8 <= HW; s += 8) {
+    float b[8], w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      b[j] = col[(size_t)(s + j) * cap];
+      w[j] = __ldg(r + (size_t)(s + j) * 9);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, __fmul_rn(b[j], w[j]));
+  }
+  for (; s < HW; ++s)
+    acc = __fadd_rn(acc, __fmul_rn(col[(size_t)s * cap], __ldg(r + (size_t)s * 9)));
+  out[(size_t)i * 9 + a] = acc;
+}
+
 // Bounds of every evaluated belief from its row of values: first maximum over
 // the FIB columns (upper, fib:294-296) and over the PBVI columns (lower,
 // pbvi:696-698), as std::max_element does.  Packed per belief:
-//   out[i*12 + 0] upper, [1] lower, [2..10] <b, R(:,a)>, [11] = fib index |
-//   pbvi index << 8 (as int bits).
+//   out[i*4 + 0] upper, [1] lower, [2] = fib index | pbvi index << 8 (as int
+//   bits).
 __global__ void pomdp_bounds_kernel(int n, int ncol, int n_pbvi,
                                     const float* __restrict__ vals,
                                     float* __restrict__ out) {
@@ -364,13 +396,12 @@ __global__ void pomdp_bounds_kernel(int n, int ncol, int n_pbvi,
   int bu = 0;
   for (int a = 1; a < 9; ++a) if (v[bu] < v[a]) bu = a;
   int bl = 0;
-  for (int j = 1; j < n_pbvi; ++j) if (v[18 + bl] < v[18 + j]) bl = j;
-  float* o = out + (size_t)i * 12;
+  for (int j = 1; j < n_pbvi; ++j) if (v[9 + bl] < v[9 + j]) bl = j;
+  float* o = out + (size_t)i * 4;
   o[0] = v[bu];
-  o[1] = n_pbvi > 0 ? v[18 + bl] : 0.0f;
-#pragma unroll
-  for (int a = 0; a < 9; ++a) o[2 + a] = v[9 + a];
-  o[11] = __int_as_float(bu | (bl << 8));
+  o[1] = n_pbvi > 0 ? v[9 + bl] : 0.0f;
+  o[2] = __int_as_float(bu | (bl << 8));
+  o[3] = 0.0f;
 }
 
 // ------------------------------------------------ FIB solver ("next" #1) ----
