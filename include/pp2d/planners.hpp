@@ -206,10 +206,11 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
     pp2d_pomdp_destroy(pomdp_);
   }
 
-  // src/pomdp/path_planning_2d.cu:80-166, read_data_from_file = true path:
-  // the alpha vectors come from the text files the reference's save_data
-  // service writes (fib_alphas, fib_actions, pbvi_alphas, pbvi_actions) in
-  // `data_dir`.
+  // src/pomdp/path_planning_2d.cu:80-166.  read_data_from_file = false: the
+  // FIB and PBVI offline solvers run on the GPU (path_planning_2d.cu:109-125);
+  // true: the alpha vectors come from the text files the reference's
+  // save_data service writes (fib_alphas, fib_actions, pbvi_alphas,
+  // pbvi_actions) in `data_dir`.
   bool initialize() override {
     if (!loadParameters()) {
       std::fprintf(stderr, "Cannot load all required parameters...\n");
@@ -230,11 +231,21 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
     initial_belief.resize(grid_map.size());
     for (size_t i = 0; i < grid_map.size(); ++i) initial_belief[i] = (1.0f - grid_map[i]) / sum;
     if (!read_from_file) {
-      std::fprintf(stderr, "the FIB / PBVI solvers are not part of this build; "
-                           "set read_data_from_file\n");
+      const size_t n = (size_t)map_height * map_width;
+      // fastInformedBound (fast_informed_bound_cuda.cu:206-276)
+      fib_alphas.resize(n * 9);
+      fib_actions.resize(9);
+      PP2D_CHECK(pp2d_pomdp_solve_fib(pomdp_, fib_alphas.data(), fib_actions.data(),
+                                      &fib_sweeps, 0));
+      // pointBasedValueIteration (point_based_value_iteration_cuda.cu:643-676);
+      // rand() of a fresh process, as in the reference node
+      pbvi_alphas.resize((size_t)belief_set_size * n);
+      pbvi_actions.resize(belief_set_size);
+      PP2D_CHECK(pp2d_pomdp_solve_pbvi(pomdp_, initial_belief.data(), belief_set_size, 1, 0,
+                                       nullptr, pbvi_alphas.data(), pbvi_actions.data()));
+    } else if (!loadFibDataFromFile() || !loadPbviDataFromFile()) {
       return false;
     }
-    if (!loadFibDataFromFile() || !loadPbviDataFromFile()) return false;
     PP2D_CHECK(pp2d_pomdp_set_alphas(pomdp_, fib_alphas.data(), fib_actions.data(),
                                      pbvi_alphas.data(), pbvi_actions.data(),
                                      belief_set_size));
@@ -271,7 +282,26 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
            saveRows(dir + "/model_data_stage_reward", sr, 9);
   }
 
+  // saveFibDataToFile / savePbviDataToFile (fast_informed_bound_cuda.cu:343-360,
+  // point_based_value_iteration_cuda.cu:747-766): "%15.8f" rows, "%10u" actions.
+  bool saveFibDataToFile(const std::string& dir) {
+    return saveRows(dir + "/fib_alphas", fib_alphas, 9) &&
+           saveBytes(dir + "/fib_actions", fib_actions);
+  }
+  bool savePbviDataToFile(const std::string& dir) {
+    return saveRows(dir + "/pbvi_alphas", pbvi_alphas, (int)((size_t)map_height * map_width)) &&
+           saveBytes(dir + "/pbvi_actions", pbvi_actions);
+  }
+  // saveDataCallback (src/pomdp/path_planning_2d.cu:259-273)
+  bool saveDataCallback(const std::string& dir) {
+    return saveModelDataToFile(dir) && saveFibDataToFile(dir) && savePbviDataToFile(dir);
+  }
+
   std::vector<float> initial_belief;
+  uint32_t fib_sweeps = 0;
+  const std::vector<float>& fibAlphas() const { return fib_alphas; }
+  const std::vector<float>& pbviAlphas() const { return pbvi_alphas; }
+  const std::vector<uint8_t>& pbviActions() const { return pbvi_actions; }
   float last_reward = 0.0f;
   pp2d_pomdp* handle() { return pomdp_; }
 
@@ -313,6 +343,13 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
       if (std::fscanf(f, "%u", &u) != 1) { std::fclose(f); return false; }
       x = (uint8_t)u;
     }
+    std::fclose(f);
+    return true;
+  }
+  static bool saveBytes(const std::string& path, const std::vector<uint8_t>& v) {
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return false;
+    for (uint8_t x : v) std::fprintf(f, "%10u\n", (unsigned)x);
     std::fclose(f);
     return true;
   }

@@ -180,13 +180,13 @@ static int launch_sweep(pp2d_mdp* h) {
   int rpu = h->rows_per_unit;
   if (rpu <= 0) {
     // Units are equal-sized, so the launch is sized to fill exactly
-    // `waves` full waves of resident CTAs (8 warps = 8 units per CTA): one
+    // `waves` full waves of resident CTAs (one unit per warp): one
     // more CTA than that would run alone in an extra wave.
     int ctas_per_sm = 0;
     PP2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY, P2P>, 256, 0));
+        &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY, P2P>, kWarpsPerCta * 32, 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    const long slots = (long)h->sm_count * ctas_per_sm * 8;   // resident warps
+    const long slots = (long)h->sm_count * ctas_per_sm * kWarpsPerCta;   // resident warps
     long rb = slots * h->waves / p.n_strips;                  // floor
     if (rb < 1) rb = 1;
     rpu = (int)((rows + rb - 1) / rb);
@@ -227,7 +227,7 @@ static int launch_sweep(pp2d_mdp* h) {
     p.p2p_debug = (unsigned int)h->p2p_debug;
     p.edge_rows = h->p2p_edge_rows;
   }
-  const int warps_per_cta = 8;
+  const int warps_per_cta = kWarpsPerCta;
   const int grid = (p.n_units + warps_per_cta - 1) / warps_per_cta;
   mdp_sweep_kernel<T, CW, POLICY, P2P><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);

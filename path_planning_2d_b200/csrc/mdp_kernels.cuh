@@ -53,6 +53,19 @@ constexpr int kPrefetch = 2;  // CW == 1 path: rows held in registers ahead of u
 constexpr int kRing = PP2D_KRING;  // CW >= 2 path: cp.async ring slots per lane (1, 2, 3 or 6)
 constexpr int kPadLeft = 8;   // zero columns left of x = 0 (32 B)
 constexpr int kLutFloat4 = 4 * 16 * 8;  // 4 action pairs x 16 rows x 8 copies
+// Tuning knobs (tools/sweep_variants.py builds alternates): how the minimum
+// over the 9 actions is taken, warps per CTA and resident CTAs per SM of the
+// fused kernel.
+#ifndef PP2D_MINV
+#define PP2D_MINV 0
+#endif
+#ifndef PP2D_WARPS
+#define PP2D_WARPS 8
+#endif
+#ifndef PP2D_MINCTAS
+#define PP2D_MINCTAS 2
+#endif
+constexpr int kWarpsPerCta = PP2D_WARPS;
 
 // Code bits.
 constexpr uint32_t kCodeRingMask = 0x3FFu;   // bits 0..9
@@ -141,7 +154,20 @@ __device__ __forceinline__ float backup(float j0, float j1, float j2, float j3,
     act = a;
     return best;
   } else {
+#if PP2D_MINV == 1
+    return fminf(fminf(fminf(c0, c1), fminf(c2, c3)),
+                 fminf(fminf(fminf(c4, c5), fminf(c6, c7)), c8));
+#elif PP2D_MINV == 2
+    // Costs are finite and >= +0, so their order as floats is their order as
+    // unsigned integers: the 3-input integer minimum (VIMNMX3) gives the same
+    // bits as FMNMX3.
+    const uint32_t m0 = __vimin3_u32(__float_as_uint(c0), __float_as_uint(c1), __float_as_uint(c2));
+    const uint32_t m1 = __vimin3_u32(__float_as_uint(c3), __float_as_uint(c4), __float_as_uint(c5));
+    const uint32_t m2 = __vimin3_u32(__float_as_uint(c6), __float_as_uint(c7), __float_as_uint(c8));
+    return __uint_as_float(__vimin3_u32(m0, m1, m2));
+#else
     return min3(min3(c0, c1, c2), min3(c3, c4, c5), min3(c6, c7, c8));
+#endif
   }
 }
 
@@ -536,16 +562,16 @@ struct Sweeper {
   }
 };
 
-// One warp per (column strip, row block) unit; 8 warps per CTA.
+// One warp per (column strip, row block) unit; kWarpsPerCta warps per CTA.
 template <int T, int CW, bool POLICY, bool P2P = false>
-__global__ void __launch_bounds__(256, (T == 2 && CW == 2) ? 2 : 1)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (T == 2 && CW == 2) ? PP2D_MINCTAS : 1)
 mdp_sweep_kernel(const SweepParams p) {
   // The table must start on a 2 KB boundary of the shared window so that the
   // row offset (bits 7..10) and the lane replica (bits 4..6) can be OR-ed
   // into the base.  The window itself starts at 1 KB (system reserved), so
   // the alignment is done at run time on an over-allocated buffer.
   using G = StripGeom<T, CW>;
-  constexpr int kWarps = 8;
+  constexpr int kWarps = kWarpsPerCta;
   __shared__ __align__(16) unsigned char
       lut_raw[kLutFloat4 * 16 + 2048 + kWarps * G::kRingBytesPerWarp];
   const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(lut_raw);

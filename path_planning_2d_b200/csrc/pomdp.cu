@@ -170,6 +170,26 @@ int launch_bayes(pp2d_pomdp* h, const std::vector<BayesItem>& items) {
   return PP2D_OK;
 }
 
+int launch_bayes_groups(pp2d_pomdp* h, const std::vector<BayesItem>& items,
+                        const std::vector<int>& first) {
+  const int n = (int)items.size(), ng = (int)first.size() - 1;
+  if (n == 0 || ng <= 0) return PP2D_OK;
+  PP2D_TRY(h->d_items.ensure(n));
+  PP2D_TRY(h->d_first.ensure(ng + 1));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), n * sizeof(BayesItem),
+                            cudaMemcpyHostToDevice, h->stream));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_first.p, first.data(), (ng + 1) * sizeof(int),
+                            cudaMemcpyHostToDevice, h->stream));
+  dim3 grid((ng + 31) / 32, (h->HW + 7) / 8);
+  pomdp_bayes_group_kernel<<<grid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+                                                        h->d_items.p, h->d_first.p, ng,
+                                                        h->d_bel, h->d_bel);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  h->n_bayes += n;
+  return PP2D_OK;
+}
+
 // tree:226-229 on the listed columns: sequential sum, then divide.
 int launch_normalize(pp2d_pomdp* h, const std::vector<int>& slots) {
   const int n = (int)slots.size();
@@ -440,10 +460,13 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
   for (int k = 0; k < nk; ++k) PP2D_TRY(alloc_slot(h, &kslots[k]));
   std::vector<Child> kids(nk);
   std::vector<BayesItem> items(nk);
+  std::vector<int> gfirst((size_t)n * kActions + 1);   // children of Q node (i, a)
+  gfirst[(size_t)n * kActions] = nk;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= 64)
   for (int i = 0; i < n; ++i) {
     int k = first[i];
     for (int a = 0; a < kActions; ++a) {
+      gfirst[(size_t)i * kActions + a] = k;
       const uint8_t* o = obs.data() + ((size_t)i * kActions + a) * kSamples;
       int count[16] = {0};
       for (int s = 0; s < kSamples; ++s) count[o[s] & 15]++;
@@ -457,7 +480,7 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
   }
   h->t_phase[2] += now_s() - t0; t0 = now_s();   // host: children lists
   // --- children beliefs: Bayes update + normalise (search_tree_cuda.cu:213-229)
-  PP2D_TRY(launch_bayes(h, items));
+  PP2D_TRY(launch_bayes_groups(h, items, gfirst));
   PP2D_TRY(launch_normalize(h, kslots));
   // --- bounds of the new V nodes (search_tree_cuda.cu:376-385) ---
   std::vector<float> ev((size_t)nk * 4);
@@ -569,7 +592,7 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();
-  h->d_rew.release(); h->d_jobslots.release();
+  h->d_rew.release(); h->d_jobslots.release(); h->d_first.release();
   delete h;
 }
 
@@ -802,8 +825,10 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     const size_t gn = std::min<size_t>(group, n - g0);
     std::vector<Tree> store(gn);
     std::vector<Tree*> trees(gn);
+    double tr = now_s();
     for (size_t i = 0; i < gn; ++i) { store[i].rng.seed(1); trees[i] = &store[i]; }
     PP2D_TRY(make_roots(h, trees, beliefs + g0 * (size_t)h->HW));
+    h->t_phase[5] += now_s() - tr;               // roots: upload + bounds
     for (uint32_t it = 0; it < max_iter; ++it) {
       std::vector<Tree*> active;
       for (Tree* t : trees)
@@ -811,6 +836,7 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
       if (active.empty()) break;
       PP2D_TRY(expand_round(h, active));
     }
+    tr = now_s();
     for (size_t i = 0; i < gn; ++i) {
       float r;
       best_action(store[i], &actions[g0 + i], &r);
@@ -823,11 +849,13 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
       }
       free_subtree_v(h, store[i], store[i].root);
     }
+    h->t_phase[6] += now_s() - tr;               // actions out, slots back
   }
   if (getenv("PP2D_POMDP_PROFILE")) {
     fprintf(stderr, "pp2d pomdp phases [s]: draws %.4f  sample(dev) %.4f  kids %.4f  "
-            "bayes+norm+bounds(dev) %.4f  bookkeeping %.4f\n", h->t_phase[0], h->t_phase[1],
-            h->t_phase[2], h->t_phase[3], h->t_phase[4]);
+            "bayes+norm+bounds(dev) %.4f  bookkeeping %.4f  roots %.4f  finish %.4f\n",
+            h->t_phase[0], h->t_phase[1], h->t_phase[2], h->t_phase[3], h->t_phase[4],
+            h->t_phase[5], h->t_phase[6]);
     for (double& t : h->t_phase) t = 0;
   }
   return PP2D_OK;

@@ -130,6 +130,45 @@ pomdp_bayes_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
   bel_out[(size_t)cell * cap + it.dst] = p;
 }
 
+// The children of one Q node (same parent belief, same action) differ only in
+// the observation: the predicted belief sum_s P(s,u,s') b(s) is computed once
+// per (Q node, cell) and multiplied by the likelihood of every observation
+// that got a child.  Same arithmetic per child as pomdp_bayes_kernel.
+// group g: children items[first[g] .. first[g+1]) (all with src / act of the
+// group's first item); threadIdx.x runs over groups, so the 9 Q nodes of one
+// expanded node read the same belief addresses.
+__global__ void __launch_bounds__(256)
+pomdp_bayes_group_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
+                         const float* __restrict__ meas_prob,
+                         const BayesItem* __restrict__ items,
+                         const int* __restrict__ first, int n_groups,
+                         const float* bel_in, float* bel_out) {
+  const int g = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int cell = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (g >= n_groups || cell >= H * W) return;
+  const int k0 = first[g], k1 = first[g + 1];
+  if (k0 == k1) return;
+  const BayesItem it = items[k0];
+  const int x = cell % W, y = cell / W;
+  float p = 0.0f;
+#pragma unroll
+  for (int s = 0; s < 9; ++s) {
+    const int sx = x + s % 3 - 1, sy = y + s / 3 - 1;
+    if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
+    const size_t sidx = (size_t)sy * W + sx;
+    const float tp = __ldg(trans_prob + 81 * sidx + 9 * it.act + (8 - s));
+    const float b = bel_in[sidx * cap + it.src];
+    if (s < 8) p = fma_ftz(tp, b, p);
+    else p = add_ftz(p, mul_ftz(tp, b));
+  }
+  const float* L = meas_prob + 16 * (size_t)cell;
+  bel_out[(size_t)cell * cap + it.dst] = mul_ftz(p, __ldg(L + it.obs));
+  for (int k = k0 + 1; k < k1; ++k) {
+    const BayesItem c = items[k];
+    bel_out[(size_t)cell * cap + c.dst] = mul_ftz(p, __ldg(L + c.obs));
+  }
+}
+
 // ---------------------------------------------------------------- B3 -------
 // tree:226-229: sum = accumulate(b, 0.0f) sequentially, then b /= sum (IEEE
 // division).  One thread per belief column.

@@ -68,5 +68,25 @@ int main(int argc, char** argv) {
     std::printf("RESULT a0=%u r0=%08x a1=%u r1=%08x\n", a0, r0, a1, r1);
     return 0;
   }
+  if (mode == "pomdp_solve" && argc >= 9) {
+    // read_data_from_file = false: FIB + PBVI solved on the GPU at start-up
+    // (src/pomdp/path_planning_2d.cu:109-125), then save_data.
+    Params p{{"map_path", argv[2]}, {"goal_x", argv[3]}, {"goal_y", argv[4]},
+             {"discount_factor", argv[5]}, {"map_resolution", "0.2"},
+             {"read_data_from_file", "false"}, {"belief_set_size", argv[6]},
+             {"max_search_tree_depth", "50"}, {"max_online_iteration", argv[7]}};
+    PomdpPathPlanning2d planner(p);
+    if (!planner.initialize()) { std::printf("INIT_FAILED\n"); return 0; }
+    if (!planner.saveDataCallback(argv[8])) { std::printf("SAVE_FAILED\n"); return 0; }
+    Belief b;
+    b.belief = planner.initial_belief;
+    const uint8_t a0 = planner.beliefCallback(b);
+    std::printf("RESULT fib_sweeps=%u fib=%016" PRIx64 " pbvi=%016" PRIx64 " acts=%016" PRIx64
+                " a0=%u\n", planner.fib_sweeps,
+                fnv(planner.fibAlphas().data(), planner.fibAlphas().size() * 4),
+                fnv(planner.pbviAlphas().data(), planner.pbviAlphas().size() * 4),
+                fnv(planner.pbviActions().data(), planner.pbviActions().size()), a0);
+    return 0;
+  }
   return 2;
 }

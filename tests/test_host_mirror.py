@@ -126,3 +126,30 @@ def test_cpp_pomdp_planner_matches_oracle(exe, tmp_path):
     assert int(kv["a0"]) == a0 and int(kv["a1"]) == a1
     assert kv["r0"] == "%08x" % np.float32(r0).view(np.uint32)
     assert kv["r1"] == "%08x" % np.float32(r1).view(np.uint32)
+
+
+@pytest.mark.gpu
+def test_cpp_pomdp_planner_solves_offline_like_the_reference(exe, tmp_path):
+    """read_data_from_file=false path: PomdpPathPlanning2d::initialize runs the
+    FIB and PBVI solvers (GPU); the alpha vectors must be the ones the
+    reference's own solvers produced (tests/golden/pbvi_ref_*.npz), and
+    save_data must write them in the reference's text format."""
+    import cv2
+    g = np.load(os.path.join(cases.GOLDEN, "pbvi_ref_map_10x10_g0.8_n40.npz"))
+    png = str(tmp_path / "map.png")
+    cv2.imwrite(png, np.where(g["grid"] == 1, 0, 255).astype(np.uint8))
+    out = subprocess.run([exe, "pomdp_solve", png, str(int(g["goal"][0])), str(int(g["goal"][1])),
+                          "0.8", "40", "4", str(tmp_path)], capture_output=True, text=True)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+    assert line, out.stdout + out.stderr
+    kv = dict(t.split("=") for t in line[0].split()[1:])
+    assert kv["fib"] == fnv(g["fib"].tobytes())
+    assert kv["pbvi"] == fnv(g["pbvi"].tobytes())
+    assert kv["acts"] == fnv(g["pbvi_actions"].tobytes())
+    saved = np.loadtxt(tmp_path / "pbvi_alphas", dtype=np.float64).reshape(g["pbvi"].shape)
+    want = np.array([[float("%15.8f" % v) for v in row] for row in g["pbvi"]])
+    assert np.array_equal(saved, want)
+    assert np.array_equal(np.loadtxt(tmp_path / "pbvi_actions", dtype=np.int64),
+                          g["pbvi_actions"].astype(np.int64))
+    assert np.loadtxt(tmp_path / "fib_alphas").shape == (g["grid"].size, 9)
+    assert (tmp_path / "model_data_trans_prob").exists()
