@@ -125,9 +125,11 @@ int pool_reserve(pp2d_pomdp* h, size_t slots_wanted) {
   PP2D_CUDA(cudaMalloc(&nb, cap * (size_t)h->HW * sizeof(float)));
   const size_t old_cap = h->d_bel ? (size_t)h->cap : 0;
   if (old_cap && h->free_slots.size() != old_cap) {
-    cudaError_t e = cudaMemcpy2DAsync(nb, cap * sizeof(float), h->d_bel, old_cap * sizeof(float),
-                                      old_cap * sizeof(float), (size_t)h->HW,
-                                      cudaMemcpyDeviceToDevice, h->stream);
+    cudaError_t e = cudaDeviceSynchronize();     // every stream that touches the pool
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(nb, cap * sizeof(float), h->d_bel, old_cap * sizeof(float),
+                            old_cap * sizeof(float), (size_t)h->HW, cudaMemcpyDeviceToDevice,
+                            h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
       cudaFree(nb);
@@ -382,117 +384,235 @@ void free_subtree_v(pp2d_pomdp* h, Tree& t, int vi) {
   if (t.v[vi].slot >= 0) { h->free_slots.push_back(t.v[vi].slot); t.v[vi].slot = -1; }
 }
 
-// One expansion round (SearchTree::expand, search_tree_cuda.cu:490-508) for
-// every tree in `trees`, all device work batched, per-tree host work spread
-// over the host cores (the trees are independent).
-int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
+// Page-locked host buffer: source / target of the asynchronous copies of a
+// round (a pageable buffer would make cudaMemcpyAsync wait for the stream).
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return PP2D_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = n + n / 2 + 64;
+    PP2D_CUDA(cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault));
+    cap = want;
+    return PP2D_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Everything one expansion round of a group of trees needs, kept between
+// rounds.  A batch is planned as TWO such groups in lock-step so that the host
+// work of one (random draws, child lists, tree bookkeeping) overlaps the
+// device work of the other.
+struct RoundCtx {
   struct Job { Tree* t; int v; };
+  struct Child { uint8_t a, z; float w; };
   std::vector<Job> jobs;
+  int n = 0, nk = 0;
+  PinnedBuf<int> slots, kslots, gfirst;
+  PinnedBuf<float> draws, rewards, ev;
+  PinnedBuf<BayesItem> items;
+  PinnedBuf<uint8_t> obs;
+  std::vector<int> first;
+  std::vector<Child> kids;
+  DevBuf<int> d_jobslots, d_kslots, d_gfirst;
+  DevBuf<float> d_prefix, d_draws, d_rew, d_sums, d_vals, d_out;
+  DevBuf<uint8_t> d_obs;
+  DevBuf<BayesItem> d_items;
+  cudaEvent_t e1 = nullptr, e2 = nullptr;
+  cudaStream_t stream = nullptr;     // own stream: the tail of one group's launches
+                                     // overlaps the other group's
+  ~RoundCtx() {
+    slots.release(); kslots.release(); gfirst.release(); draws.release(); rewards.release();
+    ev.release(); items.release(); obs.release();
+    d_jobslots.release(); d_kslots.release(); d_gfirst.release(); d_prefix.release();
+    d_draws.release(); d_rew.release(); d_sums.release(); d_vals.release(); d_out.release();
+    d_obs.release(); d_items.release();
+    if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+RoundCtx* round_ctx(pp2d_pomdp* h, int which) {
+  if (!h->round_ctx[which]) {
+    RoundCtx* c = new RoundCtx;
+    cudaEventCreateWithFlags(&c->e1, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->e2, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    h->round_ctx[which] = c;
+  }
+  return static_cast<RoundCtx*>(h->round_ctx[which]);
+}
+
+// Stage 1 of an expansion round (SearchTree::expand, search_tree_cuda.cu:490-508)
+// for every tree in `trees`: the nodes to expand, their random draws, then
+// -- enqueued, not waited for -- forward sampling (search_tree_cuda.cu:311-366)
+// and the reward of the 9 new Q nodes (search_tree_cuda.cu:168-173).
+int round_stage1(pp2d_pomdp* h, RoundCtx& c, const std::vector<Tree*>& trees) {
+  double t0 = now_s();
+  c.jobs.clear();
   for (Tree* t : trees) {
     if (t->dead) continue;
     const int v = t->v[t->root].to_expand;
     if (v < 0) { t->dead = true; continue; }
     if (!t->v[v].children.empty()) {            // re-expansion (leak in the ref)
-      for (int c : t->v[v].children) free_subtree_q(h, *t, c);
+      for (int q : t->v[v].children) free_subtree_q(h, *t, q);
       t->v[v].children.clear();
     }
-    jobs.push_back({t, v});
+    c.jobs.push_back({t, v});
   }
-  const int n = (int)jobs.size();
+  const int n = c.n = (int)c.jobs.size();
+  c.nk = 0;
   if (n == 0) return PP2D_OK;
   const int HW = h->HW;
-  double t0 = now_s();
-  // --- forward sampling (search_tree_cuda.cu:311-366) ---
-  std::vector<int> slots(n);
-  std::vector<float> draws((size_t)n * kActions * kSamples);
+  const size_t nd = (size_t)n * kActions * kSamples;
+  PP2D_TRY(c.slots.ensure(n));
+  PP2D_TRY(c.draws.ensure(nd));
+  PP2D_TRY(c.obs.ensure(nd));
+  PP2D_TRY(c.rewards.ensure((size_t)n * kActions));
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= 64)
   for (int i = 0; i < n; ++i) {
-    slots[i] = jobs[i].t->v[jobs[i].v].slot;
-    float* d = draws.data() + (size_t)i * kActions * kSamples;
+    c.slots.p[i] = c.jobs[i].t->v[c.jobs[i].v].slot;
+    float* d = c.draws.p + (size_t)i * kActions * kSamples;
     for (int k = 0; k < kActions * kSamples; ++k)
-      d[k] = (float)jobs[i].t->rng.next() / ((float)2147483647 + 1.0f);
+      d[k] = (float)c.jobs[i].t->rng.next() / ((float)2147483647 + 1.0f);
   }
-  PP2D_TRY(h->d_jobslots.ensure(n));
-  PP2D_TRY(h->d_prefix.ensure((size_t)n * HW));
-  PP2D_TRY(h->d_draws.ensure(draws.size()));
-  PP2D_TRY(h->d_obs.ensure(draws.size()));
-  PP2D_CUDA(cudaMemcpyAsync(h->d_jobslots.p, slots.data(), n * sizeof(int),
-                            cudaMemcpyHostToDevice, h->stream));
-  PP2D_CUDA(cudaMemcpyAsync(h->d_draws.p, draws.data(), draws.size() * sizeof(float),
-                            cudaMemcpyHostToDevice, h->stream));
-  pomdp_prefix_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
-      HW, h->cap, h->d_jobslots.p, n, h->d_bel, h->d_prefix.p);
+  PP2D_TRY(c.d_jobslots.ensure(n));
+  PP2D_TRY(c.d_prefix.ensure((size_t)n * HW));
+  PP2D_TRY(c.d_draws.ensure(nd));
+  PP2D_TRY(c.d_obs.ensure(nd));
+  PP2D_TRY(c.d_rew.ensure((size_t)n * kActions));
+  PP2D_CUDA(cudaMemcpyAsync(c.d_jobslots.p, c.slots.p, n * sizeof(int),
+                            cudaMemcpyHostToDevice, c.stream));
+  PP2D_CUDA(cudaMemcpyAsync(c.d_draws.p, c.draws.p, nd * sizeof(float),
+                            cudaMemcpyHostToDevice, c.stream));
+  pomdp_prefix_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(
+      HW, h->cap, c.d_jobslots.p, n, h->d_bel, c.d_prefix.p);
   count_launch();
-  const int nt = n * kActions * kSamples;
-  pomdp_sample_kernel<<<(nt + 127) / 128, 128, 0, h->stream>>>(
-      h->H, h->W, n, kSamples, h->d_tp, h->d_mp, h->d_prefix.p, h->d_draws.p,
-      h->d_uniforms, h->d_obs.p);
+  const int nt = (int)nd;
+  pomdp_sample_kernel<<<(nt + 127) / 128, 128, 0, c.stream>>>(
+      h->H, h->W, n, kSamples, h->d_tp, h->d_mp, c.d_prefix.p, c.d_draws.p,
+      h->d_uniforms, c.d_obs.p);
+  count_launch();
+  dim3 rgrid((n + 127) / 128, kActions);
+  pomdp_rewards_kernel<<<rgrid, 128, 0, c.stream>>>(HW, h->cap, c.d_jobslots.p, n, h->d_bel,
+                                                     h->d_sr, c.d_rew.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
-  std::vector<uint8_t> obs(draws.size());
-  PP2D_CUDA(cudaMemcpyAsync(obs.data(), h->d_obs.p, obs.size(), cudaMemcpyDeviceToHost,
-                            h->stream));
-  // reward of the 9 Q nodes of every expanded node (search_tree_cuda.cu:168-173)
-  std::vector<float> rewards((size_t)n * kActions);
-  PP2D_TRY(reward_dots_async(h, h->d_jobslots.p, n, rewards.data()));
-  h->t_phase[0] += now_s() - t0; t0 = now_s();   // host draws + upload (async)
-  PP2D_CUDA(cudaStreamSynchronize(h->stream));
-  h->t_phase[1] += now_s() - t0; t0 = now_s();   // prefix + sampling + rewards on device
-  // --- unique observations per Q node (search_tree_cuda.cu:181-195) ---
-  struct Child { uint8_t a, z; float w; };
-  std::vector<int> first(n + 1, 0);              // children of job i: [first[i], first[i+1])
-  std::vector<uint16_t> masks((size_t)n * kActions);
+  PP2D_CUDA(cudaMemcpyAsync(c.obs.p, c.d_obs.p, nd, cudaMemcpyDeviceToHost, c.stream));
+  PP2D_CUDA(cudaMemcpyAsync(c.rewards.p, c.d_rew.p, (size_t)n * kActions * sizeof(float),
+                            cudaMemcpyDeviceToHost, c.stream));
+  PP2D_CUDA(cudaEventRecord(c.e1, c.stream));
+  h->t_phase[0] += now_s() - t0;                 // host: draws, enqueue
+  return PP2D_OK;
+}
+
+// Stage 2: unique observations per Q node (search_tree_cuda.cu:181-195), then
+// -- enqueued -- the children beliefs (Bayes update + normalise,
+// search_tree_cuda.cu:213-229) and their bounds (search_tree_cuda.cu:376-385).
+int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
+  const int n = c.n;
+  if (n == 0) return PP2D_OK;
+  double t0 = now_s();
+  PP2D_CUDA(cudaEventSynchronize(c.e1));
+  h->t_phase[1] += now_s() - t0; t0 = now_s();   // wait: sampling + rewards on device
+  const int HW = h->HW;
+  c.first.assign(n + 1, 0);                      // children of job i: [first[i], first[i+1])
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= 64)
   for (int i = 0; i < n; ++i) {
     int cnt = 0;
     for (int a = 0; a < kActions; ++a) {
-      const uint8_t* o = obs.data() + ((size_t)i * kActions + a) * kSamples;
-      uint16_t m = 0;
-      for (int k = 0; k < kSamples; ++k) m |= (uint16_t)(1u << (o[k] & 15));
-      masks[(size_t)i * kActions + a] = m;
+      const uint8_t* o = c.obs.p + ((size_t)i * kActions + a) * kSamples;
+      uint32_t m = 0;
+      for (int k = 0; k < kSamples; ++k) m |= 1u << (o[k] & 15);
       cnt += __builtin_popcount(m);
     }
-    first[i + 1] = cnt;
+    c.first[i + 1] = cnt;
   }
-  for (int i = 0; i < n; ++i) first[i + 1] += first[i];
-  const int nk = first[n];
-  std::vector<int> kslots(nk);
-  for (int k = 0; k < nk; ++k) PP2D_TRY(alloc_slot(h, &kslots[k]));
-  std::vector<Child> kids(nk);
-  std::vector<BayesItem> items(nk);
-  std::vector<int> gfirst((size_t)n * kActions + 1);   // children of Q node (i, a)
-  gfirst[(size_t)n * kActions] = nk;
+  for (int i = 0; i < n; ++i) c.first[i + 1] += c.first[i];
+  const int nk = c.nk = c.first[n];
+  PP2D_TRY(c.kslots.ensure(nk));
+  PP2D_TRY(c.items.ensure(nk));
+  PP2D_TRY(c.gfirst.ensure((size_t)n * kActions + 1));
+  PP2D_TRY(c.ev.ensure((size_t)nk * 4));
+  for (int k = 0; k < nk; ++k) PP2D_TRY(alloc_slot(h, &c.kslots.p[k]));
+  c.kids.resize(nk);
+  c.gfirst.p[(size_t)n * kActions] = nk;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= 64)
   for (int i = 0; i < n; ++i) {
-    int k = first[i];
+    int k = c.first[i];
     for (int a = 0; a < kActions; ++a) {
-      gfirst[(size_t)i * kActions + a] = k;
-      const uint8_t* o = obs.data() + ((size_t)i * kActions + a) * kSamples;
+      c.gfirst.p[(size_t)i * kActions + a] = k;
+      const uint8_t* o = c.obs.p + ((size_t)i * kActions + a) * kSamples;
       int count[16] = {0};
       for (int s = 0; s < kSamples; ++s) count[o[s] & 15]++;
       for (int z = 0; z < 16; ++z) {
         if (!count[z]) continue;
-        kids[k] = Child{(uint8_t)a, (uint8_t)z, (float)count[z] / (float)kSamples};
-        items[k] = BayesItem{slots[i], kslots[k], (uint8_t)a, (uint8_t)z};
+        c.kids[k] = RoundCtx::Child{(uint8_t)a, (uint8_t)z, (float)count[z] / (float)kSamples};
+        c.items.p[k] = BayesItem{c.slots.p[i], c.kslots.p[k], (uint8_t)a, (uint8_t)z};
         ++k;
       }
     }
   }
-  h->t_phase[2] += now_s() - t0; t0 = now_s();   // host: children lists
-  // --- children beliefs: Bayes update + normalise (search_tree_cuda.cu:213-229)
-  PP2D_TRY(launch_bayes_groups(h, items, gfirst));
-  PP2D_TRY(launch_normalize(h, kslots));
-  // --- bounds of the new V nodes (search_tree_cuda.cu:376-385) ---
-  std::vector<float> ev((size_t)nk * 4);
-  PP2D_TRY(evaluate_slots(h, kslots, ev.data()));
-  h->t_phase[3] += now_s() - t0; t0 = now_s();   // bayes + normalise + bounds (device, synced)
-  // --- host bookkeeping ---
+  const int ng = n * kActions;
+  PP2D_TRY(c.d_items.ensure(nk));
+  PP2D_TRY(c.d_gfirst.ensure(ng + 1));
+  PP2D_TRY(c.d_kslots.ensure(nk));
+  PP2D_TRY(c.d_sums.ensure(nk));
+  PP2D_TRY(c.d_vals.ensure((size_t)nk * h->ncol));
+  PP2D_TRY(c.d_out.ensure((size_t)nk * 4));
+  PP2D_CUDA(cudaMemcpyAsync(c.d_items.p, c.items.p, nk * sizeof(BayesItem),
+                            cudaMemcpyHostToDevice, c.stream));
+  PP2D_CUDA(cudaMemcpyAsync(c.d_gfirst.p, c.gfirst.p, (ng + 1) * sizeof(int),
+                            cudaMemcpyHostToDevice, c.stream));
+  PP2D_CUDA(cudaMemcpyAsync(c.d_kslots.p, c.kslots.p, nk * sizeof(int),
+                            cudaMemcpyHostToDevice, c.stream));
+  dim3 bgrid((ng + 31) / 32, (HW + 7) / 8);
+  pomdp_bayes_group_kernel<<<bgrid, 256, 0, c.stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+                                                         c.d_items.p, c.d_gfirst.p, ng,
+                                                         h->d_bel, h->d_bel);
+  count_launch();
+  h->n_bayes += nk;
+  pomdp_colsum_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(HW, h->cap, c.d_kslots.p, nk,
+                                                               h->d_bel, c.d_sums.p);
+  count_launch();
+  dim3 sgrid((nk + 31) / 32, (HW + 7) / 8);
+  pomdp_scale_kernel<<<sgrid, 256, 0, c.stream>>>(HW, h->cap, c.d_kslots.p, nk, c.d_sums.p,
+                                                   h->d_bel);
+  count_launch();
+  dim3 vgrid((nk + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
+  pomdp_values_kernel<<<vgrid, 256, 0, c.stream>>>(HW, h->cap, h->ld, h->ncol, c.d_kslots.p, nk,
+                                                    h->d_bel, h->d_alpha, c.d_vals.p);
+  count_launch();
+  pomdp_bounds_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(nk, h->ncol, h->n_pbvi,
+                                                               c.d_vals.p, c.d_out.p);
+  count_launch();
+  PP2D_CUDA(cudaGetLastError());
+  PP2D_CUDA(cudaMemcpyAsync(c.ev.p, c.d_out.p, (size_t)nk * 4 * sizeof(float),
+                            cudaMemcpyDeviceToHost, c.stream));
+  PP2D_CUDA(cudaEventRecord(c.e2, c.stream));
+  h->t_phase[2] += now_s() - t0;                 // host: children lists, enqueue
+  return PP2D_OK;
+}
+
+// Stage 3: the new nodes enter their trees; bounds, heuristics and depths are
+// propagated to the roots (search_tree_cuda.cu:251-286, 397-450, 497-505).
+int round_stage3(pp2d_pomdp* h, RoundCtx& c) {
+  const int n = c.n;
+  if (n == 0) return PP2D_OK;
+  double t0 = now_s();
+  PP2D_CUDA(cudaEventSynchronize(c.e2));
+  h->t_phase[3] += now_s() - t0; t0 = now_s();   // wait: bayes + normalise + bounds on device
 #pragma omp parallel for schedule(dynamic, 8) num_threads(host_threads()) if (n >= 64)
   for (int i = 0; i < n; ++i) {
-    Tree& t = *jobs[i].t;
-    const int vi = jobs[i].v;
-    int kpos = first[i];
-    const int kend = first[i + 1];
+    Tree& t = *c.jobs[i].t;
+    const int vi = c.jobs[i].v;
+    int kpos = c.first[i];
+    const int kend = c.first[i + 1];
     t.v.reserve(t.v.size() + (size_t)(kend - kpos));
     t.q.reserve(t.q.size() + kActions);
     t.v[vi].children.resize(kActions);
@@ -502,12 +622,12 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
       t.v[vi].children[a] = qi;
       t.q[qi].action = (uint8_t)a;
       t.q[qi].parent = vi;
-      t.q[qi].reward = rewards[(size_t)i * kActions + a];
-      while (kpos < kend && kids[kpos].a == a) {
+      t.q[qi].reward = c.rewards.p[(size_t)i * kActions + a];
+      while (kpos < kend && c.kids[kpos].a == a) {
         t.v.emplace_back();
         const int ci = (int)t.v.size() - 1;
-        init_vnode(t.v[ci], kslots[kpos], kids[kpos].z, kids[kpos].w, qi,
-                   ev.data() + (size_t)kpos * 4, ci);
+        init_vnode(t.v[ci], c.kslots.p[kpos], c.kids[kpos].z, c.kids[kpos].w, qi,
+                   c.ev.p + (size_t)kpos * 4, ci);
         t.q[qi].children.push_back(ci);
         ++kpos;
       }
@@ -524,9 +644,17 @@ int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
     }
     t.expansions++;
   }
-  h->n_vnodes += (uint64_t)nk;
+  h->n_vnodes += (uint64_t)c.nk;
   h->t_phase[4] += now_s() - t0;                 // host: tree bookkeeping
   return PP2D_OK;
+}
+
+// One expansion round for every tree in `trees` (single group).
+int expand_round(pp2d_pomdp* h, std::vector<Tree*>& trees) {
+  RoundCtx& c = *round_ctx(h, 0);
+  PP2D_TRY(round_stage1(h, c, trees));
+  PP2D_TRY(round_stage2(h, c));
+  return round_stage3(h, c);
 }
 
 void best_action(const Tree& t, uint8_t* a, float* r) {   // tree:510-524
@@ -593,6 +721,7 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();
   h->d_rew.release(); h->d_jobslots.release(); h->d_first.release();
+  for (void*& c : h->round_ctx) { delete static_cast<RoundCtx*>(c); c = nullptr; }
   delete h;
 }
 
@@ -829,12 +958,26 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     for (size_t i = 0; i < gn; ++i) { store[i].rng.seed(1); trees[i] = &store[i]; }
     PP2D_TRY(make_roots(h, trees, beliefs + g0 * (size_t)h->HW));
     h->t_phase[5] += now_s() - tr;               // roots: upload + bounds
+    // Two halves in lock-step: while the device works on one, the host
+    // prepares / absorbs the other (all copies of a round are asynchronous).
+    const size_t half = gn >= 256 ? gn / 2 : gn;
+    RoundCtx& ca = *round_ctx(h, 0);
+    RoundCtx& cb = *round_ctx(h, 1);
+    std::vector<Tree*> act_a, act_b;
     for (uint32_t it = 0; it < max_iter; ++it) {
-      std::vector<Tree*> active;
-      for (Tree* t : trees)
-        if (!t->dead && t->v[t->root].depth < max_depth) active.push_back(t);
-      if (active.empty()) break;
-      PP2D_TRY(expand_round(h, active));
+      act_a.clear();
+      act_b.clear();
+      for (size_t i = 0; i < gn; ++i) {
+        Tree* t = trees[i];
+        if (!t->dead && t->v[t->root].depth < max_depth) (i < half ? act_a : act_b).push_back(t);
+      }
+      if (act_a.empty() && act_b.empty()) break;
+      PP2D_TRY(round_stage1(h, ca, act_a));
+      PP2D_TRY(round_stage1(h, cb, act_b));
+      PP2D_TRY(round_stage2(h, ca));
+      PP2D_TRY(round_stage2(h, cb));
+      PP2D_TRY(round_stage3(h, ca));
+      PP2D_TRY(round_stage3(h, cb));
     }
     tr = now_s();
     for (size_t i = 0; i < gn; ++i) {
@@ -852,8 +995,9 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     h->t_phase[6] += now_s() - tr;               // actions out, slots back
   }
   if (getenv("PP2D_POMDP_PROFILE")) {
-    fprintf(stderr, "pp2d pomdp phases [s]: draws %.4f  sample(dev) %.4f  kids %.4f  "
-            "bayes+norm+bounds(dev) %.4f  bookkeeping %.4f  roots %.4f  finish %.4f\n",
+    fprintf(stderr, "pp2d pomdp host phases [s]: draws+enqueue %.4f  wait(sampling) %.4f  "
+            "kids+enqueue %.4f  wait(bayes..bounds) %.4f  bookkeeping %.4f  roots %.4f  "
+            "finish %.4f\n",
             h->t_phase[0], h->t_phase[1], h->t_phase[2], h->t_phase[3], h->t_phase[4],
             h->t_phase[5], h->t_phase[6]);
     for (double& t : h->t_phase) t = 0;

@@ -108,6 +108,7 @@ struct pp2d_pomdp {
   pp2d::DevBuf<float> d_rew;               // [n][9] reward dots of expanded nodes
   pp2d::DevBuf<int> d_jobslots;
   pp2d::DevBuf<int> d_first;               // group offsets of launch_bayes_groups            // slots of the nodes being expanded
+  void* round_ctx[2] = {nullptr, nullptr};   // RoundCtx of pomdp.cu (lazily created)
   cudaStream_t stream = nullptr;
   uint64_t n_bayes = 0, n_vnodes = 0;
   double t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // PP2D_POMDP_PROFILE=1: seconds per phase
