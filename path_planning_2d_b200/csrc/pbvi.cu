@@ -77,7 +77,7 @@ Cublas g_cublas;
 // belief-set expansion kernels (belief pool layout bel[cell * cap + slot])
 
 // pbvi:147-162 sampleFromProbDensity three times (pbvi:216-222): one thread
-// per (belief i, action a).  prefix[s * n + i] is partial_sum(b_i); draws are
+// per (belief i, action a).  prefix[i * HW + s] is partial_sum(b_i); draws are
 // the host rand() values already divided by RAND_MAX+1.  find_if(x >= r) on a
 // non-decreasing prefix = binary search for the first element >= r.  A draw
 // beyond the last partial sum makes the reference index one past the array;
@@ -94,7 +94,7 @@ pbvi_sample_kernel(int H, int W, int n, const float* __restrict__ trans_prob,
   int lo = 0, hi = HW;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (prefix[(size_t)mid * n + i] >= r1) hi = mid; else lo = mid + 1;
+    if (prefix[(size_t)i * HW + mid] >= r1) hi = mid; else lo = mid + 1;
   }
   const int s = lo < HW ? lo : HW - 1;
   float cum = 0.0f;

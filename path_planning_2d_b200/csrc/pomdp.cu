@@ -219,7 +219,7 @@ int launch_prefix(pp2d_pomdp* h, const std::vector<int>& slots) {
   PP2D_TRY(h->d_prefix.ensure((size_t)n * h->HW));
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
-  pomdp_prefix_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+  pomdp_prefix_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(
       h->HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_prefix.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -296,7 +296,7 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
       h->d_vals.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
-  pomdp_bounds_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
+  pomdp_bounds_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(
       n, h->ncol, h->n_pbvi, h->d_vals.p, h->d_out.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -310,8 +310,7 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
 // slot list `d_slots` (n entries): asynchronous, [n][9] into host `out`.
 int reward_dots_async(pp2d_pomdp* h, const int* d_slots, int n, float* out) {
   PP2D_TRY(h->d_rew.ensure((size_t)n * kActions));
-  dim3 grid((n + 127) / 128, kActions);
-  pomdp_rewards_kernel<<<grid, 128, 0, h->stream>>>(h->HW, h->cap, d_slots, n, h->d_bel,
+  pomdp_rewards_kernel<<<(n * kActions + 3) / 4, 128, 0, h->stream>>>(h->HW, h->cap, d_slots, n, h->d_bel,
                                                     h->d_sr, h->d_rew.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -490,7 +489,7 @@ int round_stage1(pp2d_pomdp* h, RoundCtx& c, const std::vector<Tree*>& trees) {
                             cudaMemcpyHostToDevice, c.stream));
   PP2D_CUDA(cudaMemcpyAsync(c.d_draws.p, c.draws.p, nd * sizeof(float),
                             cudaMemcpyHostToDevice, c.stream));
-  pomdp_prefix_kernel<<<(n + 127) / 128, 128, 0, c.stream>>>(
+  pomdp_prefix_kernel<<<(n + 3) / 4, 128, 0, c.stream>>>(
       HW, h->cap, c.d_jobslots.p, n, h->d_bel, c.d_prefix.p);
   count_launch();
   const int nt = (int)nd;
@@ -498,8 +497,7 @@ int round_stage1(pp2d_pomdp* h, RoundCtx& c, const std::vector<Tree*>& trees) {
       h->H, h->W, n, kSamples, h->d_tp, h->d_mp, c.d_prefix.p, c.d_draws.p,
       h->d_uniforms, c.d_obs.p);
   count_launch();
-  dim3 rgrid((n + 127) / 128, kActions);
-  pomdp_rewards_kernel<<<rgrid, 128, 0, c.stream>>>(HW, h->cap, c.d_jobslots.p, n, h->d_bel,
+  pomdp_rewards_kernel<<<(n * kActions + 3) / 4, 128, 0, c.stream>>>(HW, h->cap, c.d_jobslots.p, n, h->d_bel,
                                                      h->d_sr, c.d_rew.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -588,7 +586,7 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
   pomdp_values_kernel<<<vgrid, 256, 0, c.stream>>>(HW, h->cap, h->ld, h->ncol, c.d_kslots.p, nk,
                                                     h->d_bel, h->d_alpha, c.d_vals.p);
   count_launch();
-  pomdp_bounds_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(nk, h->ncol, h->n_pbvi,
+  pomdp_bounds_kernel<<<(nk + 3) / 4, 128, 0, c.stream>>>(nk, h->ncol, h->n_pbvi,
                                                                c.d_vals.p, c.d_out.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -645,6 +643,7 @@ int round_stage3(pp2d_pomdp* h, RoundCtx& c) {
     t.expansions++;
   }
   h->n_vnodes += (uint64_t)c.nk;
+  c.n = 0;                                       // this round is absorbed
   h->t_phase[4] += now_s() - t0;                 // host: tree bookkeeping
   return PP2D_OK;
 }
@@ -908,7 +907,7 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
                                                       h->d_slots.p, n, h->d_bel,
                                                       h->d_alpha, h->d_vals.p);
     count_launch();
-    pomdp_bounds_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(n, h->ncol, h->n_pbvi,
+    pomdp_bounds_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(n, h->ncol, h->n_pbvi,
                                                                 h->d_vals.p, h->d_out.p);
     count_launch();
     PP2D_CUDA(cudaGetLastError());
@@ -958,27 +957,33 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     for (size_t i = 0; i < gn; ++i) { store[i].rng.seed(1); trees[i] = &store[i]; }
     PP2D_TRY(make_roots(h, trees, beliefs + g0 * (size_t)h->HW));
     h->t_phase[5] += now_s() - tr;               // roots: upload + bounds
-    // Two halves in lock-step: while the device works on one, the host
-    // prepares / absorbs the other (all copies of a round are asynchronous).
+    // Two halves, half a round apart: while the device runs the Bayes /
+    // bounds launches of one half, the host absorbs the previous round of the
+    // other half and prepares its next one (all copies are asynchronous, each
+    // half has its own stream).
     const size_t half = gn >= 256 ? gn / 2 : gn;
-    RoundCtx& ca = *round_ctx(h, 0);
-    RoundCtx& cb = *round_ctx(h, 1);
-    std::vector<Tree*> act_a, act_b;
-    for (uint32_t it = 0; it < max_iter; ++it) {
-      act_a.clear();
-      act_b.clear();
-      for (size_t i = 0; i < gn; ++i) {
-        Tree* t = trees[i];
-        if (!t->dead && t->v[t->root].depth < max_depth) (i < half ? act_a : act_b).push_back(t);
+    RoundCtx* ctx[2] = {round_ctx(h, 0), round_ctx(h, 1)};
+    ctx[0]->n = ctx[1]->n = 0;
+    std::vector<Tree*> active;
+    bool more[2] = {true, half < gn};
+    for (uint32_t it = 0; it < max_iter && (more[0] || more[1]); ++it) {
+      for (int g = 0; g < 2; ++g) {
+        if (!more[g]) continue;
+        RoundCtx& c = *ctx[g];
+        PP2D_TRY(round_stage3(h, c));            // previous round of this half
+        active.clear();
+        const size_t i0 = g == 0 ? 0 : half, i1 = g == 0 ? half : gn;
+        for (size_t i = i0; i < i1; ++i) {
+          Tree* t = trees[i];
+          if (!t->dead && t->v[t->root].depth < max_depth) active.push_back(t);
+        }
+        if (active.empty()) { more[g] = false; continue; }
+        PP2D_TRY(round_stage1(h, c, active));
+        PP2D_TRY(round_stage2(h, c));
       }
-      if (act_a.empty() && act_b.empty()) break;
-      PP2D_TRY(round_stage1(h, ca, act_a));
-      PP2D_TRY(round_stage1(h, cb, act_b));
-      PP2D_TRY(round_stage2(h, ca));
-      PP2D_TRY(round_stage2(h, cb));
-      PP2D_TRY(round_stage3(h, ca));
-      PP2D_TRY(round_stage3(h, cb));
     }
+    PP2D_TRY(round_stage3(h, *ctx[0]));
+    PP2D_TRY(round_stage3(h, *ctx[1]));
     tr = now_s();
     for (size_t i = 0; i < gn; ++i) {
       float r;

@@ -125,7 +125,7 @@ int launch_bayes(pp2d_pomdp* h, const std::vector<BayesItem>& items);
 int launch_bayes_groups(pp2d_pomdp* h, const std::vector<BayesItem>& items,
                         const std::vector<int>& first);
 int launch_normalize(pp2d_pomdp* h, const std::vector<int>& slots);
-int launch_prefix(pp2d_pomdp* h, const std::vector<int>& slots);   // -> h->d_prefix [s*n+i]
+int launch_prefix(pp2d_pomdp* h, const std::vector<int>& slots);   // -> h->d_prefix [i*HW+s]
 int launch_scatter(pp2d_pomdp* h, const std::vector<int>& slots, const float* host_rows);
 int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows);
 }  // namespace pp2d

@@ -173,7 +173,7 @@ pomdp_bayes_group_kernel(int H, int W, int cap, const float* __restrict__ trans_
 // tree:226-229: sum = accumulate(b, 0.0f) sequentially, then b /= sum (IEEE
 // division).  One thread per belief column.
 // The sum is a serial chain of float adds by construction; the loads are
-// issued 16 at a time so that memory latency overlaps.
+// issued 32 at a time so that memory latency overlaps.
 __global__ void __launch_bounds__(128)
 pomdp_colsum_kernel(int HW, int cap, const int* __restrict__ slots, int n,
                     const float* __restrict__ bel, float* __restrict__ sums) {
@@ -182,12 +182,12 @@ pomdp_colsum_kernel(int HW, int cap, const int* __restrict__ slots, int n,
   const float* col = bel + slots[i];
   float sum = 0.0f;
   int s = 0;
-  for (; s + 16 <= HW; s += 16) {
-    float v[16];
+  for (; s + 32 <= HW; s += 32) {
+    float v[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = col[(size_t)(s + j) * cap];
+    for (int j = 0; j < 32; ++j) v[j] = col[(size_t)(s + j) * cap];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) sum = __fadd_rn(sum, v[j]);
+    for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, v[j]);
   }
   for (; s < HW; ++s) sum = __fadd_rn(sum, col[(size_t)s * cap]);
   sums[i] = sum;
@@ -206,28 +206,31 @@ pomdp_scale_kernel(int HW, int cap, const int* __restrict__ slots, int n,
 
 // ---------------------------------------------------------------- B7 -------
 // tree:326-328: distribution = partial_sum(belief) (sequential float adds).
-// One thread per expanded V node; prefix[s * n + i].
+// One WARP per expanded V node: the lanes fetch 32 consecutive cells (their
+// addresses are a pool row apart, so all 32 loads are in flight together),
+// then every lane replays the 32 adds in order from registers (shuffles) and
+// keeps the partial sum of its own cell.  prefix[i * HW + s].
 __global__ void __launch_bounds__(128)
 pomdp_prefix_kernel(int HW, int cap, const int* __restrict__ slots, int n,
                     const float* __restrict__ bel, float* __restrict__ prefix) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= n) return;
   const float* col = bel + slots[i];
+  float* out = prefix + (size_t)i * HW;
   float acc = 0.0f;
-  int s = 0;
-  for (; s + 16 <= HW; s += 16) {
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = col[(size_t)(s + j) * cap];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      acc = __fadd_rn(acc, v[j]);
-      prefix[(size_t)(s + j) * n + i] = acc;
+  float nxt = lane < HW ? col[(size_t)lane * cap] : 0.0f;
+  for (int s0 = 0; s0 < HW; s0 += 32) {
+    const float v = nxt;
+    const int sn = s0 + 32 + lane;
+    nxt = sn < HW ? col[(size_t)sn * cap] : 0.0f;      // next chunk while this one is summed
+    float mine = 0.0f;
+    const int cnt = min(32, HW - s0);
+    for (int j = 0; j < cnt; ++j) {
+      acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, j));
+      if (j == lane) mine = acc;
     }
-  }
-  for (; s < HW; ++s) {
-    acc = __fadd_rn(acc, col[(size_t)s * cap]);
-    prefix[(size_t)s * n + i] = acc;
+    if (lane < cnt) out[s0 + lane] = mine;
   }
 }
 
@@ -265,7 +268,7 @@ pomdp_sample_kernel(int H, int W, int n, int S,
   int lo = 0, hi = HW;                       // first s with prefix[s] >= r
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (prefix[(size_t)mid * n + i] >= r) hi = mid; else lo = mid + 1;
+    if (prefix[(size_t)i * HW + mid] >= r) hi = mid; else lo = mid + 1;
   }
   int s1 = lo < HW ? lo : HW - 1;
   float cum = 0.0f;
@@ -392,33 +395,32 @@ pomdp_values_kernel(int HW, int cap, int ld, int ncol,
 }
 
 // tree:168-173: reward[i][a] = inner_product(b_i, R(:,a), 0.0f) for the nodes
-// being expanded: one thread per (belief, action), the same sequential
-// multiply-then-add chain as pomdp_values_kernel; loads issued 8 cells ahead
-// of the chain.  stage_reward is the reference table [HW][9].
+// being expanded: one WARP per (belief, action).  The lanes fetch and multiply
+// 32 consecutive cells, then every lane replays the 32 rounded adds in order
+// (the same sequential multiply-then-add chain as pomdp_values_kernel).
+// stage_reward is the reference table [HW][9].
 __global__ void __launch_bounds__(128)
 pomdp_rewards_kernel(int HW, int cap, const int* __restrict__ slots, int n,
                      const float* __restrict__ bel, const float* __restrict__ stage_reward,
                      float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int a = blockIdx.y;
-  if (i >= n) return;
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= n * 9) return;
+  const int a = w % 9, i = w / 9;
   const float* col = bel + slots[i];
   const float* r = stage_reward + a;
   float acc = 0.0f;
-  int s = 0;
-  for (; s + 8 <= HW; s += 8) {
-    float b[8], w[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      b[j] = col[(size_t)(s + j) * cap];
-      w[j] = __ldg(r + (size_t)(s + j) * 9);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc = __fadd_rn(acc, __fmul_rn(b[j], w[j]));
+  float nb = lane < HW ? col[(size_t)lane * cap] : 0.0f;
+  float nr = lane < HW ? __ldg(r + (size_t)lane * 9) : 0.0f;
+  for (int s0 = 0; s0 < HW; s0 += 32) {
+    const float p = __fmul_rn(nb, nr);
+    const int sn = s0 + 32 + lane;
+    nb = sn < HW ? col[(size_t)sn * cap] : 0.0f;
+    nr = sn < HW ? __ldg(r + (size_t)sn * 9) : 0.0f;
+    const int cnt = min(32, HW - s0);
+    for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, j));
   }
-  for (; s < HW; ++s)
-    acc = __fadd_rn(acc, __fmul_rn(col[(size_t)s * cap], __ldg(r + (size_t)s * 9)));
-  out[(size_t)i * 9 + a] = acc;
+  if (lane == 0) out[(size_t)i * 9 + a] = acc;
 }
 
 // Bounds of every evaluated belief from its row of values: first maximum over
@@ -426,21 +428,39 @@ pomdp_rewards_kernel(int HW, int cap, const int* __restrict__ slots, int n,
 // pbvi:696-698), as std::max_element does.  Packed per belief:
 //   out[i*4 + 0] upper, [1] lower, [2] = fib index | pbvi index << 8 (as int
 //   bits).
-__global__ void pomdp_bounds_kernel(int n, int ncol, int n_pbvi,
-                                    const float* __restrict__ vals,
-                                    float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+pomdp_bounds_kernel(int n, int ncol, int n_pbvi, const float* __restrict__ vals,
+                    float* __restrict__ out) {
+  // one warp per belief: lane-local first maximum over a strided subset of the
+  // columns, then (value, index) reduction where ties keep the smaller index
+  // -- the element std::max_element returns.
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= n) return;
   const float* v = vals + (size_t)i * ncol;
-  int bu = 0;
-  for (int a = 1; a < 9; ++a) if (v[bu] < v[a]) bu = a;
-  int bl = 0;
-  for (int j = 1; j < n_pbvi; ++j) if (v[9 + bl] < v[9 + j]) bl = j;
-  float* o = out + (size_t)i * 4;
-  o[0] = v[bu];
-  o[1] = n_pbvi > 0 ? v[9 + bl] : 0.0f;
-  o[2] = __int_as_float(bu | (bl << 8));
-  o[3] = 0.0f;
+  float bu = 0.0f, bl = 0.0f;
+  int iu = -1, il = -1;
+  if (lane < 9) { bu = v[lane]; iu = lane; }
+  for (int j = lane; j < n_pbvi; j += 32) {
+    const float x = v[9 + j];
+    if (il < 0 || bl < x) { bl = x; il = j; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ou = __shfl_xor_sync(0xffffffffu, bu, off);
+    const int oiu = __shfl_xor_sync(0xffffffffu, iu, off);
+    if (oiu >= 0 && (iu < 0 || bu < ou || (bu == ou && oiu < iu))) { bu = ou; iu = oiu; }
+    const float ol = __shfl_xor_sync(0xffffffffu, bl, off);
+    const int oil = __shfl_xor_sync(0xffffffffu, il, off);
+    if (oil >= 0 && (il < 0 || bl < ol || (bl == ol && oil < il))) { bl = ol; il = oil; }
+  }
+  if (lane == 0) {
+    float* o = out + (size_t)i * 4;
+    o[0] = bu;
+    o[1] = n_pbvi > 0 ? bl : 0.0f;
+    o[2] = __int_as_float(iu | ((il < 0 ? 0 : il) << 8));
+    o[3] = 0.0f;
+  }
 }
 
 // ------------------------------------------------ FIB solver ("next" #1) ----
