@@ -209,6 +209,50 @@ def reference_cuda_on_this_gpu(grid, goal, gamma):
         return {"error": str(e)}
 
 
+def syn16k_section(rank, world, barrier, steps=5):
+    """BASELINE.json configs[3]: ONE synthetic 16384 x 16384 grid, row-sharded
+    over the N GPUs of the run (strong scaling: 16384/N rows each; N = 1 keeps
+    the whole grid on one GPU).  Same step as the headline: 100 sweeps + the
+    residual, ghost rows through the fused kernel's peer stores."""
+    import torch
+    import torch.distributed as dist
+    import cases
+    from path_planning_2d_b200.distributed import ShardedValueIteration
+    n = 16384
+    grid, goal = cases.synthetic_map(n, n, 0.20, seed=12345, goal=(n // 2, 2048))
+    vi = ShardedValueIteration(grid, goal, cases.GAMMA, rank=rank, world_size=world)
+
+    def step():
+        vi.sweeps(SWEEPS_PER_STEP - 2, want_action=False)
+        vi.sweeps(2, want_action=True)
+        r = vi.shard.residual_tensor()
+        if world > 1:
+            dist.all_reduce(r, op=dist.ReduceOp.MAX)
+        return r
+
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    rows = vi.rows[1] - vi.rows[0]
+    vi.close()
+    return {"cell_updates_per_sec": n * n * SWEEPS_PER_STEP * steps / (ms * 1e-3),
+            "ms_per_step": ms / steps, "steps": steps, "scaling": "strong",
+            "workload": f"syn16k: 16384x16384 grid, i.i.d. 20% occupied (PCG64 seed 12345), "
+                        f"goal {goal}, row-sharded over {world} GPU(s), {rows} rows per GPU",
+            "hbm_gbs_algorithmic_per_gpu": n * n * SWEEPS_PER_STEP * steps / (ms * 1e-3)
+            * ALGO_BYTES_PER_CELL_UPDATE / 1e9 / world}
+
+
 def qv_tree_section(rank, world, with_cpu):
     """BASELINE.json configs[4]: batched QV-Tree Search, 1250 queries per GPU
     (10 000 on 8 GPUs), sharded independently, no collective on the data path."""
@@ -432,6 +476,9 @@ def run_main_arm(args):
             line["reference_cuda_same_gpu"] = ref_cuda
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_port_throughput(grid, goal, gamma)
+    syn16k = None if args.no_syn16k else syn16k_section(rank, world, barrier)
+    if rank == 0 and syn16k:
+        line["syn16k"] = syn16k
     qv = None if args.no_qv else qv_tree_section(rank, world, world == 1 and not args.no_cpu)
     if rank == 0:
         if qv:
@@ -471,6 +518,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip cpu_baseline")
     ap.add_argument("--no-qv", action="store_true", help="skip the QV-tree section")
+    ap.add_argument("--no-syn16k", action="store_true",
+                    help="skip the 16384x16384 strong-scaling section")
     ap.add_argument("--no-ref-cuda", action="store_true",
                     help="skip the reference-kernels-on-this-GPU line")
     args = ap.parse_args()

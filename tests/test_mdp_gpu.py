@@ -239,6 +239,48 @@ def test_full_size_properties_4096():
     assert np.array_equal(ac[:256, :256][sel], ora.act[sel])
 
 
+def test_full_size_16384_row_shards_equal_the_unsharded_grid():
+    """BASELINE.json configs[3] size (16384 x 16384, 2.7e8 cells) on one GPU:
+    8 row shards of 2048 rows with ghost-row exchange after every launch must
+    reproduce the unsharded solve bit for bit (Jacobi is partition invariant;
+    the oracle is too slow at this size).  Fused pairs, a single sweep and the
+    arg-min sweep are all exercised."""
+    import torch
+    from path_planning_2d_b200.distributed import device_tensor
+    n = 16384
+    grid, goal = cases.synthetic_map(n, n, 0.20, seed=12345, goal=(n // 2, 2048))
+    plan = [(2, False), (2, False), (1, False), (2, True)]
+    with MdpPathPlanning2d(grid, goal, cases.GAMMA) as whole:
+        for k, wa in plan:
+            whole.sweeps(k, wa)
+        cost, action = whole.download()
+        res = whole.residual()
+    bounds = list(range(0, n + 1, 2048))
+    shards = [MdpPathPlanning2d(grid, goal, cases.GAMMA, rows=(a, b))
+              for a, b in zip(bounds[:-1], bounds[1:])]
+    try:
+        for k, wa in plan:
+            for s in shards:
+                s.sweeps(k, wa)
+            halos = [s.halo() for s in shards]
+            for i in range(len(shards) - 1):
+                up, dn = halos[i], halos[i + 1]
+                t = lambda p: device_tensor(p, up.bytes)
+                t(dn.recv_top).copy_(t(up.send_bottom))
+                t(up.recv_bottom).copy_(t(dn.send_top))
+            torch.cuda.synchronize()
+        for s, a, b in zip(shards, bounds[:-1], bounds[1:]):
+            c, act = s.download()
+            assert np.array_equal(_bits(c), _bits(cost[a:b])), (a, b)
+            assert np.array_equal(act, action[a:b]), (a, b)
+        assert max(s.residual() for s in shards) == res
+    finally:
+        for s in shards:
+            s.close()
+    assert cost[goal[1], goal[0]] == 0.0
+    assert np.all(action[grid == 1] == 0)
+
+
 def test_reset_reuses_the_handle():
     grid, goal = cases.synthetic_map(97, 143, 0.25, seed=21)
     grid2, goal2 = cases.synthetic_map(97, 143, 0.1, seed=22, goal=(5, 90))

@@ -9,7 +9,7 @@ echo "== bench reference arm"; python bench.py --impl reference --steps 3 --warm
 echo "== bench"; python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "exit $?"; cut -c1-400 $OUT/bench_$TAG.json
 echo "== ncu launch list (MDP step)"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu --no-ref-cuda --no-qv > $OUT/ncu_launches_$TAG.log 2>&1; echo "exit $?"
+  python bench.py --steps 2 --warmup 3 --no-cpu --no-ref-cuda --no-qv --no-syn16k > $OUT/ncu_launches_$TAG.log 2>&1; echo "exit $?"
 echo "== ncu launch list (QV-tree batch, fixture alphas: the solver launches are skipped)"
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pomdp_ -c 600 --csv --log-file $OUT/pomdp_launches_$TAG.csv \
   python tools/bench_pomdp.py 1250 --fixture > $OUT/pomdp_ncu_$TAG.log 2>&1; echo "exit $?"
