@@ -511,6 +511,10 @@ class StdoutGuard:
 
 
 def main():
+    # OpenMP workers of the QV-tree host code sleep between parallel regions
+    # instead of spinning (several ranks share the node's cores); must be set
+    # before libgomp is loaded.
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

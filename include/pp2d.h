@@ -272,6 +272,11 @@ int pp2d_pomdp_solve_pbvi(pp2d_pomdp* h, const float* initial_belief, uint32_t n
                           float* alphas, uint8_t* actions);
 
 int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs);
+/* Host threads used for the per-tree work of pp2d_pomdp_plan_batch (random
+ * draws, child lists, tree bookkeeping; the trees of a batch are independent).
+ * 0 = default: PP2D_HOST_THREADS, else min(16, CPUs of the process /
+ * LOCAL_WORLD_SIZE).  The reference is single-threaded (ros::spin). */
+void pp2d_set_host_threads(int n);
 /*
  * Batched cudaBayesBeliefUpdate (point_based_value_iteration_cuda.cu:88-133;
  * call sites search_tree_cuda.cu:217, 601): out[i] = update(in[i], actions[i],

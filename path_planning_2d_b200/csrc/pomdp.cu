@@ -261,16 +261,23 @@ int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows)
 
 namespace {
 
-// Host threads for the per-tree work of a batch: PP2D_HOST_THREADS, else the
-// CPUs this process may run on, at most 16.  (Set explicitly rather than left
-// to OMP_NUM_THREADS, which torchrun forces to 1.)
+// Host threads for the per-tree work of a batch: pp2d_set_host_threads, else
+// PP2D_HOST_THREADS, else the CPUs this process may run on divided by the
+// ranks sharing the node (LOCAL_WORLD_SIZE, set by torchrun), at most 16.
+// (Set explicitly rather than left to OMP_NUM_THREADS, which torchrun forces
+// to 1; more threads than cores makes OpenMP's spinning barriers crawl.)
+std::atomic<int> g_host_threads{0};
 int host_threads() {
+  const int forced = g_host_threads.load(std::memory_order_relaxed);
+  if (forced > 0) return forced;
   static const int n = [] {
     const char* e = getenv("PP2D_HOST_THREADS");
     if (e && atoi(e) > 0) return atoi(e);
     cpu_set_t set;
     int c = 1;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) c = CPU_COUNT(&set);
+    const char* lw = getenv("LOCAL_WORLD_SIZE");
+    if (lw && atoi(lw) > 1) c /= atoi(lw);
     return std::max(1, std::min(16, c));
   }();
   return n;
@@ -816,6 +823,8 @@ int pp2d_pomdp_solve_fib(pp2d_pomdp* h, float* alphas, uint8_t* actions,
   cudaFree(a1); cudaFree(a2); cudaFree(prev); cudaFree(d_res);
   return rc;
 }
+
+void pp2d_set_host_threads(int n) { g_host_threads.store(n > 0 ? n : 0); }
 
 int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
