@@ -172,26 +172,6 @@ int launch_bayes(pp2d_pomdp* h, const std::vector<BayesItem>& items) {
   return PP2D_OK;
 }
 
-int launch_bayes_groups(pp2d_pomdp* h, const std::vector<BayesItem>& items,
-                        const std::vector<int>& first) {
-  const int n = (int)items.size(), ng = (int)first.size() - 1;
-  if (n == 0 || ng <= 0) return PP2D_OK;
-  PP2D_TRY(h->d_items.ensure(n));
-  PP2D_TRY(h->d_first.ensure(ng + 1));
-  PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), n * sizeof(BayesItem),
-                            cudaMemcpyHostToDevice, h->stream));
-  PP2D_CUDA(cudaMemcpyAsync(h->d_first.p, first.data(), (ng + 1) * sizeof(int),
-                            cudaMemcpyHostToDevice, h->stream));
-  dim3 grid((ng + 31) / 32, (h->HW + 7) / 8);
-  pomdp_bayes_group_kernel<<<grid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
-                                                        h->d_items.p, h->d_first.p, ng,
-                                                        h->d_bel, h->d_bel);
-  count_launch();
-  PP2D_CUDA(cudaGetLastError());
-  h->n_bayes += n;
-  return PP2D_OK;
-}
-
 // tree:226-229 on the listed columns: sequential sum, then divide.
 int launch_normalize(pp2d_pomdp* h, const std::vector<int>& slots) {
   const int n = (int)slots.size();
@@ -310,19 +290,6 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
   PP2D_CUDA(cudaMemcpyAsync(out, h->d_out.p, (size_t)n * 4 * sizeof(float),
                             cudaMemcpyDeviceToHost, h->stream));
   PP2D_CUDA(cudaStreamSynchronize(h->stream));
-  return PP2D_OK;
-}
-
-// <b, R(:,a)> for the 9 actions (tree:168-173) of the beliefs in the device
-// slot list `d_slots` (n entries): asynchronous, [n][9] into host `out`.
-int reward_dots_async(pp2d_pomdp* h, const int* d_slots, int n, float* out) {
-  PP2D_TRY(h->d_rew.ensure((size_t)n * kActions));
-  pomdp_rewards_kernel<<<(n * kActions + 3) / 4, 128, 0, h->stream>>>(h->HW, h->cap, d_slots, n, h->d_bel,
-                                                    h->d_sr, h->d_rew.p);
-  count_launch();
-  PP2D_CUDA(cudaGetLastError());
-  PP2D_CUDA(cudaMemcpyAsync(out, h->d_rew.p, (size_t)n * kActions * sizeof(float),
-                            cudaMemcpyDeviceToHost, h->stream));
   return PP2D_OK;
 }
 
@@ -726,7 +693,6 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();
-  h->d_rew.release(); h->d_jobslots.release(); h->d_first.release();
   for (void*& c : h->round_ctx) { delete static_cast<RoundCtx*>(c); c = nullptr; }
   delete h;
 }

@@ -105,9 +105,6 @@ struct pp2d_pomdp {
   pp2d::DevBuf<float> d_prefix, d_draws, d_vals, d_rows, d_sums;
   pp2d::DevBuf<uint8_t> d_obs;
   pp2d::DevBuf<float> d_out;               // 4 floats per evaluated belief
-  pp2d::DevBuf<float> d_rew;               // [n][9] reward dots of expanded nodes
-  pp2d::DevBuf<int> d_jobslots;
-  pp2d::DevBuf<int> d_first;               // group offsets of launch_bayes_groups            // slots of the nodes being expanded
   void* round_ctx[2] = {nullptr, nullptr};   // RoundCtx of pomdp.cu (lazily created)
   cudaStream_t stream = nullptr;
   uint64_t n_bayes = 0, n_vnodes = 0;
@@ -121,9 +118,6 @@ int pool_reserve(pp2d_pomdp* h, size_t slots_wanted);
 int alloc_slot(pp2d_pomdp* h, int* out);
 // the batched B2 / B3 / B7 launches on pool columns (pomdp.cu)
 int launch_bayes(pp2d_pomdp* h, const std::vector<BayesItem>& items);
-// same, items grouped by Q node: group g = items[first[g] .. first[g+1])
-int launch_bayes_groups(pp2d_pomdp* h, const std::vector<BayesItem>& items,
-                        const std::vector<int>& first);
 int launch_normalize(pp2d_pomdp* h, const std::vector<int>& slots);
 int launch_prefix(pp2d_pomdp* h, const std::vector<int>& slots);   // -> h->d_prefix [i*HW+s]
 int launch_scatter(pp2d_pomdp* h, const std::vector<int>& slots, const float* host_rows);
