@@ -144,6 +144,7 @@ struct pp2d_mdp {
   int p2p_debug = 0, p2p_edge_rows = 16;
   // tuning knobs (environment overridable, see mdp_config)
   int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6, waves = 1;
+  bool fused_policy = true;   // arg-min sweep as the second half of a fused pair
 };
 
 namespace pp2d {
@@ -239,6 +240,8 @@ static int launch_sweep(pp2d_mdp* h) {
 
 template <int T, bool POLICY>
 static int launch_sweep_cw(pp2d_mdp* h, int cw) {
+  if (T == 2 && POLICY)      // fused pair whose second sweep is the arg-min one
+    return h->p2p ? launch_sweep<2, 2, true, true>(h) : launch_sweep<2, 2, true, false>(h);
   if (T == 2 && !POLICY && h->p2p)
     return cw == 4 ? launch_sweep<2, 4, false, true>(h)
                    : launch_sweep<2, 2, false, true>(h);
@@ -336,6 +339,7 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->trapped.push_back(0.0f);
   h->cw2 = env_int("PP2D_MDP_CW2", 2);
   h->cw1 = env_int("PP2D_MDP_CW1", 4);
+  h->fused_policy = env_int("PP2D_MDP_FUSED_POLICY", 1) != 0;
   h->rows_per_unit = env_int("PP2D_MDP_ROWS_PER_UNIT", 0);
   h->prefetch_rows = env_int("PP2D_MDP_PREFETCH_ROWS", 6);
   h->waves = env_int("PP2D_MDP_WAVES", 1);
@@ -442,7 +446,9 @@ int pp2d_mdp_sweeps_ex(pp2d_mdp* h, uint32_t n, int want_action) {
   // Value-only sweeps are fused in pairs; when the action grid is wanted the
   // last sweep is the arg-min variant, which leaves exactly what the
   // reference holds after n launches of cudaOneStepValueIteration.
-  uint32_t plain = want_action ? n - 1 : n;
+  // With n >= 2 the arg-min sweep is the second half of a fused pair.
+  const bool fused_tail = want_action && n >= 2 && h->fused_policy;
+  uint32_t plain = want_action ? n - (fused_tail ? 2 : 1) : n;
   int rc;
   while (plain >= 2) {
     if ((rc = launch_sweep_cw<2, false>(h, h->cw2)) != PP2D_OK) return rc;
@@ -451,7 +457,9 @@ int pp2d_mdp_sweeps_ex(pp2d_mdp* h, uint32_t n, int want_action) {
   if (plain == 1)
     if ((rc = launch_sweep_cw<1, false>(h, h->cw1)) != PP2D_OK) return rc;
   if (want_action) {
-    if ((rc = launch_sweep_cw<1, true>(h, h->cw1)) != PP2D_OK) return rc;
+    if (fused_tail) rc = launch_sweep_cw<2, true>(h, 2);
+    else rc = launch_sweep_cw<1, true>(h, h->cw1);
+    if (rc != PP2D_OK) return rc;
     h->action_sweep = h->n_sweeps;
   }
   h->action_host_valid = false;

@@ -309,6 +309,7 @@ struct Sweeper {
   float G4[2][CW];
   float nxt[kPrefetch][CW];              // prefetched raw J^0 rows
   uint32_t cnx[kPrefetch][(CW + 1) / 2]; // prefetched code rows
+  uint32_t cprev[(CW + 1) / 2];          // codes of row y-1 (T == 2 && POLICY)
 
   const SweepParams& p;
   uint32_t lane_base;        // shared address of this lane's table replica
@@ -369,7 +370,7 @@ struct Sweeper {
     uint32_t act[CW];
 #pragma unroll
     for (int j = 0; j < CW; ++j) {
-      v1[j] = backup<POLICY>(A[a0][j], A[a0][j + 1], A[a0][j + 2],
+      v1[j] = backup<(POLICY && T == 1)>(A[a0][j], A[a0][j + 1], A[a0][j + 2],
                              A[a1][j], A[a1][j + 1], A[a1][j + 2],
                              A[a2][j], A[a2][j + 1], A[a2][j + 2],
                              L[lc][j], G4[lc][j], p.gamma, p.ga, p.gb, act[j]);
@@ -394,16 +395,28 @@ struct Sweeper {
       fill_row<CW>(v1, B[a2]);
       if constexpr (J2) {
         float v2[CW];
+        uint32_t act2[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
-          v2[j] = backup<false>(B[a0][j], B[a0][j + 1], B[a0][j + 2],
-                                B[a1][j], B[a1][j + 1], B[a1][j + 2],
-                                B[a2][j], B[a2][j + 1], B[a2][j + 2],
-                                L[lp][j], G4[lp][j], p.gamma, p.ga, p.gb,
-                                act[j]);
+          // the arg-min of a fused launch belongs to its SECOND sweep
+          v2[j] = backup<POLICY>(B[a0][j], B[a0][j + 1], B[a0][j + 2],
+                                 B[a1][j], B[a1][j + 1], B[a1][j + 2],
+                                 B[a2][j], B[a2][j + 1], B[a2][j + 2],
+                                 L[lp][j], G4[lp][j], p.gamma, p.ga, p.gb,
+                                 act2[j]);
         }
         if (valid) {
           store_own<CW>(pout, v2);
+          if constexpr (POLICY) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              if (x0 + j < p.W) {
+                const uint32_t cj = (j & 1) ? (cprev[j >> 1] >> 16) : cprev[j >> 1];
+                // Occupied cells tie on every action in the reference -> 0.
+                pact[j] = (cj & kCodeOccBit) ? 0 : (uint8_t)act2[j];
+              }
+            }
+          }
           if constexpr (PEER) {
             // The first / last two owned rows are also the neighbours' ghost
             // rows: written straight into their HBM over NVLink.
@@ -413,8 +426,13 @@ struct Sweeper {
               store_own<CW>(pdn + (size_t)(yout - (p.H - kPadRows)) * p.pitch, v2);
           }
         }
+        if constexpr (POLICY) pact += p.W;
         if constexpr (PEER) ++yout;
         pout += p.pitch;
+      }
+      if constexpr (POLICY) {
+#pragma unroll
+        for (int j = 0; j < (CW + 1) / 2; ++j) cprev[j] = cc[j];
       }
     }
   }

@@ -173,8 +173,10 @@ class ShardedValueIteration:
         while left > 0:
             k = min(HALO_ROWS, left)
             last = (left - k == 0)
-            if self.p2p and k == 2 and not (want_action and last):
-                self.shard.sweeps(2, False)      # ghost rows travel inside the kernel
+            if self.p2p and k == 2:
+                # ghost rows travel inside the fused kernel (value-only pair, or
+                # a pair whose second sweep also writes the greedy action)
+                self.shard.sweeps(2, want_action and last)
                 self._fused_pending = True
             else:
                 if self.p2p:
