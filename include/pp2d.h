@@ -137,6 +137,18 @@ int pp2d_mdp_residual(pp2d_mdp* h, float* inf_norm);
 int pp2d_mdp_solve(pp2d_mdp* h, uint32_t* sweeps_out, double* residuals,
                    uint32_t max_residuals);
 
+/* policyIteration() (src/mdp/path_planning_2d.cu:271-357; dead code in the
+ * reference, its call is commented out at :115-116) on a freshly created or
+ * reset, unsharded handle: rounds of 50 evaluation sweeps
+ * (cudaOneStepPolicyEvaluation, path_planning_2d_cuda.cu:266-306), the
+ * inf-norm of the change of J over the round, one policy improvement
+ * (cudaPolicyImprovment, :308-355), until the inf-norm is <=
+ * 5/(1-gamma)*1e-3.  residuals / changed (optional, caller-sized for
+ * max_rounds entries, or large enough when max_rounds = 0) receive one entry
+ * per round; max_rounds = 0 runs to the stopping rule. */
+int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* residuals,
+                              uint32_t* changed, uint32_t max_rounds);
+
 /*
  * Replaces the two result cudaMemcpy calls
  * (src/mdp/path_planning_2d.cu:118-126).  cost: rows*width floats,

@@ -179,6 +179,21 @@ class MdpPathPlanning2d : public PathPlanning2dBase {
     } while (cost_inf_norm > max_optimal_cost * 1e-3);
   }
 
+  // src/mdp/path_planning_2d.cu:271-357.  As in the reference it is not called
+  // by initialize() (the call is commented out there, :115-116); it needs the
+  // state initialize() starts from (J = 0, action = 0), i.e. a reset handle.
+  void policyIteration() {
+    std::vector<double> res(4096);
+    std::vector<uint32_t> changed(4096);
+    uint32_t sweeps = 0;
+    PP2D_CHECK(pp2d_mdp_policy_iteration(mdp_, &sweeps, res.data(), changed.data(), 0));
+    total_iterations += (int)sweeps;
+    for (uint32_t r = 0; r < sweeps / 50; ++r) {
+      std::printf("Inf-norm: %f\n", res[r]);
+      std::printf("# of changed actions: %u\n", changed[r]);
+    }
+  }
+
   pp2d_mdp* mdp_ = nullptr;
 };
 

@@ -206,6 +206,126 @@ int oracle_mdp_value_iteration(uint32_t height, uint32_t width,
   return total;
 }
 
+/* Flush-to-zero of the reference's device arithmetic (--use_fast_math:
+ * FMUL.FTZ / FFMA.FTZ flush denormal inputs and results to a signed zero).
+ * It matters in policy iteration only: J of the goal decays geometrically to
+ * 0 once the policy says "stay" there; value iteration never produces a
+ * denormal (J is 0 or >= 1). */
+static inline float ftz(float x) {
+  return (fabsf(x) < FLT_MIN) ? copysignf(0.0f, x) : x;
+}
+
+/* mdp_cuda:266-306 cudaOneStepPolicyEvaluation: one backup under the FIXED
+ * policy in `action`.  nvcc 12.9 / sm_100a: t = FMUL.FTZ(J_k, gamma), then
+ * cost = FFMA.FTZ(P_k, t, cost) for k = 0..8 -- note (gamma*J)*P here, against
+ * (gamma*P)*J in the value-iteration kernel. */
+ORACLE_CLONES
+void oracle_mdp_policy_evaluation(uint32_t height, uint32_t width, float gamma,
+                                  const float* trans_prob, const float* stage_cost,
+                                  const float* prev, float* curr, const uint8_t* action) {
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 0; y < (int64_t)height; ++y) {
+    for (int64_t x = 0; x < (int64_t)width; ++x) {
+      int64_t idx = y * width + x;
+      const uint8_t u = action[idx];
+      const float* tp = trans_prob + idx * 81 + u * 9;
+      float cost = stage_cost[idx * 9 + u];
+      int i = 0;
+      for (int oy = -1; oy < 2; ++oy)
+        for (int ox = -1; ox < 2; ++ox, ++i) {
+          int64_t nx = x + ox, ny = y + oy;
+          float ctg = 0.0f;
+          if (nx >= 0 && nx < (int64_t)width && ny >= 0 && ny < (int64_t)height)
+            ctg = prev[ny * width + nx];
+          float t = ftz(gamma * ftz(ctg));              /* FMUL.FTZ */
+          cost = ftz(fmaf(t, ftz(tp[i]), ftz(cost)));   /* FFMA.FTZ */
+        }
+      curr[idx] = cost;
+    }
+  }
+}
+
+/* mdp_cuda:308-355 cudaPolicyImprovment: greedy action for the given J (first
+ * strict minimum); same product order as the evaluation kernel. */
+ORACLE_CLONES
+void oracle_mdp_policy_improvement(uint32_t height, uint32_t width, float gamma,
+                                   const float* trans_prob, const float* stage_cost,
+                                   const float* J, uint8_t* action) {
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 0; y < (int64_t)height; ++y) {
+    for (int64_t x = 0; x < (int64_t)width; ++x) {
+      int64_t idx = y * width + x;
+      float t[9];
+      int i = 0;
+      for (int oy = -1; oy < 2; ++oy)
+        for (int ox = -1; ox < 2; ++ox, ++i) {
+          int64_t nx = x + ox, ny = y + oy;
+          float ctg = 0.0f;
+          if (nx >= 0 && nx < (int64_t)width && ny >= 0 && ny < (int64_t)height)
+            ctg = J[ny * width + nx];
+          t[i] = ftz(gamma * ftz(ctg));
+        }
+      float opt_cost = FLT_MAX;
+      uint8_t opt_action = 0;
+      for (uint8_t u = 0; u < 9; ++u) {
+        const float* tp = trans_prob + idx * 81 + u * 9;
+        float cost = stage_cost[idx * 9 + u];
+        for (int k = 0; k < 9; ++k) cost = ftz(fmaf(t[k], ftz(tp[k]), ftz(cost)));
+        if (cost < opt_cost) { opt_cost = cost; opt_action = u; }
+      }
+      action[idx] = opt_action;
+    }
+  }
+}
+
+/* mdp_host:271-357 policyIteration (dead code in the reference: its call is
+ * commented out, mdp_host:115-116): J1 = J2 = 0, action = 0; rounds of 50
+ * evaluation sweeps, the inf-norm of the change of J over the round, one
+ * improvement; stop when the inf-norm is <= 5.0/(1.0-gamma)*1e-3.  Returns the
+ * number of evaluation sweeps; residuals / changed (optional) get one entry
+ * per round (changed = number of actions the improvement altered). */
+int oracle_mdp_policy_iteration(uint32_t height, uint32_t width, uint32_t gx, uint32_t gy,
+                                float gamma, const uint8_t* map, float* J_out,
+                                uint8_t* action_out, double* residuals, uint32_t* changed,
+                                int max_rounds) {
+  uint64_t n = (uint64_t)height * width;
+  float* tp = (float*)malloc(sizeof(float) * n * 81);
+  float* sc = (float*)malloc(sizeof(float) * n * 9);
+  float* j1 = (float*)calloc(n, sizeof(float));
+  float* j2 = (float*)calloc(n, sizeof(float));
+  float* jprev = (float*)calloc(n, sizeof(float));
+  uint8_t* aprev = (uint8_t*)calloc(n, 1);
+  if (!tp || !sc || !j1 || !j2 || !jprev || !aprev) {
+    free(tp); free(sc); free(j1); free(j2); free(jprev); free(aprev);
+    return -1;
+  }
+  memset(action_out, 0, n);
+  oracle_mdp_generate_model(height, width, gx, gy, map, tp, sc);
+  int total = 0, round = 0;
+  double inf_norm = 0.0;
+  double max_optimal_cost = 5.0 / (1.0 - gamma);
+  do {
+    for (int i = 0; i < 25; ++i) {
+      oracle_mdp_policy_evaluation(height, width, gamma, tp, sc, j1, j2, action_out);
+      oracle_mdp_policy_evaluation(height, width, gamma, tp, sc, j2, j1, action_out);
+    }
+    total += 50;
+    inf_norm = oracle_mdp_inf_norm(n, jprev, j1);
+    memcpy(jprev, j1, sizeof(float) * n);
+    oracle_mdp_policy_improvement(height, width, gamma, tp, sc, j1, action_out);
+    uint32_t diff = 0;
+    for (uint64_t i = 0; i < n; ++i) diff += aprev[i] != action_out[i];
+    memcpy(aprev, action_out, n);
+    if (residuals && (max_rounds <= 0 || round < max_rounds)) residuals[round] = inf_norm;
+    if (changed && (max_rounds <= 0 || round < max_rounds)) changed[round] = diff;
+    ++round;
+    if (max_rounds > 0 && round >= max_rounds) break;
+  } while (inf_norm > max_optimal_cost * 1e-3);
+  memcpy(J_out, j1, sizeof(float) * n);
+  free(tp); free(sc); free(j1); free(j2); free(jprev); free(aprev);
+  return total;
+}
+
 /* mdp_host:168-189 beliefCallback: action at the first strict maximum of the
  * belief (initial mode 0.0f at index 0). */
 uint8_t oracle_mdp_plan(uint64_t n, const float* belief,

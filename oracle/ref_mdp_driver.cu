@@ -106,6 +106,64 @@ int ref_mdp_solve(uint32_t h, uint32_t w, const uint8_t* map, uint32_t gx,
   return total;
 }
 
+/* policyIteration (path_planning_2d.cu:271-357, dead code in the reference:
+ * its call is commented out at :115-116) with the reference kernels
+ * cudaOneStepPolicyEvaluation / cudaPolicyImprovment; OpenCV's absdiff /
+ * minMaxIdx / compare replaced by float loops.  Returns the number of
+ * evaluation sweeps. */
+int ref_mdp_policy_iteration(uint32_t h, uint32_t w, const uint8_t* map, uint32_t gx,
+                             uint32_t gy, float gamma, float* J_out, uint8_t* action_out,
+                             double* residuals, uint32_t* changed, int max_rounds) {
+  ref_setup(h, w, map, gx, gy);
+  const size_t n = static_cast<size_t>(h) * w;
+  float* prev = static_cast<float*>(calloc(n, sizeof(float)));
+  float* curr = static_cast<float*>(calloc(n, sizeof(float)));
+  uint8_t* aprev = static_cast<uint8_t*>(calloc(n, 1));
+  uint8_t* acurr = static_cast<uint8_t*>(calloc(n, 1));
+  dim3 grid = ref_grid(h, w), block(8, 8);
+  int total = 0, round = 0;
+  double inf_norm = 0.0;
+  double max_optimal_cost = 5.0 / (1.0 - gamma);               /* :290 */
+  do {
+    for (int i = 0; i < 25; ++i) {                             /* :295-306 */
+      cudaOneStepPolicyEvaluation<<<grid, block>>>(
+          h, w, gamma, dev_trans_prob, dev_stage_cost, dev_optimal_cost1,
+          dev_optimal_cost2, dev_optimal_action);
+      checkCudaErrors(cudaDeviceSynchronize());
+      cudaOneStepPolicyEvaluation<<<grid, block>>>(
+          h, w, gamma, dev_trans_prob, dev_stage_cost, dev_optimal_cost2,
+          dev_optimal_cost1, dev_optimal_action);
+      checkCudaErrors(cudaDeviceSynchronize());
+    }
+    total += 50;
+    checkCudaErrors(cudaMemcpy(curr, dev_optimal_cost1, sizeof(float) * n,
+                               cudaMemcpyDeviceToHost));       /* :312 */
+    float m = 0.0f;
+    for (size_t i = 0; i < n; ++i) {
+      float d = std::fabs(prev[i] - curr[i]);
+      if (d > m) m = d;
+    }
+    inf_norm = m;
+    memcpy(prev, curr, sizeof(float) * n);
+    cudaPolicyImprovment<<<grid, block>>>(h, w, gamma, dev_trans_prob, dev_stage_cost,
+                                          dev_optimal_cost1, dev_optimal_action);  /* :333 */
+    checkCudaErrors(cudaDeviceSynchronize());
+    checkCudaErrors(cudaMemcpy(acurr, dev_optimal_action, n, cudaMemcpyDeviceToHost));
+    uint32_t diff = 0;
+    for (size_t i = 0; i < n; ++i) diff += aprev[i] != acurr[i];
+    memcpy(aprev, acurr, n);
+    if (residuals && (max_rounds <= 0 || round < max_rounds)) residuals[round] = inf_norm;
+    if (changed && (max_rounds <= 0 || round < max_rounds)) changed[round] = diff;
+    ++round;
+    if (max_rounds > 0 && round >= max_rounds) break;
+  } while (inf_norm > max_optimal_cost * 1e-3);                /* :353 */
+  checkCudaErrors(cudaMemcpy(J_out, dev_optimal_cost1, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  memcpy(action_out, acurr, n);
+  free(prev); free(curr); free(aprev); free(acurr);
+  freeDeviceMemory();
+  return total;
+}
+
 /* Time n_sweeps (even) of the reference sweep kernel, launched and
  * synchronised exactly as mdp_host:226-237 does, with CUDA events around the
  * loop.  Model build and upload are outside the timed region.  Returns 0 and

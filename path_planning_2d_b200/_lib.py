@@ -44,6 +44,7 @@ SIGNATURES = {
     "pp2d_mdp_residual": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "pp2d_mdp_residual_device": (_i, [_vp, ctypes.POINTER(_vp)]),
     "pp2d_mdp_solve": (_i, [_vp, ctypes.POINTER(_u32), _vp, _u32]),
+    "pp2d_mdp_policy_iteration": (_i, [_vp, _vp, _vp, _vp, _u32]),
     "pp2d_mdp_download": (_i, [_vp, _vp, _vp]),
     "pp2d_mdp_plan": (_i, [_vp, _vp, _vp]),
     "pp2d_mdp_plan_batch": (_i, [_vp, _vp, _u32, _vp]),

@@ -145,6 +145,10 @@ struct pp2d_mdp {
   // tuning knobs (environment overridable, see mdp_config)
   int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6, waves = 1;
   bool fused_policy = true;   // arg-min sweep as the second half of a fused pair
+  // policy iteration (pp2d_mdp_policy_iteration): evaluation sweeps since the
+  // reset; occupied cells then follow J_n = (gamma*J_{n-1}) + 2
+  bool pi_mode = false;
+  std::vector<float> trapped_pi;
 };
 
 namespace pp2d {
@@ -155,6 +159,18 @@ static float trapped_cost(pp2d_mdp* h, uint32_t n) {
   while (h->trapped.size() <= n)
     h->trapped.push_back(fmaf(h->gamma, h->trapped.back(), 2.0f));
   return h->trapped[n];
+}
+
+// Occupied cell under policy evaluation: P = e_4, g = 2 for every action, so
+// J_n = fma(fmul(gamma, J_{n-1}), 1, 2) = (gamma*J_{n-1}) + 2, two roundings.
+static float trapped_cost_pi(pp2d_mdp* h, uint32_t n) {
+  if (h->trapped_pi.empty()) h->trapped_pi.push_back(0.0f);
+  while (h->trapped_pi.size() <= n)
+    h->trapped_pi.push_back(h->gamma * h->trapped_pi.back() + 2.0f);
+  return h->trapped_pi[n];
+}
+static float occupied_cost(pp2d_mdp* h, uint32_t n) {
+  return h->pi_mode ? trapped_cost_pi(h, n) : trapped_cost(h, n);
 }
 
 template <int T, int CW, bool POLICY, bool P2P = false>
@@ -294,6 +310,7 @@ static int upload_map(pp2d_mdp* h, const uint8_t* map) {
   h->cur = 0;
   h->n_sweeps = h->n_chk = h->action_sweep = 0;
   h->action_host_valid = false;
+  h->pi_mode = false;
   return PP2D_OK;
 }
 
@@ -443,6 +460,9 @@ int pp2d_mdp_sweeps_ex(pp2d_mdp* h, uint32_t n, int want_action) {
   if (h->sharded && n > 2)
     return fail(PP2D_ERR_STATE,
                 "a shard can advance at most 2 sweeps between halo exchanges");
+  if (h->pi_mode)
+    return fail(PP2D_ERR_STATE, "value-iteration sweeps after pp2d_mdp_policy_iteration "
+                                "need a pp2d_mdp_reset first");
   // Value-only sweeps are fused in pairs; when the action grid is wanted the
   // last sweep is the arg-min variant, which leaves exactly what the
   // reference holds after n launches of cudaOneStepValueIteration.
@@ -479,7 +499,7 @@ int pp2d_mdp_residual_device(pp2d_mdp* h, void** dev_float_out) {
   // is the closed form and enters the reduction as a floor value.
   float floor_val = 0.0f;
   if (h->has_occupied)
-    floor_val = fabsf(trapped_cost(h, h->n_sweeps) - trapped_cost(h, h->n_chk));
+    floor_val = fabsf(occupied_cost(h, h->n_sweeps) - occupied_cost(h, h->n_chk));
   uint32_t floor_bits;
   memcpy(&floor_bits, &floor_val, sizeof(floor_bits));
   // Owned rows only (ghost rows belong to the neighbours).
@@ -533,6 +553,66 @@ int pp2d_mdp_solve(pp2d_mdp* h, uint32_t* sweeps_out, double* residuals,
   return PP2D_OK;
 }
 
+int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* residuals,
+                              uint32_t* changed, uint32_t max_rounds) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (h->sharded)
+    return fail(PP2D_ERR_STATE, "pp2d_mdp_policy_iteration needs an unsharded handle");
+  if (h->n_sweeps != 0)
+    return fail(PP2D_ERR_STATE, "pp2d_mdp_policy_iteration starts from J = 0, action = 0: "
+                                "call pp2d_mdp_reset first");
+  h->pi_mode = true;
+  const size_t owned = (size_t)h->H * h->W;
+  uint8_t* prev_action = nullptr;
+  unsigned int* d_changed = nullptr;
+  PolicyParams p;
+  p.code = h->code; p.action = h->action;
+  p.W = (int)h->W; p.H = (int)h->H; p.pitch = h->pitch; p.gamma = h->gamma;
+  dim3 grid((h->W + 255) / 256, h->H);
+  std::vector<uint8_t> a_prev(owned, 0), a_curr(owned);
+  // path_planning_2d.cu:271-357
+  const double max_optimal_cost = 5.0 / (1.0 - h->gamma);
+  double cost_inf_norm = 0.0;
+  uint32_t round = 0;
+  (void)prev_action; (void)d_changed;
+  do {
+    for (int i = 0; i < 50; ++i) {                     // 25 ping-pong pairs
+      p.jin = h->j[h->cur];
+      p.jout = h->j[h->cur ^ 1];
+      mdp_policy_kernel<false><<<grid, 256, 0, h->stream>>>(p);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      h->cur ^= 1;
+      h->n_sweeps += 1;
+    }
+    PP2D_CUDA(cudaGetLastError());
+    float r = 0.f;
+    int rc = pp2d_mdp_residual(h, &r);
+    if (rc != PP2D_OK) return rc;
+    cost_inf_norm = r;
+    p.jin = h->j[h->cur];
+    p.jout = nullptr;
+    mdp_policy_kernel<true><<<grid, 256, 0, h->stream>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PP2D_CUDA(cudaGetLastError());
+    h->action_sweep = h->n_sweeps;
+    h->action_host_valid = false;
+    if (changed) {                                      // "# of changed actions", :343-347
+      PP2D_CUDA(cudaMemcpyAsync(a_curr.data(), h->action, owned, cudaMemcpyDeviceToHost,
+                                h->stream));
+      PP2D_CUDA(cudaStreamSynchronize(h->stream));
+      uint32_t diff = 0;
+      for (size_t i = 0; i < owned; ++i) diff += a_prev[i] != a_curr[i];
+      a_prev.swap(a_curr);
+      if (max_rounds == 0 || round < max_rounds) changed[round] = diff;
+    }
+    if (residuals && (max_rounds == 0 || round < max_rounds)) residuals[round] = cost_inf_norm;
+    ++round;
+    if (max_rounds > 0 && round >= max_rounds) break;
+  } while (cost_inf_norm > max_optimal_cost * 1e-3);
+  if (evaluation_sweeps) *evaluation_sweeps = h->n_sweeps;
+  return sync_if_needed(h);
+}
+
 int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
   const size_t owned = (size_t)h->H * h->W;
@@ -541,7 +621,7 @@ int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action) {
     dim3 grid((h->W + 255) / 256, h->H);
     mdp_export_kernel<<<grid, 256, 0, h->stream>>>(
         h->j[h->cur], h->code, h->dense, (int)h->W, (int)h->H, h->pitch,
-        trapped_cost(h, h->n_sweeps));
+        occupied_cost(h, h->n_sweeps));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PP2D_CUDA(cudaGetLastError());
     PP2D_CUDA(cudaMemcpyAsync(cost, h->dense, owned * sizeof(float),

@@ -41,6 +41,7 @@
 #include <stdint.h>
 
 #include "async_copy.cuh"
+#include "fp_exact.cuh"
 
 namespace pp2d {
 
@@ -677,6 +678,119 @@ mdp_residual_kernel(const float4* __restrict__ j, float4* __restrict__ chk,
   if (threadIdx.x == 0) {
     for (int i = 1; i < 8; ++i) m = fmaxf(m, wm[i]);
     atomicMax(result, __float_as_uint(m));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Policy iteration (path_planning_2d_cuda.cu:266-355, called from the
+// reference's policyIteration(), path_planning_2d.cu:271-357 -- dead code
+// there).  Not a hot path: one thread per cell,
+// the model of the cell rebuilt from its code word.
+//   evaluation:  J'(s) = g(s,u) + sum_k P(s,u,k) * (gamma * J(n_k)),  u = pi(s)
+//   improvement: pi(s) = first arg-min over u of the same expression
+// Arithmetic of the reference kernels (nvcc 12.9, sm_100a): t_k = FMUL(J_k,
+// gamma) once per neighbour, cost = FFMA(P_k, t_k, cost) for k = 0..8 --
+// (gamma*J)*P, NOT the (gamma*P)*J of the value-iteration kernel, all with
+// flush-to-zero (J of the goal decays into the denormal range).  Zero
+// probabilities contribute fma(0, t, c) = c and are skipped.  Occupied cells
+// (stored as 0, see the header of this file) follow J_n = (gamma*J_{n-1}) + 2
+// and keep action 0; unlike in value iteration the goal is an ordinary cell
+// here (its J is only 0 once the policy says "stay").
+struct PolicyParams {
+  const float* jin;
+  float* jout;             // evaluation only
+  const uint16_t* code;
+  uint8_t* action;
+  int W, H, pitch;
+  float gamma;
+};
+
+// P(s,u,.) and g(s,u) of one action from the ring code of the cell
+// (path_planning_2d_cuda.cu:76-172).  blocked: bit i = slot i occupied or out
+// of map (bit 4 unused: the cell itself is free here).
+__device__ __forceinline__ void policy_model(uint32_t blocked, bool is_goal, int u,
+                                             float (&P)[9], float& g) {
+  // slots with non-zero naive probability, ascending; side[u] as in the
+  // reference's switch
+  const int s0[9] = {0, 0, 1, 0, 4, 2, 3, 4, 4};
+  const int s1[9] = {1, 1, 2, 3, 4, 4, 4, 6, 5};
+  const int s2[9] = {3, 2, 4, 4, 4, 5, 6, 7, 7};
+  const int s3[9] = {4, 4, 5, 6, 4, 8, 7, 8, 8};
+#pragma unroll
+  for (int i = 0; i < 9; ++i) P[i] = 0.0f;
+  if (u == 4) {
+    P[4] = 1.0f;
+    g = is_goal ? 0.0f : 2.0f;                       // cuda.cu:171
+    return;
+  }
+  const int sl[4] = {s0[u], s1[u], s2[u], s3[u]};
+  float naive[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) naive[j] = (sl[j] == u) ? 0.7f : 0.1f;
+  // stage cost over the NAIVE probabilities, ascending slot (cuda.cu:166-169)
+  g = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    g = fmaf(((blocked >> sl[j]) & 1u) && sl[j] != 4 ? 2.0f : 1.0f, naive[j], g);
+  // blocked mass moves to "stay", ascending slot (cuda.cu:142-147)
+  float stay = 0.1f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (sl[j] == 4) continue;
+    if ((blocked >> sl[j]) & 1u) stay += naive[j];
+    else P[sl[j]] = naive[j];
+  }
+  P[4] = stay;
+}
+
+// ring bit r of the code -> neighbour slot: s0 s1 s2 s5 s8 s7 s6 s3
+__device__ __forceinline__ uint32_t blocked_slots(uint32_t code) {
+  return ((code >> 0) & 1u) << 0 | ((code >> 1) & 1u) << 1 | ((code >> 2) & 1u) << 2 |
+         ((code >> 3) & 1u) << 5 | ((code >> 4) & 1u) << 8 | ((code >> 5) & 1u) << 7 |
+         ((code >> 6) & 1u) << 6 | ((code >> 7) & 1u) << 3;
+}
+
+template <bool IMPROVE>
+__global__ void __launch_bounds__(256)
+mdp_policy_kernel(const PolicyParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= p.W || y >= p.H) return;
+  const size_t q = (size_t)(y + kPadRows) * p.pitch + x + kPadLeft;
+  const uint32_t code = p.code[q];
+  const size_t dense = (size_t)y * p.W + x;
+  if (code & kCodeOccBit) {                // trapped: closed form on download
+    if (IMPROVE) p.action[dense] = 0;
+    else p.jout[q] = 0.0f;
+    return;
+  }
+  const bool is_goal = !(code & kCodeLiveBit);
+  const uint32_t blocked = blocked_slots(code);
+  float t[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    t[i] = mul_ftz(p.jin[q + (size_t)((i / 3 - 1) * p.pitch) + (i % 3 - 1)], p.gamma);
+  if (IMPROVE) {
+    float opt = 3.402823466e+38f;
+    int oa = 0;
+    for (int u = 0; u < 9; ++u) {
+      float P[9], g;
+      policy_model(blocked, is_goal, u, P, g);
+      float cost = g;
+#pragma unroll
+      for (int i = 0; i < 9; ++i)
+        if (P[i] != 0.0f) cost = fma_ftz(P[i], t[i], cost);
+      if (cost < opt) { opt = cost; oa = u; }
+    }
+    p.action[dense] = (uint8_t)oa;
+  } else {
+    float P[9], g;
+    policy_model(blocked, is_goal, p.action[dense], P, g);
+    float cost = g;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (P[i] != 0.0f) cost = fma_ftz(P[i], t[i], cost);
+    p.jout[q] = cost;
   }
 }
 

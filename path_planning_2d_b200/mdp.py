@@ -111,6 +111,18 @@ class MdpPathPlanning2d:
                                             res.ctypes.data, max_batches))
         return n.value, res[:min(max_batches, n.value // 100)].copy()
 
+    def policyIteration(self, max_rounds=0):
+        """src/mdp/path_planning_2d.cu:271-357 on a fresh / reset handle; returns
+        (evaluation sweeps, [inf-norm per round], [changed actions per round])."""
+        n = ctypes.c_uint32()
+        cap = max_rounds if max_rounds else 4096
+        res = np.zeros(cap, dtype=np.float64)
+        chg = np.zeros(cap, dtype=np.uint32)
+        _lib.check(self._lib.pp2d_mdp_policy_iteration(
+            self._h, ctypes.byref(n), res.ctypes.data, chg.ctypes.data, max_rounds))
+        rounds = n.value // 50
+        return n.value, res[:rounds].copy(), chg[:rounds].copy()
+
     def download(self, cost=True, action=True):
         n = self.rows * self.map_width
         c = np.empty(n, dtype=np.float32) if cost else None

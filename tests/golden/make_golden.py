@@ -14,6 +14,10 @@
       as <outdir>/ref_<name>.npz.  The files committed in tests/golden/ were
       produced this way on a B200 (see DESIGN.md "Oracle pin").
 
+  python tests/golden/make_golden.py pi [outdir]
+      (GPU box)  policyIteration() with the reference's own kernels ->
+      pi_ref_<name>.npz.
+
   python tests/golden/make_golden.py pomdp [outdir]
       (GPU box)  Reference POMDP kernels: tables, Bayes updates, FIB sweeps,
       cuRAND uniforms, forward sampling -> pomdp_<name>.npz.
@@ -122,6 +126,35 @@ def make_ref(outdir):
         print(name, grid.shape, "sweeps", n, "residuals", res)
 
 
+def make_pi(outdir):
+    """policyIteration() of the reference (dead code there) with its own kernels
+    cudaOneStepPolicyEvaluation / cudaPolicyImprovment (oracle/_ref, GPU box)."""
+    os.makedirs(outdir, exist_ok=True)
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libpp2d_ref_mdp.so"))
+    vp, u32 = ctypes.c_void_p, ctypes.c_uint32
+    lib.ref_mdp_policy_iteration.restype = ctypes.c_int
+    lib.ref_mdp_policy_iteration.argtypes = [u32, u32, vp, u32, u32, ctypes.c_float, vp, vp,
+                                             vp, vp, ctypes.c_int]
+    todo = [(name, cases.load_bundled(name), goal) for name, (goal, _) in cases.BUNDLED.items()]
+    for h, w, seed in [(37, 53, 1), (64, 130, 2), (1, 17, 3), (23, 1, 4), (2, 2, 5)]:
+        grid, goal = cases.synthetic_map(h, w, 0.25, seed=seed)
+        todo.append((f"syn{seed}_{h}x{w}", grid, goal))
+    for name, grid, goal in todo:
+        h, w = grid.shape
+        J = np.zeros(h * w, np.float32)
+        A = np.zeros(h * w, np.uint8)
+        res = np.zeros(4096, np.float64)
+        chg = np.zeros(4096, np.uint32)
+        n = lib.ref_mdp_policy_iteration(h, w, grid.ctypes.data, goal[0], goal[1],
+                                         cases.GAMMA, J.ctypes.data, A.ctypes.data,
+                                         res.ctypes.data, chg.ctypes.data, 0)
+        np.savez_compressed(os.path.join(outdir, f"pi_ref_{name}.npz"), grid=grid,
+                            goal=np.array(goal), gamma=np.float32(cases.GAMMA),
+                            J=J.reshape(h, w), action=A.reshape(h, w), sweeps=np.int32(n),
+                            residuals=res[:n // 50], changed=chg[:n // 50])
+        print(name, grid.shape, "evaluation sweeps", n, "rounds", n // 50)
+
+
 def make_pomdp(outdir):
     """POMDP half: outputs of the reference kernels (oracle/_ref, GPU box)."""
     import pomdp_oracle_py as po
@@ -194,7 +227,10 @@ def make_tree(outdir, only=None):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) >= 2 and sys.argv[1] == "tree":
+    if len(sys.argv) >= 2 and sys.argv[1] == "pi":
+        make_pi(sys.argv[2] if len(sys.argv) > 2 else
+                os.path.join(ROOT, "gpurun_out", "golden_ref"))
+    elif len(sys.argv) >= 2 and sys.argv[1] == "tree":
         make_tree(sys.argv[2] if len(sys.argv) > 2 else
                   os.path.join(ROOT, "gpurun_out", "golden_ref"),
                   sys.argv[3] if len(sys.argv) > 3 else None)

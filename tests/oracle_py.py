@@ -84,6 +84,24 @@ def value_iteration(grid, goal, gamma, max_batches=0):
     return J.reshape(h, w), A.reshape(h, w), n, res[:n // 100].copy()
 
 
+def policy_iteration(grid, goal, gamma, max_rounds=0):
+    """oracle_mdp_policy_iteration -> (J, action, evaluation sweeps, residuals, changed)."""
+    grid = np.ascontiguousarray(grid, dtype=np.uint8)
+    h, w = grid.shape
+    J = np.zeros(h * w, np.float32)
+    A = np.zeros(h * w, np.uint8)
+    res = np.zeros(256, np.float64)
+    chg = np.zeros(256, np.uint32)
+    f = lib().oracle_mdp_policy_iteration
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                  ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    n = f(h, w, goal[0], goal[1], gamma, grid.ctypes.data, J.ctypes.data, A.ctypes.data,
+          res.ctypes.data, chg.ctypes.data, max_rounds)
+    return J.reshape(h, w), A.reshape(h, w), n, res[:n // 50].copy(), chg[:n // 50].copy()
+
+
 def tables(grid, goal):
     grid = np.ascontiguousarray(grid, dtype=np.uint8)
     h, w = grid.shape
