@@ -305,15 +305,17 @@ def qv_tree_section(rank, world, with_cpu):
         import pomdp_oracle_py as po
         m = po.Model(grid, goal)
         k = 6
+        same = True
         t0 = time.perf_counter()
         for i in range(k):
             t = po.Tree(m, cases.GAMMA, fib, pbvi, pf.uniforms(), mine[i], fa, pa)
             a, r, st, rc = t.plan(50, 15)
             t.close()
-            assert a == acts[i], "oracle and GPU disagree on a plan"
+            same = same and a == acts[i] and np.float32(r) == vals[i]
         out["cpu_baseline"] = {"value": k / (time.perf_counter() - t0), "unit": "plans/s",
                                "cores": 1, "kind": "port",
-                               "sample": f"first {k} queries, oracle/pomdp_oracle.c, 1 thread"}
+                               "sample": f"first {k} queries, oracle/pomdp_oracle.c, 1 thread",
+                               "same_actions_and_values_as_gpu": bool(same)}
     return out
 
 
@@ -483,11 +485,22 @@ def run_main_arm(args):
         if ref_cuda:
             line["reference_cuda_same_gpu"] = ref_cuda
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_port_throughput(grid, goal, gamma)
-    syn16k = None if args.no_syn16k else syn16k_section(rank, world, barrier)
+            try:
+                line["cpu_baseline"] = cpu_port_throughput(grid, goal, gamma)
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"] = {"error": repr(e)}
+    # the side sections must never cost the headline line
+    syn16k = qv = None
+    try:
+        syn16k = None if args.no_syn16k else syn16k_section(rank, world, barrier)
+    except Exception as e:  # pragma: no cover
+        syn16k = {"error": repr(e)}
     if rank == 0 and syn16k:
         line["syn16k"] = syn16k
-    qv = None if args.no_qv else qv_tree_section(rank, world, world == 1 and not args.no_cpu)
+    try:
+        qv = None if args.no_qv else qv_tree_section(rank, world, world == 1 and not args.no_cpu)
+    except Exception as e:  # pragma: no cover
+        qv = {"error": repr(e)}
     if rank == 0:
         if qv:
             line["qv_tree"] = qv
