@@ -24,11 +24,14 @@
  *     bookkeeping) is plain x86-64 g++: sequential float mul then add, no
  *     FMA.  Build this file with -ffp-contract=off.
  *
- * Parity pin: B1 and B2 are checked against the reference's own kernels run
- * on a B200 (oracle/_ref/libpp2d_ref_pomdp.so, tests/golden/pomdp_*.npz).
- * The host-side tree logic has no executable reference here (Boost and ROS
- * are absent): for B3-B10 this file is a line-by-line
- * restatement and parity is "unpinned" beyond the kernels it calls.
+ * Parity pin: every function here is checked against the reference's OWN code
+ * run on a B200.  Kernels (B1, B2, FIB sweep, sampling): oracle/_ref/
+ * libpp2d_ref_pomdp.so -> tests/golden/pomdp_*.npz.  Host-side tree logic
+ * (B3-B10: SearchTree, VNode, QNode, evaluateFibCpu, evaluatePbviCpu): the
+ * four reference translation units compiled unmodified against stand-in
+ * headers for ROS and Boost.MultiArray (oracle/_ref/libpp2d_ref_pomdp_full.so,
+ * oracle/stubs/) -> tests/golden/tree_*.npz, compared node by node and bit for
+ * bit by tests/test_tree_pin_cpu.py.  See DESIGN.md section 2.
  */
 #include <float.h>
 #include <math.h>
