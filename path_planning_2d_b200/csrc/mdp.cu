@@ -563,8 +563,6 @@ int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* 
                                 "call pp2d_mdp_reset first");
   h->pi_mode = true;
   const size_t owned = (size_t)h->H * h->W;
-  uint8_t* prev_action = nullptr;
-  unsigned int* d_changed = nullptr;
   PolicyParams p;
   p.code = h->code; p.action = h->action;
   p.W = (int)h->W; p.H = (int)h->H; p.pitch = h->pitch; p.gamma = h->gamma;
@@ -574,7 +572,6 @@ int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* 
   const double max_optimal_cost = 5.0 / (1.0 - h->gamma);
   double cost_inf_norm = 0.0;
   uint32_t round = 0;
-  (void)prev_action; (void)d_changed;
   do {
     for (int i = 0; i < 50; ++i) {                     // 25 ping-pong pairs
       p.jin = h->j[h->cur];
