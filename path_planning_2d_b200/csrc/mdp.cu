@@ -145,6 +145,7 @@ struct pp2d_mdp {
   // tuning knobs (environment overridable, see mdp_config)
   int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6, waves = 1;
   bool fused_policy = true;   // arg-min sweep as the second half of a fused pair
+  int linear_units = -1;      // -1 = choose per launch, 0 = row blocks, 1 = strip-major runs
   // policy iteration (pp2d_mdp_policy_iteration): evaluation sweeps since the
   // reset; occupied cells then follow J_n = (gamma*J_{n-1}) + 2
   bool pi_mode = false;
@@ -175,6 +176,9 @@ static float occupied_cost(pp2d_mdp* h, uint32_t n) {
 
 template <int T, int CW, bool POLICY, bool P2P = false>
 static int launch_sweep(pp2d_mdp* h) {
+  // strip-major runs exist for the fused kernels at CW = 2 (the ones that
+  // dominate a solve)
+  constexpr bool kHasLin = (T == 2 && CW == 2);
   using G = StripGeom<T, CW>;
   SweepParams p;
   memset(&p, 0, sizeof(p));
@@ -195,23 +199,41 @@ static int launch_sweep(pp2d_mdp* h) {
   p.y_end = (T == 1 && !POLICY) ? (int)h->H + 1 : (int)h->H;
   const int rows = p.y_end - p.y_begin;
   int rpu = h->rows_per_unit;
+  p.lin_len = 0;
   if (rpu <= 0) {
-    // Units are equal-sized, so the launch is sized to fill exactly
-    // `waves` full waves of resident CTAs (one unit per warp): one
-    // more CTA than that would run alone in an extra wave.
+    // Launch sized to exactly `waves` full waves of resident CTAs (one unit
+    // per warp); the units are equal runs of the strip-major row sequence.
     int ctas_per_sm = 0;
     PP2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY, P2P>, kWarpsPerCta * 32, 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    const long slots = (long)h->sm_count * ctas_per_sm * kWarpsPerCta;   // resident warps
-    long rb = slots * h->waves / p.n_strips;                  // floor
+    const long long slots = (long long)h->sm_count * ctas_per_sm * kWarpsPerCta * h->waves;
+    // (a) whole row blocks per strip: floor(slots / strips) blocks, no restart;
+    long long rb = slots / p.n_strips;
     if (rb < 1) rb = 1;
-    rpu = (int)((rows + rb - 1) / rb);
-    if (rpu < 8) rpu = 8;
+    long long rpu_blocks = (rows + rb - 1) / rb;
+    if (rpu_blocks < 8) rpu_blocks = 8;
+    // (b) equal runs of the strip-major row sequence: every slot busy, but a
+    // unit that crosses a strip boundary primes its pipeline twice (~4 rows).
+    const long long total = (long long)p.n_strips * rows;
+    long long len = (total + slots - 1) / slots;
+    if (len < 8) len = 8;
+    if (len > rows) len = rows;               // at most one strip boundary per unit
+    const long long restart_rows = 4;
+    if (kHasLin && h->linear_units != 0 &&
+        (h->linear_units > 0 || len + restart_rows < rpu_blocks)) {
+      p.lin_len = (int)len;
+      p.rows_per_unit = (int)len;
+      p.n_units = (int)((total + len - 1) / len);
+    } else {
+      p.rows_per_unit = (int)rpu_blocks;
+      p.n_units = p.n_strips * (int)((rows + rpu_blocks - 1) / rpu_blocks);
+    }
+  } else {
+    p.rows_per_unit = rpu;
+    const int n_rb = (rows + rpu - 1) / rpu;
+    p.n_units = p.n_strips * n_rb;
   }
-  p.rows_per_unit = rpu;
-  const int n_rb = (rows + rpu - 1) / rpu;
-  p.n_units = p.n_strips * n_rb;
   p.prefetch_rows = h->prefetch_rows;
   p.gamma = h->gamma * 1.0f;
   p.ga = h->gamma * 0.7f;
@@ -219,21 +241,40 @@ static int launch_sweep(pp2d_mdp* h) {
   if (P2P) {
     // Boundary units of this launch: those whose rows touch the first / last
     // two owned rows (they wait for and signal the neighbours).
-    int top_blocks = 0, bot_blocks = 0;
-    for (int rb = 0; rb < n_rb; ++rb) {
-      const int y0 = rb * rpu, y1 = std::min(y0 + rpu, (int)h->H);
-      if (y0 < kPadRows) ++top_blocks;
-      if (y1 > (int)h->H - kPadRows) ++bot_blocks;
+    // (same enumeration of the segments as Sweeper::run)
+    unsigned int top_segs = 0, bot_segs = 0;
+    auto count = [&](int y0, int y1) {
+      if (y0 < kPadRows) ++top_segs;
+      if (y1 > (int)h->H - kPadRows) ++bot_segs;
+    };
+    if (p.lin_len > 0) {
+      const long long R = rows, total = (long long)p.n_strips * R;
+      for (long long u = 0; u < p.n_units; ++u) {
+        long long lo = u * p.lin_len;
+        const long long hi = std::min(lo + (long long)p.lin_len, total);
+        while (lo < hi) {
+          const long long k = lo / R, a = lo - k * R, b = std::min(R, a + (hi - lo));
+          count(p.y_begin + (int)a, p.y_begin + (int)b);
+          lo += b - a;
+        }
+      }
+    } else {
+      const int n_rb = (rows + p.rows_per_unit - 1) / p.rows_per_unit;
+      for (int rb = 0; rb < n_rb; ++rb) {
+        const int y0 = rb * p.rows_per_unit;
+        for (int k = 0; k < p.n_strips; ++k)
+          count(y0, std::min(y0 + p.rows_per_unit, (int)h->H));
+      }
     }
     h->p2p_iter += 1;
     const int nxt = h->cur ^ 1;
     if (h->up_j[nxt]) {
-      h->p2p_expect_top += (unsigned int)(top_blocks * p.n_strips);
+      h->p2p_expect_top += top_segs;
       p.peer_up_out = h->up_j[nxt] + (size_t)(h->up_H + kPadRows) * h->pitch;
       p.up_flag_remote = h->up_flags + kFlagFromDown;
     }
     if (h->down_j[nxt]) {
-      h->p2p_expect_bot += (unsigned int)(bot_blocks * p.n_strips);
+      h->p2p_expect_bot += bot_segs;
       p.peer_down_out = h->down_j[nxt];
       p.down_flag_remote = h->down_flags + kFlagFromUp;
     }
@@ -246,7 +287,14 @@ static int launch_sweep(pp2d_mdp* h) {
   }
   const int warps_per_cta = kWarpsPerCta;
   const int grid = (p.n_units + warps_per_cta - 1) / warps_per_cta;
-  mdp_sweep_kernel<T, CW, POLICY, P2P><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+  if constexpr (kHasLin) {
+    if (p.lin_len > 0)
+      mdp_sweep_kernel<T, CW, POLICY, P2P, true><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+    else
+      mdp_sweep_kernel<T, CW, POLICY, P2P, false><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+  } else {
+    mdp_sweep_kernel<T, CW, POLICY, P2P><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   PP2D_CUDA(cudaGetLastError());
   h->cur ^= 1;
@@ -357,6 +405,7 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->cw2 = env_int("PP2D_MDP_CW2", 2);
   h->cw1 = env_int("PP2D_MDP_CW1", 4);
   h->fused_policy = env_int("PP2D_MDP_FUSED_POLICY", 1) != 0;
+  h->linear_units = env_int("PP2D_MDP_LINEAR_UNITS", -1);
   h->rows_per_unit = env_int("PP2D_MDP_ROWS_PER_UNIT", 0);
   h->prefetch_rows = env_int("PP2D_MDP_PREFETCH_ROWS", 6);
   h->waves = env_int("PP2D_MDP_WAVES", 1);

@@ -94,6 +94,7 @@ struct SweepParams {
   unsigned int expect_top, expect_bot;  // cumulative boundary-unit counts
   unsigned int p2p_debug;               // bit0 no waits, bit1 no peer stores, bit2 no signals
   int edge_rows;                        // rows of a boundary unit processed first
+  int lin_len;           // LIN kernels: units are runs of lin_len rows of the strip-major sequence
 };
 
 // Flag block of a shard (uint32 each, cudaMalloc'ed, IPC-shared).
@@ -301,7 +302,10 @@ struct StripGeom {
   static constexpr int kRingBytesPerWarp = (CW >= 2) ? kRing * kSlotBytes : 0;
 };
 
-template <int T, int CW, bool POLICY, bool P2P = false>
+// LIN: units are runs of the strip-major row sequence (see run()); a separate
+// instantiation because the loop around the marching code costs registers the
+// row-block scheme cannot spare (126 of 128).
+template <int T, int CW, bool POLICY, bool P2P = false, bool LIN = false>
 struct Sweeper {
   using G = StripGeom<T, CW>;
   float A[3][CW + 2];        // J^0 rows y-1, y, y+1 (rotating)
@@ -504,18 +508,49 @@ struct Sweeper {
     if constexpr (CW >= 2) cp_async_wait<0>();
   }
 
+  // A unit is a run of `lin_len` rows of the strip-major sequence (strip 0 rows
+  // y_begin..y_end-1, strip 1 rows ..., ...): every warp of the one-wave launch
+  // gets the same number of rows whatever W and H are (with whole row blocks
+  // per strip, 274 strips x 8 blocks fill only 92.6 % of the 2368 warp slots at
+  // W = 16384).  A unit that crosses a strip boundary marches twice.
   __device__ __forceinline__ void run(int unit, int lane) {
-    const int k = unit % p.n_strips;
-    const int rb = unit / p.n_strips;
-    const int y0 = p.y_begin + rb * p.rows_per_unit;      // rows [y0, y1)
-    const int y1 = min(y0 + p.rows_per_unit, p.y_end);
+    if constexpr (LIN) {
+      l1_ahead = (size_t)(p.prefetch_rows - kPrefetch) * (size_t)p.pitch;
+      if constexpr (CW >= 2) {
+        ring_j += lane * (CW * 4);
+        ring_c += lane * (CW * 2);
+      }
+      const int R = p.y_end - p.y_begin;
+      int lo = unit * p.lin_len;
+      const int hi = min(lo + p.lin_len, p.n_strips * R);
+      while (lo < hi) {
+        const int k = lo / R;
+        const int a = lo - k * R;
+        const int b = min(R, a + (hi - lo));
+        run_segment(k, p.y_begin + a, p.y_begin + b, lane);
+        lo += b - a;
+      }
+    } else {
+      const int k = unit % p.n_strips;
+      const int rb = unit / p.n_strips;
+      const int y0 = p.y_begin + rb * p.rows_per_unit;      // rows [y0, y1)
+      const int y1 = min(y0 + p.rows_per_unit, p.y_end);
+      run_segment(k, y0, y1, lane);
+    }
+  }
+
+  // Rows [y0, y1) of strip k.
+  __device__ __forceinline__ void run_segment(const int k, const int y0, const int y1,
+                                              const int lane) {
     x0 = k * G::S + G::XOFF + lane * CW;
     valid = (lane >= G::HL) && (lane < 32 - G::HL) && (x0 < p.W);
     const size_t col = (size_t)(x0 + kPadLeft);
-    l1_ahead = (size_t)(p.prefetch_rows - kPrefetch) * (size_t)p.pitch;
-    if constexpr (CW >= 2) {
-      ring_j += lane * (CW * 4);
-      ring_c += lane * (CW * 2);
+    if constexpr (!LIN) {
+      l1_ahead = (size_t)(p.prefetch_rows - kPrefetch) * (size_t)p.pitch;
+      if constexpr (CW >= 2) {
+        ring_j += lane * (CW * 4);
+        ring_c += lane * (CW * 2);
+      }
     }
     int r0 = y0, r1 = y1;            // rows marched without peer stores
     if constexpr (P2P) {
@@ -582,7 +617,7 @@ struct Sweeper {
 };
 
 // One warp per (column strip, row block) unit; kWarpsPerCta warps per CTA.
-template <int T, int CW, bool POLICY, bool P2P = false>
+template <int T, int CW, bool POLICY, bool P2P = false, bool LIN = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (T == 2 && CW == 2) ? PP2D_MINCTAS : 1)
 mdp_sweep_kernel(const SweepParams p) {
   // The table must start on a 2 KB boundary of the shared window so that the
@@ -608,7 +643,7 @@ mdp_sweep_kernel(const SweepParams p) {
                : "=r"(lane_base) : "r"(lut_addr), "r"((lane & 7) << 4) : "memory");
   const uint32_t ring_warp =
       lut_addr + kLutFloat4 * 16 + (threadIdx.x >> 5) * G::kRingBytesPerWarp;
-  Sweeper<T, CW, POLICY, P2P> s(p, lane_base, ring_warp);
+  Sweeper<T, CW, POLICY, P2P, LIN> s(p, lane_base, ring_warp);
   s.run(unit, lane);
 }
 

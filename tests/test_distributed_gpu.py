@@ -46,13 +46,14 @@ def _worker(rank, world, port, out_dir, p2p):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [True, False])
-def test_nccl_sharded_solve_matches_single_gpu(tmp_path, p2p):
+@pytest.mark.parametrize("p2p,lin", [(True, -1), (False, -1), (True, 1), (True, 0)])
+def test_nccl_sharded_solve_matches_single_gpu(tmp_path, monkeypatch, p2p, lin):
     """p2p=True: ghost rows written by the fused kernel into the neighbours'
     HBM (CUDA IPC + device flags); p2p=False: NCCL send/recv after every launch."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("PP2D_MDP_LINEAR_UNITS", str(lin))   # unit scheme of the sweep kernels
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), p2p), nprocs=world,
              join=True)

@@ -78,21 +78,24 @@ def test_ragged_shapes_step_by_step(shape, p_occ):
         assert mdp.sweep_count == ora.n
 
 
-@pytest.mark.parametrize("cw2,cw1,rpu", [(1, 1, 16), (2, 2, 5), (4, 4, 64),
-                                         (2, 4, 0), (4, 1, 7)])
-def test_every_kernel_variant(monkeypatch, cw2, cw1, rpu):
-    """Column widths per lane (1/2/4) and rows per unit are tuning knobs; all
-    variants must give the same bits."""
+@pytest.mark.parametrize("cw2,cw1,rpu,lin", [(1, 1, 16, -1), (2, 2, 5, -1), (4, 4, 64, -1),
+                                             (2, 4, 0, 0), (4, 1, 7, -1), (2, 4, 0, 1),
+                                             (4, 2, 0, 1), (1, 1, 0, 1)])
+def test_every_kernel_variant(monkeypatch, cw2, cw1, rpu, lin):
+    """Column widths per lane (1/2/4), rows per unit and the unit scheme (whole
+    row blocks per strip / equal runs of the strip-major row sequence) are
+    tuning knobs; all variants must give the same bits."""
     monkeypatch.setenv("PP2D_MDP_CW2", str(cw2))
     monkeypatch.setenv("PP2D_MDP_CW1", str(cw1))
     monkeypatch.setenv("PP2D_MDP_ROWS_PER_UNIT", str(rpu))
+    monkeypatch.setenv("PP2D_MDP_LINEAR_UNITS", str(lin))
     grid, goal = cases.synthetic_map(211, 387, 0.25, seed=7)
     ora = oracle_py.OracleMdp(grid, goal, 0.9)
     with MdpPathPlanning2d(grid, goal, 0.9) as mdp:
         for k in (6, 1, 9):
             mdp.sweeps(k)
             ora.sweeps(k)
-            _assert_same(mdp, ora, f"variant cw2={cw2} cw1={cw1} rpu={rpu}")
+            _assert_same(mdp, ora, f"variant cw2={cw2} cw1={cw1} rpu={rpu} lin={lin}")
 
 
 @pytest.mark.parametrize("gamma", [0.5, 0.9, 0.99, 0.999])
