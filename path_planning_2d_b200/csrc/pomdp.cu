@@ -398,6 +398,9 @@ struct RoundCtx {
   cudaEvent_t e1 = nullptr, e2 = nullptr;
   cudaStream_t stream = nullptr;     // own stream: the tail of one group's launches
                                      // overlaps the other group's
+  cudaStream_t stream_hi = nullptr;  // stage 1 (small sampling kernels): high priority, so
+                                     // that it is not queued behind the other group's
+                                     // values launch and the host can move on
   ~RoundCtx() {
     slots.release(); kslots.release(); gfirst.release(); draws.release(); rewards.release();
     ev.release(); items.release(); obs.release();
@@ -407,6 +410,7 @@ struct RoundCtx {
     if (e1) cudaEventDestroy(e1);
     if (e2) cudaEventDestroy(e2);
     if (stream) cudaStreamDestroy(stream);
+    if (stream_hi) cudaStreamDestroy(stream_hi);
   }
 };
 
@@ -416,6 +420,9 @@ RoundCtx* round_ctx(pp2d_pomdp* h, int which) {
     cudaEventCreateWithFlags(&c->e1, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->e2, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    int lo_prio = 0, hi_prio = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+    cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, hi_prio);
     h->round_ctx[which] = c;
   }
   return static_cast<RoundCtx*>(h->round_ctx[which]);
@@ -460,25 +467,25 @@ int round_stage1(pp2d_pomdp* h, RoundCtx& c, const std::vector<Tree*>& trees) {
   PP2D_TRY(c.d_obs.ensure(nd));
   PP2D_TRY(c.d_rew.ensure((size_t)n * kActions));
   PP2D_CUDA(cudaMemcpyAsync(c.d_jobslots.p, c.slots.p, n * sizeof(int),
-                            cudaMemcpyHostToDevice, c.stream));
+                            cudaMemcpyHostToDevice, c.stream_hi));
   PP2D_CUDA(cudaMemcpyAsync(c.d_draws.p, c.draws.p, nd * sizeof(float),
-                            cudaMemcpyHostToDevice, c.stream));
-  pomdp_prefix_kernel<<<(n + 3) / 4, 128, 0, c.stream>>>(
+                            cudaMemcpyHostToDevice, c.stream_hi));
+  pomdp_prefix_kernel<<<(n + 3) / 4, 128, 0, c.stream_hi>>>(
       HW, h->cap, c.d_jobslots.p, n, h->d_bel, c.d_prefix.p);
   count_launch();
   const int nt = (int)nd;
-  pomdp_sample_kernel<<<(nt + 127) / 128, 128, 0, c.stream>>>(
+  pomdp_sample_kernel<<<(nt + 127) / 128, 128, 0, c.stream_hi>>>(
       h->H, h->W, n, kSamples, h->d_tp, h->d_mp, c.d_prefix.p, c.d_draws.p,
       h->d_uniforms, c.d_obs.p);
   count_launch();
-  pomdp_rewards_kernel<<<(n * kActions + 3) / 4, 128, 0, c.stream>>>(HW, h->cap, c.d_jobslots.p, n, h->d_bel,
+  pomdp_rewards_kernel<<<(n * kActions + 3) / 4, 128, 0, c.stream_hi>>>(HW, h->cap, c.d_jobslots.p, n, h->d_bel,
                                                      h->d_sr, c.d_rew.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
-  PP2D_CUDA(cudaMemcpyAsync(c.obs.p, c.d_obs.p, nd, cudaMemcpyDeviceToHost, c.stream));
+  PP2D_CUDA(cudaMemcpyAsync(c.obs.p, c.d_obs.p, nd, cudaMemcpyDeviceToHost, c.stream_hi));
   PP2D_CUDA(cudaMemcpyAsync(c.rewards.p, c.d_rew.p, (size_t)n * kActions * sizeof(float),
-                            cudaMemcpyDeviceToHost, c.stream));
-  PP2D_CUDA(cudaEventRecord(c.e1, c.stream));
+                            cudaMemcpyDeviceToHost, c.stream_hi));
+  PP2D_CUDA(cudaEventRecord(c.e1, c.stream_hi));
   h->t_phase[0] += now_s() - t0;                 // host: draws, enqueue
   return PP2D_OK;
 }
