@@ -967,17 +967,26 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     PP2D_TRY(round_stage3(h, *ctx[0]));
     PP2D_TRY(round_stage3(h, *ctx[1]));
     tr = now_s();
-    for (size_t i = 0; i < gn; ++i) {
-      float r;
-      best_action(store[i], &actions[g0 + i], &r);
-      if (values) values[g0 + i] = r;
-      if (stats) {
-        stats[(g0 + i) * 4 + 0] = (uint32_t)store[i].v.size();
-        stats[(g0 + i) * 4 + 1] = (uint32_t)store[i].q.size();
-        stats[(g0 + i) * 4 + 2] = store[i].v[store[i].root].depth;
-        stats[(g0 + i) * 4 + 3] = store[i].expansions;
+    const int gni = (int)gn;
+#pragma omp parallel num_threads(host_threads()) if (gni >= 64)
+    {
+      std::vector<int> back;                       // belief slots of this thread's trees
+#pragma omp for schedule(static) nowait
+      for (int i = 0; i < gni; ++i) {
+        float r;
+        best_action(store[i], &actions[g0 + i], &r);
+        if (values) values[g0 + i] = r;
+        if (stats) {
+          stats[(g0 + i) * 4 + 0] = (uint32_t)store[i].v.size();
+          stats[(g0 + i) * 4 + 1] = (uint32_t)store[i].q.size();
+          stats[(g0 + i) * 4 + 2] = store[i].v[store[i].root].depth;
+          stats[(g0 + i) * 4 + 3] = store[i].expansions;
+        }
+        for (VNodeH& v : store[i].v)               // every node still holding a belief
+          if (v.slot >= 0) { back.push_back(v.slot); v.slot = -1; }
       }
-      free_subtree_v(h, store[i], store[i].root);
+#pragma omp critical
+      h->free_slots.insert(h->free_slots.end(), back.begin(), back.end());
     }
     h->t_phase[6] += now_s() - tr;               // actions out, slots back
   }
