@@ -385,13 +385,14 @@ struct RoundCtx {
   struct Child { uint8_t a, z; float w; };
   std::vector<Job> jobs;
   int n = 0, nk = 0;
-  PinnedBuf<int> slots, kslots, gfirst;
+  PinnedBuf<int> slots, kslots, gfirst, kgroup;
   PinnedBuf<float> draws, rewards, ev;
   PinnedBuf<BayesItem> items;
   PinnedBuf<uint8_t> obs;
   std::vector<int> first;
   std::vector<Child> kids;
-  DevBuf<int> d_jobslots, d_kslots, d_gfirst;
+  DevBuf<int> d_jobslots, d_kslots, d_gfirst, d_kgroup;
+  DevBuf<float> d_pred;              // [HW][ngp] predictions of the Q nodes of a round
   DevBuf<float> d_prefix, d_draws, d_rew, d_sums, d_vals, d_out;
   DevBuf<uint8_t> d_obs;
   DevBuf<BayesItem> d_items;
@@ -402,7 +403,8 @@ struct RoundCtx {
                                      // that it is not queued behind the other group's
                                      // values launch and the host can move on
   ~RoundCtx() {
-    slots.release(); kslots.release(); gfirst.release(); draws.release(); rewards.release();
+    slots.release(); kslots.release(); gfirst.release(); kgroup.release(); draws.release();
+    rewards.release(); d_kgroup.release(); d_pred.release();
     ev.release(); items.release(); obs.release();
     d_jobslots.release(); d_kslots.release(); d_gfirst.release(); d_prefix.release();
     d_draws.release(); d_rew.release(); d_sums.release(); d_vals.release(); d_out.release();
@@ -517,6 +519,7 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
   PP2D_TRY(c.kslots.ensure(nk));
   PP2D_TRY(c.items.ensure(nk));
   PP2D_TRY(c.gfirst.ensure((size_t)n * kActions + 1));
+  PP2D_TRY(c.kgroup.ensure(nk));
   PP2D_TRY(c.ev.ensure((size_t)nk * 4));
   for (int k = 0; k < nk; ++k) PP2D_TRY(alloc_slot(h, &c.kslots.p[k]));
   c.kids.resize(nk);
@@ -533,6 +536,7 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
         if (!count[z]) continue;
         c.kids[k] = RoundCtx::Child{(uint8_t)a, (uint8_t)z, (float)count[z] / (float)kSamples};
         c.items.p[k] = BayesItem{c.slots.p[i], c.kslots.p[k], (uint8_t)a, (uint8_t)z};
+        c.kgroup.p[k] = i * kActions + a;
         ++k;
       }
     }
@@ -550,18 +554,24 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
                             cudaMemcpyHostToDevice, c.stream));
   PP2D_CUDA(cudaMemcpyAsync(c.d_kslots.p, c.kslots.p, nk * sizeof(int),
                             cudaMemcpyHostToDevice, c.stream));
+  const int ngp = (ng + 31) / 32 * 32;
+  PP2D_TRY(c.d_kgroup.ensure(nk));
+  PP2D_TRY(c.d_pred.ensure((size_t)HW * ngp));
+  PP2D_CUDA(cudaMemcpyAsync(c.d_kgroup.p, c.kgroup.p, nk * sizeof(int), cudaMemcpyHostToDevice,
+                            c.stream));
   dim3 bgrid((ng + 31) / 32, (HW + 7) / 8);
-  pomdp_bayes_group_kernel<<<bgrid, 256, 0, c.stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
-                                                         c.d_items.p, c.d_gfirst.p, ng,
-                                                         h->d_bel, h->d_bel);
+  pomdp_predict_kernel<<<bgrid, 256, 0, c.stream>>>(h->H, h->W, h->cap, ngp, h->d_tp,
+                                                     c.d_items.p, c.d_gfirst.p, ng, h->d_bel,
+                                                     c.d_pred.p);
   count_launch();
   h->n_bayes += nk;
-  pomdp_colsum_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(HW, h->cap, c.d_kslots.p, nk,
-                                                               h->d_bel, c.d_sums.p);
+  pomdp_child_sum_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(
+      HW, ngp, h->d_mp, c.d_items.p, c.d_kgroup.p, nk, c.d_pred.p, c.d_sums.p);
   count_launch();
   dim3 sgrid((nk + 31) / 32, (HW + 7) / 8);
-  pomdp_scale_kernel<<<sgrid, 256, 0, c.stream>>>(HW, h->cap, c.d_kslots.p, nk, c.d_sums.p,
-                                                   h->d_bel);
+  pomdp_child_write_kernel<<<sgrid, 256, 0, c.stream>>>(HW, h->cap, ngp, h->d_mp, c.d_items.p,
+                                                         c.d_kgroup.p, nk, c.d_pred.p,
+                                                         c.d_sums.p, h->d_bel);
   count_launch();
   dim3 vgrid((nk + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
   pomdp_values_kernel<<<vgrid, 256, 0, c.stream>>>(HW, h->cap, h->ld, h->ncol, c.d_kslots.p, nk,

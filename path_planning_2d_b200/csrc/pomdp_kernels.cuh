@@ -132,23 +132,25 @@ pomdp_bayes_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
 
 // The children of one Q node (same parent belief, same action) differ only in
 // the observation: the predicted belief sum_s P(s,u,s') b(s) is computed once
-// per (Q node, cell) and multiplied by the likelihood of every observation
-// that got a child.  Same arithmetic per child as pomdp_bayes_kernel.
-// group g: children items[first[g] .. first[g+1]) (all with src / act of the
-// group's first item); threadIdx.x runs over groups, so the 9 Q nodes of one
-// expanded node read the same belief addresses.
+// per (Q node, cell).  group g: children items[first[g] .. first[g+1]) (all
+// with the src / act of the group's first item); threadIdx.x runs over groups,
+// so the 9 Q nodes of one expanded node read the same belief addresses.
+// Bayes update, column sum and division of a round without ever storing the
+// un-normalised children: the prediction of a Q node is written
+// once to pred[cell * ngp + g]; the sequential sum of a child and its
+// normalised belief are both formed from pred * L on the fly.  Per element the
+// operations are those of pomdp_bayes_kernel + pomdp_colsum_kernel +
+// pomdp_scale_kernel (FMUL.FTZ by the likelihood, sequential rounded adds,
+// IEEE division), so the bits are the same; the traffic drops from
+// 4 x |children| to 2 x |Q nodes| + 1 x |children| belief-sized passes.
 __global__ void __launch_bounds__(256)
-pomdp_bayes_group_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
-                         const float* __restrict__ meas_prob,
-                         const BayesItem* __restrict__ items,
-                         const int* __restrict__ first, int n_groups,
-                         const float* bel_in, float* bel_out) {
+pomdp_predict_kernel(int H, int W, int cap, int ngp, const float* __restrict__ trans_prob,
+                     const BayesItem* __restrict__ items, const int* __restrict__ first,
+                     int n_groups, const float* __restrict__ bel, float* __restrict__ pred) {
   const int g = blockIdx.x * 32 + (threadIdx.x & 31);
   const int cell = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (g >= n_groups || cell >= H * W) return;
-  const int k0 = first[g], k1 = first[g + 1];
-  if (k0 == k1) return;
-  const BayesItem it = items[k0];
+  const BayesItem it = items[first[g]];
   const int x = cell % W, y = cell / W;
   float p = 0.0f;
 #pragma unroll
@@ -157,16 +159,52 @@ pomdp_bayes_group_kernel(int H, int W, int cap, const float* __restrict__ trans_
     if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
     const size_t sidx = (size_t)sy * W + sx;
     const float tp = __ldg(trans_prob + 81 * sidx + 9 * it.act + (8 - s));
-    const float b = bel_in[sidx * cap + it.src];
+    const float b = bel[sidx * cap + it.src];
     if (s < 8) p = fma_ftz(tp, b, p);
     else p = add_ftz(p, mul_ftz(tp, b));
   }
-  const float* L = meas_prob + 16 * (size_t)cell;
-  bel_out[(size_t)cell * cap + it.dst] = mul_ftz(p, __ldg(L + it.obs));
-  for (int k = k0 + 1; k < k1; ++k) {
-    const BayesItem c = items[k];
-    bel_out[(size_t)cell * cap + c.dst] = mul_ftz(p, __ldg(L + c.obs));
+  pred[(size_t)cell * ngp + g] = p;
+}
+
+// sums[k] = accumulate over cells of pred * L(., z_k), in cell order.
+__global__ void __launch_bounds__(128)
+pomdp_child_sum_kernel(int HW, int ngp, const float* __restrict__ meas_prob,
+                       const BayesItem* __restrict__ items, const int* __restrict__ kgroup,
+                       int n, const float* __restrict__ pred, float* __restrict__ sums) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float* pc = pred + kgroup[k];
+  const float* L = meas_prob + items[k].obs;
+  float sum = 0.0f;
+  int s = 0;
+  for (; s + 16 <= HW; s += 16) {
+    float v[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] = pc[(size_t)(s + j) * ngp];
+      l[j] = __ldg(L + (size_t)(s + j) * 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sum = __fadd_rn(sum, mul_ftz(v[j], l[j]));
   }
+  for (; s < HW; ++s)
+    sum = __fadd_rn(sum, mul_ftz(pc[(size_t)s * ngp], __ldg(L + (size_t)s * 16)));
+  sums[k] = sum;
+}
+
+// child belief = (pred * L) / sum, written once into its pool column.
+__global__ void __launch_bounds__(256)
+pomdp_child_write_kernel(int HW, int cap, int ngp, const float* __restrict__ meas_prob,
+                         const BayesItem* __restrict__ items, const int* __restrict__ kgroup,
+                         int n, const float* __restrict__ pred, const float* __restrict__ sums,
+                         float* __restrict__ bel) {
+  const int k = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int cell = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (k >= n || cell >= HW) return;
+  const BayesItem it = items[k];
+  const float v = mul_ftz(pred[(size_t)cell * ngp + kgroup[k]],
+                          __ldg(meas_prob + 16 * (size_t)cell + it.obs));
+  bel[(size_t)cell * cap + it.dst] = __fdiv_rn(v, sums[k]);
 }
 
 // ---------------------------------------------------------------- B3 -------
