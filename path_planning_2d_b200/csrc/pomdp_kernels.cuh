@@ -177,15 +177,15 @@ pomdp_child_sum_kernel(int HW, int ngp, const float* __restrict__ meas_prob,
   const float* L = meas_prob + items[k].obs;
   float sum = 0.0f;
   int s = 0;
-  for (; s + 16 <= HW; s += 16) {
-    float v[16], l[16];
+  for (; s + 32 <= HW; s += 32) {
+    float v[32], l[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 32; ++j) {
       v[j] = pc[(size_t)(s + j) * ngp];
       l[j] = __ldg(L + (size_t)(s + j) * 16);
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) sum = __fadd_rn(sum, mul_ftz(v[j], l[j]));
+    for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, mul_ftz(v[j], l[j]));
   }
   for (; s < HW; ++s)
     sum = __fadd_rn(sum, mul_ftz(pc[(size_t)s * ngp], __ldg(L + (size_t)s * 16)));
