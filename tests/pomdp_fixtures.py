@@ -1,10 +1,12 @@
 """Inputs for the POMDP tests and bench: beliefs and alpha vectors.
 
 The alpha vectors the tree consumes come from the FIB and PBVI offline
-solvers in the reference ("next" rows of SURVEY.md section 8f).  Here FIB
-alphas are produced by the oracle's restatement of the FIB solver and the
-PBVI set is replaced by blind-policy value vectors (valid lower bounds) and
-convex mixtures of them; the tree code only needs *some* alpha set."""
+solvers (reference: fast_informed_bound_cuda.cu, point_based_value_iteration_
+cuda.cu; product: pp2d_pomdp_solve_fib / pp2d_pomdp_solve_pbvi, which the
+bench uses).  The tree tests need small, CPU-computable sets: FIB alphas from
+the oracle's restatement of the FIB solver, and as lower-bound set blind-policy
+value vectors (valid lower bounds) plus convex mixtures of them -- the tree
+code accepts any alpha set."""
 import os
 
 import numpy as np
@@ -65,7 +67,8 @@ def bundled_alphas(n_pbvi=500, seed=0):
     9 FIB alpha vectors (oracle FIB solver run to its stopping rule, committed
     as tests/golden/alphas_sparse_map_100x40.npz) and n_pbvi lower-bound
     vectors = the 9 blind-policy values plus seeded convex mixtures of them
-    (stand-in for the PBVI set, which is a "next" row)."""
+    (a CPU-computable lower-bound set of the same size as the reference's PBVI
+    set; used by profiling runs that must skip the 29 000 solver launches)."""
     g = np.load(os.path.join(cases.GOLDEN, "alphas_sparse_map_100x40.npz"))
     fib, blind = g["fib"], g["blind"]
     rng = np.random.default_rng(seed)
