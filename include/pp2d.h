@@ -143,11 +143,11 @@ int pp2d_mdp_solve(pp2d_mdp* h, uint32_t* sweeps_out, double* residuals,
  * (cudaOneStepPolicyEvaluation, path_planning_2d_cuda.cu:266-306), the
  * inf-norm of the change of J over the round, one policy improvement
  * (cudaPolicyImprovment, :308-355), until the inf-norm is <=
- * 5/(1-gamma)*1e-3.  residuals / changed (optional, caller-sized for
- * max_rounds entries, or large enough when max_rounds = 0) receive one entry
- * per round; max_rounds = 0 runs to the stopping rule. */
+ * 5/(1-gamma)*1e-3.  residuals / changed (optional, `capacity` entries each)
+ * receive one entry per round, rounds beyond `capacity` are not recorded;
+ * max_rounds = 0 runs to the stopping rule. */
 int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* residuals,
-                              uint32_t* changed, uint32_t max_rounds);
+                              uint32_t* changed, uint32_t capacity, uint32_t max_rounds);
 
 /*
  * Replaces the two result cudaMemcpy calls
@@ -211,7 +211,13 @@ int pp2d_mdp_halo(pp2d_mdp* h, pp2d_halo* out);
 #define PP2D_IPC_DESC_BYTES 256
 int pp2d_mdp_ipc_export(pp2d_mdp* h, void* desc /* PP2D_IPC_DESC_BYTES */);
 int pp2d_mdp_ipc_connect(pp2d_mdp* h, const void* up_desc, const void* down_desc);
-/* timed_out != 0: a flag wait gave up (neighbour missing); results invalid. */
+/* timed_out != 0: a flag wait gave up after PP2D_P2P_SPIN_LIMIT polls (default
+ * 2^24, a few seconds: the neighbour is missing or did not run the same
+ * launches); J of this shard is invalid from then on.  The failure is also
+ * reported without this call: the residual of the shard becomes +inf
+ * (pp2d_mdp_residual fails with PP2D_ERR_STATE, a caller that reduces
+ * pp2d_mdp_residual_device itself sees inf) and pp2d_mdp_download fails with
+ * PP2D_ERR_STATE.  pp2d_mdp_reset clears the condition. */
 int pp2d_mdp_p2p_status(pp2d_mdp* h, int* timed_out);
 
 /* Device-side residual for shards: enqueue the reduction, then read it. */
@@ -241,6 +247,19 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h);
  * (model_generation_cuda.cu:366-371); any pointer may be NULL. */
 int pp2d_pomdp_model_tables(pp2d_pomdp* h, float* trans_prob, float* meas_prob,
                             float* stage_reward);
+/*
+ * Replaces the upload half of loadModelDataFromFile
+ * (src/pomdp/model_generation_cuda.cu:109-159, the three cudaMemcpy at
+ * :150-156; call site src/pomdp/path_planning_2d.cu:131): the reference's
+ * DEFAULT launch (read_data_from_file=true) does not generate the model, it
+ * reads the "%15.8f" text tables back and uploads those -- rounded to 8
+ * decimals, so e.g. 0.02^4 becomes 0.00000016.  The tables replace the ones
+ * pp2d_pomdp_create generated (layouts as in pp2d_pomdp_model_tables); any
+ * pointer may be NULL (that table is kept).  Parsing the files stays on the
+ * host side (include/pp2d/planners.hpp: loadModelDataFromFile).
+ */
+int pp2d_pomdp_set_model_tables(pp2d_pomdp* h, const float* trans_prob,
+                                const float* meas_prob, const float* stage_reward);
 /* The 100 curand_uniform values cudaForwardSampling consumes for its 50
  * samples (search_tree_cuda.cu:84-92,117,134; XORWOW, seed 1234, subsequence
  * = sample index, re-initialised per call, hence constant). */

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -186,9 +187,10 @@ class MdpPathPlanning2d : public PathPlanning2dBase {
     std::vector<double> res(4096);
     std::vector<uint32_t> changed(4096);
     uint32_t sweeps = 0;
-    PP2D_CHECK(pp2d_mdp_policy_iteration(mdp_, &sweeps, res.data(), changed.data(), 0));
+    PP2D_CHECK(pp2d_mdp_policy_iteration(mdp_, &sweeps, res.data(), changed.data(),
+                                         (uint32_t)res.size(), 0));
     total_iterations += (int)sweeps;
-    for (uint32_t r = 0; r < sweeps / 50; ++r) {
+    for (uint32_t r = 0; r < sweeps / 50 && r < res.size(); ++r) {
       std::printf("Inf-norm: %f\n", res[r]);
       std::printf("# of changed actions: %u\n", changed[r]);
     }
@@ -222,10 +224,13 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
   }
 
   // src/pomdp/path_planning_2d.cu:80-166.  read_data_from_file = false: the
-  // FIB and PBVI offline solvers run on the GPU (path_planning_2d.cu:109-125);
-  // true: the alpha vectors come from the text files the reference's
-  // save_data service writes (fib_alphas, fib_actions, pbvi_alphas,
-  // pbvi_actions) in `data_dir`.
+  // model is generated and the FIB and PBVI offline solvers run on the GPU
+  // (path_planning_2d.cu:109-125); true (the launch-file default): model
+  // tables AND alpha vectors come from the text files the reference's
+  // save_data service writes (model_data_trans_prob, model_data_meas_prob,
+  // model_data_stage_reward, fib_alphas, fib_actions, pbvi_alphas,
+  // pbvi_actions) in `data_dir` (path_planning_2d.cu:127-143), or, with
+  // data_format = "binary", from the lossless pp2d_data.bin.
   bool initialize() override {
     if (!loadParameters()) {
       std::fprintf(stderr, "Cannot load all required parameters...\n");
@@ -258,7 +263,11 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
       pbvi_actions.resize(belief_set_size);
       PP2D_CHECK(pp2d_pomdp_solve_pbvi(pomdp_, initial_belief.data(), belief_set_size, 1, 0,
                                        nullptr, pbvi_alphas.data(), pbvi_actions.data()));
-    } else if (!loadFibDataFromFile() || !loadPbviDataFromFile()) {
+    } else if (data_format == "binary") {
+      if (!loadDataBinary(data_dir)) return false;
+    } else if (!loadModelDataFromFile() || !loadFibDataFromFile() || !loadPbviDataFromFile()) {
+      // path_planning_2d.cu:127-143: the default launch starts from the seven
+      // text files; the model tables it plans with are the ROUNDED ones
       return false;
     }
     PP2D_CHECK(pp2d_pomdp_set_alphas(pomdp_, fib_alphas.data(), fib_actions.data(),
@@ -309,7 +318,60 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
   }
   // saveDataCallback (src/pomdp/path_planning_2d.cu:259-273)
   bool saveDataCallback(const std::string& dir) {
+    if (data_format == "binary") return saveDataBinary(dir);
     return saveModelDataToFile(dir) && saveFibDataToFile(dir) && savePbviDataToFile(dir);
+  }
+
+  // Lossless variant of the checkpoint: one file,
+  // raw little-endian float32 / uint8 arrays in the order of the seven text
+  // files, so that a planner restarted from it plans with the bits it saved.
+  struct BinaryHeader {
+    char magic[8];                      // "PP2DCKP1"
+    uint32_t height, width, belief_set_size, reserved;
+  };
+  bool saveDataBinary(const std::string& dir) {
+    const size_t n = (size_t)map_height * map_width;
+    std::vector<float> tp(n * 81), mp(n * 16), sr(n * 9);
+    PP2D_CHECK(pp2d_pomdp_model_tables(pomdp_, tp.data(), mp.data(), sr.data()));
+    FILE* f = std::fopen((dir + "/pp2d_data.bin").c_str(), "wb");
+    if (!f) return false;
+    BinaryHeader hd = {{'P', 'P', '2', 'D', 'C', 'K', 'P', '1'}, map_height, map_width,
+                       belief_set_size, 0};
+    bool ok = std::fwrite(&hd, sizeof(hd), 1, f) == 1;
+    auto put = [&](const void* p, size_t bytes) {
+      ok = ok && (bytes == 0 || std::fwrite(p, 1, bytes, f) == bytes);
+    };
+    put(tp.data(), tp.size() * 4); put(mp.data(), mp.size() * 4); put(sr.data(), sr.size() * 4);
+    put(fib_alphas.data(), fib_alphas.size() * 4); put(fib_actions.data(), fib_actions.size());
+    put(pbvi_alphas.data(), pbvi_alphas.size() * 4); put(pbvi_actions.data(), pbvi_actions.size());
+    return std::fclose(f) == 0 && ok;
+  }
+  bool loadDataBinary(const std::string& dir) {
+    FILE* f = std::fopen((dir + "/pp2d_data.bin").c_str(), "rb");
+    if (!f) { std::fprintf(stderr, "cannot open %s/pp2d_data.bin\n", dir.c_str()); return false; }
+    BinaryHeader hd;
+    bool ok = std::fread(&hd, sizeof(hd), 1, f) == 1 &&
+              std::memcmp(hd.magic, "PP2DCKP1", 8) == 0 && hd.height == map_height &&
+              hd.width == map_width && hd.belief_set_size == belief_set_size;
+    if (!ok) {
+      std::fprintf(stderr, "Data dimension is not set properly\n");
+      std::fclose(f);
+      return false;
+    }
+    const size_t n = (size_t)map_height * map_width;
+    std::vector<float> tp(n * 81), mp(n * 16), sr(n * 9);
+    fib_alphas.resize(n * 9); fib_actions.resize(9);
+    pbvi_alphas.resize((size_t)belief_set_size * n); pbvi_actions.resize(belief_set_size);
+    auto get = [&](void* p, size_t bytes) {
+      ok = ok && (bytes == 0 || std::fread(p, 1, bytes, f) == bytes);
+    };
+    get(tp.data(), tp.size() * 4); get(mp.data(), mp.size() * 4); get(sr.data(), sr.size() * 4);
+    get(fib_alphas.data(), fib_alphas.size() * 4); get(fib_actions.data(), fib_actions.size());
+    get(pbvi_alphas.data(), pbvi_alphas.size() * 4); get(pbvi_actions.data(), pbvi_actions.size());
+    std::fclose(f);
+    if (!ok) { std::fprintf(stderr, "Data dimension is not set properly\n"); return false; }
+    PP2D_CHECK(pp2d_pomdp_set_model_tables(pomdp_, tp.data(), mp.data(), sr.data()));
+    return true;
   }
 
   std::vector<float> initial_belief;
@@ -333,6 +395,7 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
     if (!getParam("max_search_tree_depth", max_search_tree_depth)) return false;
     if (!getParam("max_online_iteration", max_online_iteration)) return false;
     getParam("data_dir", data_dir);
+    getParam("data_format", data_format);     // "text" (reference) | "binary" (lossless)
     int32_t n = 500;                        // belief_set_size, path_planning_2d.cu:122
     if (getParam("belief_set_size", n)) belief_set_size = (uint32_t)n;
     return true;
@@ -378,6 +441,17 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
     std::fclose(f);
     return true;
   }
+  // model_generation_cuda.cu:109-159: the three "%15.8f" tables, then upload.
+  bool loadModelDataFromFile() {
+    const size_t n = (size_t)map_height * map_width;
+    std::vector<float> tp(n * 81), mp(n * 16), sr(n * 9);
+    if (!readFloats(data_dir + "/model_data_trans_prob", tp) ||
+        !readFloats(data_dir + "/model_data_meas_prob", mp) ||
+        !readFloats(data_dir + "/model_data_stage_reward", sr))
+      return false;
+    PP2D_CHECK(pp2d_pomdp_set_model_tables(pomdp_, tp.data(), mp.data(), sr.data()));
+    return true;
+  }
   // fast_informed_bound_cuda.cu:361-394
   bool loadFibDataFromFile() {
     fib_alphas.resize((size_t)map_height * map_width * 9);
@@ -398,7 +472,7 @@ class PomdpPathPlanning2d : public PathPlanning2dBase {
   bool read_from_file = true;
   int32_t max_search_tree_depth = 50, max_online_iteration = 15;
   uint32_t belief_set_size = 500;
-  std::string data_dir = ".";
+  std::string data_dir = ".", data_format = "text";
   std::vector<float> fib_alphas, pbvi_alphas;
   std::vector<uint8_t> fib_actions, pbvi_actions;
 };

@@ -31,6 +31,8 @@
 #include <map>
 #include <vector>
 
+#include <unistd.h>
+
 #include <cuda_runtime.h>
 
 /* SearchTree::root is private; the dump below needs to walk the tree. */
@@ -58,6 +60,14 @@ void backupAlphaVectors(const uint32_t height, const uint32_t width, const float
                         const uint32_t set_size, const float* const __restrict__ b_set_in,
                         float* const __restrict__ alphas_out,
                         uint8_t* const __restrict__ actions_out);
+/* the save_data service / read_data_from_file=true path
+ * (src/pomdp/path_planning_2d.cu:41-56, 127-143, 259-273) */
+void saveModelDataToFile(const uint32_t, const uint32_t);
+bool loadModelDataFromFile(const uint32_t, const uint32_t);
+void saveFibDataToFile(const uint32_t, const uint32_t);
+bool loadFibDataFromFile(const uint32_t, const uint32_t);
+void savePbviDataToFile(const uint32_t, const uint32_t);
+bool loadPbviDataFromFile(const uint32_t, const uint32_t);
 void evaluateFibCpu(const uint32_t, const uint32_t, const float* const, float&, uint8_t&);
 void evaluatePbviCpu(const uint32_t, const uint32_t, const float* const, float&, uint8_t&);
 
@@ -172,6 +182,36 @@ int ref_full_set_alphas(const float* fib, const uint8_t* fib_actions, const floa
   memcpy(host_pbvi_alphas, pbvi, n * g_npbvi * sizeof(float));
   if (pbvi_actions) memcpy(host_pbvi_actions, pbvi_actions, g_npbvi);
   else memset(host_pbvi_actions, 0, g_npbvi);
+  return 0;
+}
+
+/* saveDataCallback (src/pomdp/path_planning_2d.cu:259-273): the reference's
+ * own writers, which always write into the current directory. */
+int ref_full_save_data(const char* dir) {
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof(cwd)) || chdir(dir) != 0) return -1;
+  saveModelDataToFile(g_h, g_w);
+  saveFibDataToFile(g_h, g_w);
+  savePbviDataToFile(g_h, g_w);
+  return chdir(cwd);
+}
+/* The read_data_from_file=true branch of initialize()
+ * (src/pomdp/path_planning_2d.cu:127-143): the reference's own readers replace
+ * host_* and dev_* tables and alpha vectors by what the text files hold. */
+int ref_full_load_data(const char* dir) {
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof(cwd)) || chdir(dir) != 0) return -1;
+  const bool ok = loadModelDataFromFile(g_h, g_w) && loadFibDataFromFile(g_h, g_w) &&
+                  loadPbviDataFromFile(g_h, g_w);
+  if (chdir(cwd) != 0) return -1;
+  return ok ? 0 : -2;
+}
+int ref_full_get_alphas(float* fib, uint8_t* fib_actions, float* pbvi, uint8_t* pbvi_actions) {
+  const size_t n = (size_t)g_h * g_w;
+  if (fib) memcpy(fib, host_fib_alphas, n * 9 * sizeof(float));
+  if (fib_actions) memcpy(fib_actions, host_fib_actions, 9);
+  if (pbvi) memcpy(pbvi, host_pbvi_alphas, n * g_npbvi * sizeof(float));
+  if (pbvi_actions) memcpy(pbvi_actions, host_pbvi_actions, g_npbvi);
   return 0;
 }
 

@@ -44,7 +44,7 @@ SIGNATURES = {
     "pp2d_mdp_residual": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "pp2d_mdp_residual_device": (_i, [_vp, ctypes.POINTER(_vp)]),
     "pp2d_mdp_solve": (_i, [_vp, ctypes.POINTER(_u32), _vp, _u32]),
-    "pp2d_mdp_policy_iteration": (_i, [_vp, _vp, _vp, _vp, _u32]),
+    "pp2d_mdp_policy_iteration": (_i, [_vp, _vp, _vp, _vp, _u32, _u32]),
     "pp2d_mdp_download": (_i, [_vp, _vp, _vp]),
     "pp2d_mdp_plan": (_i, [_vp, _vp, _vp]),
     "pp2d_mdp_plan_batch": (_i, [_vp, _vp, _u32, _vp]),
@@ -59,6 +59,7 @@ SIGNATURES = {
                                ctypes.POINTER(_vp)]),
     "pp2d_pomdp_destroy": (None, [_vp]),
     "pp2d_pomdp_model_tables": (_i, [_vp, _vp, _vp, _vp]),
+    "pp2d_pomdp_set_model_tables": (_i, [_vp, _vp, _vp, _vp]),
     "pp2d_pomdp_sampling_uniforms": (_i, [_vp, _vp]),
     "pp2d_pomdp_set_alphas": (_i, [_vp, _vp, _vp, _vp, _vp, _u32]),
     "pp2d_pomdp_solve_fib": (_i, [_vp, _vp, _vp, ctypes.POINTER(_u32), _u32]),

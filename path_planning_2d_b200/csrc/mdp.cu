@@ -142,6 +142,10 @@ struct pp2d_mdp {
   void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned int p2p_iter = 0, p2p_expect_top = 0, p2p_expect_bot = 0;
   int p2p_debug = 0, p2p_edge_rows = 16;
+  unsigned int p2p_spin_limit = 1u << 24;   // polls (32-256 ns apart) before kFlagError
+  // ghost-row contract of a shard without peer-to-peer rows: sweeps that may
+  // still run before the caller has to refresh the ghost rows (pp2d_mdp_halo)
+  int halo_budget = kPadRows;
   // tuning knobs (environment overridable, see mdp_config)
   int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6, waves = 1;
   bool fused_policy = true;   // arg-min sweep as the second half of a fused pair
@@ -284,6 +288,7 @@ static int launch_sweep(pp2d_mdp* h) {
     p.expect_bot = h->p2p_expect_bot;
     p.p2p_debug = (unsigned int)h->p2p_debug;
     p.edge_rows = h->p2p_edge_rows;
+    p.spin_limit = h->p2p_spin_limit;
   }
   const int warps_per_cta = kWarpsPerCta;
   const int grid = (p.n_units + warps_per_cta - 1) / warps_per_cta;
@@ -340,6 +345,10 @@ static int upload_map(pp2d_mdp* h, const uint8_t* map) {
   PP2D_CUDA(cudaMemsetAsync(h->j[1], 0, h->plane * sizeof(float), h->stream));
   PP2D_CUDA(cudaMemsetAsync(h->jchk, 0, h->plane * sizeof(float), h->stream));
   PP2D_CUDA(cudaMemsetAsync(h->action, 0, owned, h->stream));
+  // a timed-out hand-shake of an earlier solve must not poison this one (the
+  // launch counters in the flag block are cumulative and stay)
+  PP2D_CUDA(cudaMemsetAsync(h->flags + kFlagError, 0, sizeof(unsigned int), h->stream));
+  h->halo_budget = kPadRows;
   PP2D_CUDA(cudaMemcpyAsync(h->occ, map + (size_t)occ_row0 * h->W,
                             (size_t)occ_rows * h->W, cudaMemcpyHostToDevice,
                             h->stream));
@@ -411,6 +420,10 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->waves = env_int("PP2D_MDP_WAVES", 1);
   h->p2p_debug = env_int("PP2D_P2P_DEBUG", 0);
   h->p2p_edge_rows = env_int("PP2D_P2P_EDGE_ROWS", 16);
+  {
+    const int lim = env_int("PP2D_P2P_SPIN_LIMIT", 1 << 24);
+    h->p2p_spin_limit = lim > 0 ? (unsigned int)lim : 1u;
+  }
   if (h->p2p_edge_rows < kPadRows) h->p2p_edge_rows = kPadRows;
   if (h->waves < 1) h->waves = 1;
   if (h->prefetch_rows < kPrefetch) h->prefetch_rows = kPrefetch;
@@ -447,7 +460,7 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
 extern "C" {
 
 const char* pp2d_last_error(void) { return g_err; }
-int pp2d_abi_version(void) { return 1; }
+int pp2d_abi_version(void) { return 2; }
 uint64_t pp2d_kernel_launches(void) { return g_launches.load(); }
 
 int pp2d_mdp_create(uint32_t height, uint32_t width, const uint8_t* map,
@@ -512,6 +525,19 @@ int pp2d_mdp_sweeps_ex(pp2d_mdp* h, uint32_t n, int want_action) {
   if (h->pi_mode)
     return fail(PP2D_ERR_STATE, "value-iteration sweeps after pp2d_mdp_policy_iteration "
                                 "need a pp2d_mdp_reset first");
+  // Ghost rows are good for kPadRows sweeps.  Fused peer-to-peer launches
+  // refresh the neighbours' ghost rows themselves; everything else (shards
+  // without peer mappings, single sweeps, PP2D_MDP_FUSED_POLICY=0) consumes
+  // the budget until the caller exchanges rows through pp2d_mdp_halo.
+  const bool has_neighbour = h->sharded && (h->row_begin > 0 || h->row_begin + h->H < h->Htot);
+  const bool p2p_fused = h->p2p && n == 2 && (!want_action || h->fused_policy);
+  if (has_neighbour && !p2p_fused) {
+    if ((int)n > h->halo_budget)
+      return fail(PP2D_ERR_STATE,
+                  "%u sweep(s) requested but the ghost rows are only good for %d more: "
+                  "exchange them first (pp2d_mdp_halo)", n, h->halo_budget);
+    h->halo_budget -= (int)n;
+  }
   // Value-only sweeps are fused in pairs; when the action grid is wanted the
   // last sweep is the arg-min variant, which leaves exactly what the
   // reference holds after n launches of cudaOneStepValueIteration.
@@ -559,7 +585,8 @@ int pp2d_mdp_residual_device(pp2d_mdp* h, void** dev_float_out) {
   if (grid < 1) grid = 1;
   mdp_residual_kernel<<<grid, 256, 0, h->stream>>>(
       reinterpret_cast<const float4*>(h->j[h->cur] + off),
-      reinterpret_cast<float4*>(h->jchk + off), n4, floor_bits, h->resid);
+      reinterpret_cast<float4*>(h->jchk + off), n4, floor_bits, h->resid,
+      h->p2p ? h->flags + kFlagError : nullptr);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   PP2D_CUDA(cudaGetLastError());
   h->n_chk = h->n_sweeps;
@@ -575,6 +602,9 @@ int pp2d_mdp_residual(pp2d_mdp* h, float* inf_norm) {
                             cudaMemcpyDeviceToHost, h->stream));
   PP2D_CUDA(cudaStreamSynchronize(h->stream));
   memcpy(inf_norm, h->resid_host, sizeof(float));
+  if (h->p2p && std::isinf(*inf_norm))
+    return fail(PP2D_ERR_STATE, "peer-to-peer ghost-row hand-shake timed out "
+                                "(a neighbour shard did not run the same launches)");
   return PP2D_OK;
 }
 
@@ -603,7 +633,7 @@ int pp2d_mdp_solve(pp2d_mdp* h, uint32_t* sweeps_out, double* residuals,
 }
 
 int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* residuals,
-                              uint32_t* changed, uint32_t max_rounds) {
+                              uint32_t* changed, uint32_t capacity, uint32_t max_rounds) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
   if (h->sharded)
     return fail(PP2D_ERR_STATE, "pp2d_mdp_policy_iteration needs an unsharded handle");
@@ -649,9 +679,9 @@ int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* 
       uint32_t diff = 0;
       for (size_t i = 0; i < owned; ++i) diff += a_prev[i] != a_curr[i];
       a_prev.swap(a_curr);
-      if (max_rounds == 0 || round < max_rounds) changed[round] = diff;
+      if (round < capacity) changed[round] = diff;
     }
-    if (residuals && (max_rounds == 0 || round < max_rounds)) residuals[round] = cost_inf_norm;
+    if (residuals && round < capacity) residuals[round] = cost_inf_norm;
     ++round;
     if (max_rounds > 0 && round >= max_rounds) break;
   } while (cost_inf_norm > max_optimal_cost * 1e-3);
@@ -661,6 +691,14 @@ int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* 
 
 int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (h->p2p) {
+    int timed_out = 0;
+    int rc = pp2d_mdp_p2p_status(h, &timed_out);
+    if (rc != PP2D_OK) return rc;
+    if (timed_out)
+      return fail(PP2D_ERR_STATE, "peer-to-peer ghost-row hand-shake timed out: J and the "
+                                  "action grid of this shard are invalid");
+  }
   const size_t owned = (size_t)h->H * h->W;
   if (cost) {
     if (!h->dense) PP2D_CUDA(cudaMalloc(&h->dense, owned * sizeof(float)));
@@ -816,6 +854,7 @@ int pp2d_mdp_halo(pp2d_mdp* h, pp2d_halo* out) {
   out->send_bottom = j + (size_t)h->H * row;               // rows H-2, H-1
   out->recv_bottom = j + (size_t)(h->H + kPadRows) * row;  // rows H, H+1
   out->bytes = kPadRows * row * sizeof(float);
+  h->halo_budget = kPadRows;     // the caller is about to refresh the ghost rows
   return PP2D_OK;
 }
 

@@ -95,6 +95,7 @@ struct SweepParams {
   unsigned int p2p_debug;               // bit0 no waits, bit1 no peer stores, bit2 no signals
   int edge_rows;                        // rows of a boundary unit processed first
   int lin_len;           // LIN kernels: units are runs of lin_len rows of the strip-major sequence
+  unsigned int spin_limit;  // P2P: polls of a neighbour flag before giving up (kFlagError)
 };
 
 // Flag block of a shard (uint32 each, cudaMalloc'ed, IPC-shared).
@@ -177,10 +178,25 @@ __device__ __forceinline__ float backup(float j0, float j1, float j2, float j3,
 // compiler to just before its first use, which collapses the kPrefetch-deep
 // software pipeline (seen in the ncu source view: long-scoreboard stalls on
 // the first use of every prefetched register).
-template <int CW>
+// NC: the non-coherent (read-only) path.  It is only legal for data nobody
+// writes while the kernel runs, so the P2P instantiations -- whose ghost rows
+// of jin are written by the neighbour GPU during the launch, ordered by the
+// flag hand-shake -- use ordinary weak loads, which the acquire of the flag
+// wait does order.
+template <int CW, bool NC = true>
 __device__ __forceinline__ void load_own(const float* __restrict__ p,
                                          float (&o)[CW]) {
-  if constexpr (CW == 1) {
+  if constexpr (!NC) {
+    if constexpr (CW == 1) {
+      asm volatile("ld.global.f32 %0, [%1];" : "=f"(o[0]) : "l"(p) : "memory");
+    } else if constexpr (CW == 2) {
+      asm volatile("ld.global.v2.f32 {%0, %1}, [%2];"
+                   : "=f"(o[0]), "=f"(o[1]) : "l"(p) : "memory");
+    } else {
+      asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "l"(p) : "memory");
+    }
+  } else if constexpr (CW == 1) {
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(o[0]) : "l"(p));
   } else if constexpr (CW == 2) {
     asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];"
@@ -358,7 +374,7 @@ struct Sweeper {
       constexpr int q = I % kPrefetch;
       fill_row<CW>(nxt[q], A[a2]);
       cc[0] = cnx[q][0];
-      load_own<CW>(pin, nxt[q]);
+      load_own<CW, !P2P>(pin, nxt[q]);
       load_codes<CW>(pcode, cnx[q]);
       asm volatile("prefetch.global.L1 [%0];" :: "l"(pin + l1_ahead));
       asm volatile("prefetch.global.L1 [%0];" :: "l"(pcode + l1_ahead));
@@ -454,9 +470,9 @@ struct Sweeper {
     const float* jin = p.jin + col + (size_t)(ys - 1 + kPadRows) * pitch;
     {
       float r[CW];
-      load_own<CW>(jin, r);
+      load_own<CW, !P2P>(jin, r);
       fill_row<CW>(r, A[0]);
-      load_own<CW>(jin + pitch, r);
+      load_own<CW, !P2P>(jin + pitch, r);
       fill_row<CW>(r, A[1]);
     }
     pin = jin + 2 * pitch;                                  // row ys+1
@@ -473,7 +489,7 @@ struct Sweeper {
     } else {
 #pragma unroll
       for (int d = 0; d < kPrefetch; ++d) {
-        load_own<CW>(pin, nxt[d]);
+        load_own<CW, !P2P>(pin, nxt[d]);
         load_codes<CW>(pcode, cnx[d]);
         pin += pitch;
         pcode += pitch;
@@ -580,10 +596,16 @@ struct Sweeper {
           for (int side = 0; side < 2; ++side) {
             if (!(side == 0 ? top : bot)) continue;
             const unsigned int* f = p.flags + (side == 0 ? kFlagFromUp : kFlagFromDown);
-            long long spins = 0;
+            // A neighbour that never shows up (crashed rank, mismatched launch
+            // counts) must not hang the GPU: after spin_limit polls the error
+            // word is set.  The rows this launch produces from stale ghost rows
+            // are wrong from here on; mdp_residual_kernel turns the error word
+            // into an infinite residual and every host entry point that returns
+            // results checks it, so the failure cannot pass silently.
+            unsigned int spins = 0;
             while ((int)(ld_acquire_sys(f) - want) < 0) {
-              if (++spins > (1ll << 20)) { atomicExch(p.flags + kFlagError, 1u); break; }
-              __nanosleep(64);
+              if (++spins > p.spin_limit) { atomicExch(p.flags + kFlagError, 1u); break; }
+              __nanosleep(spins < 64u ? 32u : 256u);
             }
           }
         }
@@ -696,8 +718,12 @@ __global__ void mdp_code_kernel(const CodeParams p) {
 // order preserving for non-negative floats.
 __global__ void __launch_bounds__(256)
 mdp_residual_kernel(const float4* __restrict__ j, float4* __restrict__ chk,
-                    size_t n4, uint32_t floor_bits, uint32_t* result) {
+                    size_t n4, uint32_t floor_bits, uint32_t* result,
+                    const unsigned int* p2p_error) {
   float m = __uint_as_float(floor_bits);
+  // a ghost-row hand-shake timed out: J is not to be trusted, and the
+  // stopping rule must never be satisfied by it
+  if (p2p_error != nullptr && *p2p_error != 0u) m = __uint_as_float(0x7f800000u);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
     float4 a = j[i], b = chk[i];

@@ -676,6 +676,13 @@ int pp2d_pomdp_create(uint32_t height, uint32_t width, const uint8_t* map,
   int dev_count = 0;
   PP2D_CUDA(cudaGetDeviceCount(&dev_count));
   if (dev_count == 0) return fail(PP2D_ERR_CUDA, "no CUDA device");
+  int dev = 0;
+  PP2D_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  PP2D_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(PP2D_ERR_CUDA, "device %s is sm_%d%d; this library is sm_100a only",
+                prop.name, prop.major, prop.minor);
   pp2d_pomdp* h = new (std::nothrow) pp2d_pomdp;
   if (!h) return fail(PP2D_ERR_INVALID, "out of host memory");
   h->H = (int)height; h->W = (int)width; h->HW = h->H * h->W;
@@ -724,6 +731,21 @@ int pp2d_pomdp_model_tables(pp2d_pomdp* h, float* trans_prob, float* meas_prob,
     PP2D_CUDA(cudaMemcpy(meas_prob, h->d_mp, n * 16 * sizeof(float), cudaMemcpyDeviceToHost));
   if (stage_reward)
     PP2D_CUDA(cudaMemcpy(stage_reward, h->d_sr, n * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+  return PP2D_OK;
+}
+
+int pp2d_pomdp_set_model_tables(pp2d_pomdp* h, const float* trans_prob,
+                                const float* meas_prob, const float* stage_reward) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  const size_t n = (size_t)h->HW;
+  // every stream that reads the tables (rounds of a batch in flight)
+  PP2D_CUDA(cudaDeviceSynchronize());
+  if (trans_prob)
+    PP2D_CUDA(cudaMemcpy(h->d_tp, trans_prob, n * 81 * sizeof(float), cudaMemcpyHostToDevice));
+  if (meas_prob)
+    PP2D_CUDA(cudaMemcpy(h->d_mp, meas_prob, n * 16 * sizeof(float), cudaMemcpyHostToDevice));
+  if (stage_reward)
+    PP2D_CUDA(cudaMemcpy(h->d_sr, stage_reward, n * 9 * sizeof(float), cudaMemcpyHostToDevice));
   return PP2D_OK;
 }
 
@@ -820,6 +842,10 @@ int pp2d_pomdp_bayes_update(pp2d_pomdp* h, const float* beliefs_in, uint32_t n,
   if (!h || !beliefs_in || !actions || !observations || !beliefs_out)
     return fail(PP2D_ERR_INVALID, "NULL argument");
   if (n == 0) return PP2D_OK;
+  for (uint32_t i = 0; i < n; ++i)
+    if (actions[i] >= kActions || observations[i] >= 16)
+      return fail(PP2D_ERR_INVALID, "item %u: action %u / observation %u out of range (9 / 16)",
+                  i, actions[i], observations[i]);
   PP2D_TRY(pool_reserve(h, (size_t)h->cap - h->free_slots.size() + 2 * (size_t)n));
   const int HW = h->HW;
   std::vector<int> in(n), outs(n);
@@ -929,7 +955,11 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
   if (n == 0) return PP2D_OK;
   if (max_iter > 255) max_iter = 255;           // uint8_t counter, pomdp:218-223
   // Worst case per query: root + max_iter * 9 * 16 children.
-  const size_t per_query = 1 + (size_t)max_iter * kActions * 16;
+  size_t per_query = 1 + (size_t)max_iter * kActions * 16;
+  // PP2D_POMDP_SLOTS_PER_QUERY: reserve fewer slots per query up front; the
+  // pool then grows in place (pool_reserve) when the trees outgrow it.
+  const char* spq = getenv("PP2D_POMDP_SLOTS_PER_QUERY");
+  if (spq && atol(spq) > 0) per_query = std::min<size_t>(per_query, (size_t)atol(spq));
   size_t free_b = 0, total_b = 0;
   PP2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
   size_t budget = free_b / 2 + (size_t)h->cap * h->HW * sizeof(float);
@@ -1096,54 +1126,92 @@ int64_t pp2d_tree_dump(const pp2d_tree* tt, float* out, uint64_t cap_nodes) {
 /* SearchTree::update(a, z), search_tree_cuda.cu:548-626 */
 int pp2d_tree_update(pp2d_tree* tt, uint8_t a, uint8_t z) {
   if (!tt) return fail(PP2D_ERR_INVALID, "tree is NULL");
+  if (a >= kActions || z >= 16)
+    return fail(PP2D_ERR_INVALID, "action %u / observation %u out of range (9 / 16)", a, z);
   pp2d_pomdp* h = tt->h;
   Tree& t = tt->t;
-  VNodeH& root = t.v[t.root];
-  if (root.children.empty())
+  if (t.v[t.root].children.empty())
     return fail(PP2D_ERR_STATE, "update() on an unexpanded root (nullptr in the reference)");
+  // Nothing is freed before the arguments are known to be usable.
   int root_q = -1;
-  for (int c : root.children) {
+  for (int c : t.v[t.root].children)
     if (t.q[c].action == a) root_q = c;
-    else free_subtree_q(h, t, c);
-  }
   if (root_q < 0) return fail(PP2D_ERR_INVALID, "no Q node for action %u", a);
   int root_v = -1;
-  for (int c : t.q[root_q].children) {
+  for (int c : t.q[root_q].children)
     if (t.v[c].obs == z) root_v = c;
-    else free_subtree_v(h, t, c);
-  }
-  if (root_v >= 0) {
-    t.v[root_v].parent = -1;
-  } else {
+  int new_slot = -1;
+  float ev[4] = {0, 0, 0, 0};
+  if (root_v < 0) {
     // new root from one Bayes update of the old root belief (tree:586-614)
-    int slot = -1;
-    PP2D_TRY(alloc_slot(h, &slot));
-    BayesItem it{root.slot, slot, a, z};
-    PP2D_TRY(h->d_items.ensure(1));
-    PP2D_TRY(h->d_slots.ensure(1));
-    PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, &it, sizeof(it), cudaMemcpyHostToDevice, h->stream));
-    dim3 bgrid(1, (h->HW + 7) / 8);
-    pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
-                                                     h->d_items.p, 1, h->d_bel, h->d_bel);
-    count_launch();
-    h->n_bayes++;
-    PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, &slot, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    PP2D_TRY(normalize_slots(h, 1, nullptr));
-    std::vector<int> s1{slot};
-    float ev[4];
-    PP2D_TRY(evaluate_slots(h, s1, ev));
-    t.v.emplace_back();
-    root_v = (int)t.v.size() - 1;
-    init_vnode(t.v[root_v], slot, 0, 0.0f, -1, ev, root_v);
-    h->n_vnodes++;
+    PP2D_TRY(alloc_slot(h, &new_slot));
+    int rc = [&]() -> int {
+      BayesItem it{t.v[t.root].slot, new_slot, a, z};
+      PP2D_TRY(h->d_items.ensure(1));
+      PP2D_TRY(h->d_slots.ensure(1));
+      PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, &it, sizeof(it), cudaMemcpyHostToDevice, h->stream));
+      dim3 bgrid(1, (h->HW + 7) / 8);
+      pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+                                                       h->d_items.p, 1, h->d_bel, h->d_bel);
+      count_launch();
+      h->n_bayes++;
+      PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, &new_slot, sizeof(int), cudaMemcpyHostToDevice,
+                                h->stream));
+      PP2D_TRY(normalize_slots(h, 1, nullptr));
+      std::vector<int> s1{new_slot};
+      return evaluate_slots(h, s1, ev);
+    }();
+    if (rc != PP2D_OK) { h->free_slots.push_back(new_slot); return rc; }
   }
-  // drop the old root and the chosen Q node (their beliefs only)
+  // The subtrees that are not kept give their beliefs back (tree:556-584).
+  for (int c : t.v[t.root].children)
+    if (c != root_q) free_subtree_q(h, t, c);
+  for (int c : t.q[root_q].children)
+    if (c != root_v) free_subtree_v(h, t, c);
   VNodeH& old_root = t.v[t.root];
   if (old_root.slot >= 0) { h->free_slots.push_back(old_root.slot); old_root.slot = -1; }
-  old_root.children.clear();
-  t.q[root_q].children.clear();
-  t.root = root_v;
-  t.dead = false;
+  // Rebuild the node arrays from the kept subtree: a long-running planner
+  // re-roots once per belief message, and dropped nodes must not accumulate.
+  Tree fresh;
+  fresh.rng = t.rng;
+  fresh.expansions = t.expansions;
+  if (root_v >= 0) {
+    std::vector<int> vmap(t.v.size(), -1), qmap(t.q.size(), -1);
+    struct Item { int idx; bool is_q; };
+    std::vector<Item> stack{{root_v, false}};
+    while (!stack.empty()) {                       // number the kept nodes
+      const Item it = stack.back();
+      stack.pop_back();
+      if (it.is_q) {
+        qmap[it.idx] = (int)fresh.q.size();
+        fresh.q.push_back(t.q[it.idx]);
+        for (int c : t.q[it.idx].children) stack.push_back({c, false});
+      } else {
+        vmap[it.idx] = (int)fresh.v.size();
+        fresh.v.push_back(t.v[it.idx]);
+        for (int c : t.v[it.idx].children) stack.push_back({c, true});
+      }
+    }
+    auto mv = [&](int v) { return v >= 0 ? vmap[v] : -1; };
+    for (VNodeH& v : fresh.v) {
+      v.parent = v.parent >= 0 ? qmap[v.parent] : -1;
+      v.to_expand = mv(v.to_expand);
+      for (int& c : v.children) c = qmap[c];
+    }
+    for (QNodeH& q : fresh.q) {
+      q.parent = vmap[q.parent];
+      q.to_expand = mv(q.to_expand);
+      for (int& c : q.children) c = vmap[c];
+    }
+    fresh.root = vmap[root_v];
+    fresh.v[fresh.root].parent = -1;
+  } else {
+    fresh.v.emplace_back();
+    fresh.root = 0;
+    init_vnode(fresh.v[0], new_slot, 0, 0.0f, -1, ev, 0);
+    h->n_vnodes++;
+  }
+  t = std::move(fresh);
   return PP2D_OK;
 }
 

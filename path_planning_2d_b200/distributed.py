@@ -44,6 +44,24 @@ def partition_rows(height, world_size):
     return bounds
 
 
+def grid_checksum(cost, action, row_begin=0):
+    """Partition-invariant checksum of (rows of) a solution: CRC-32 of every
+    row of J (float bits) and of the action grid, each weighted by its global
+    row number, summed modulo 2^64.  The sum over the shards of a row-sharded
+    solve equals the checksum of the unsharded grids exactly when every row is
+    bit-identical (up to CRC collisions), so bench.py can print ONE number per
+    GPU count for the 16384^2 grid instead of shipping 1.25 GiB around."""
+    import zlib
+    cost = np.ascontiguousarray(cost, dtype=np.float32)
+    action = np.ascontiguousarray(action, dtype=np.uint8)
+    total = 0
+    for r in range(cost.shape[0]):
+        g = row_begin + r
+        total += zlib.crc32(cost[r].tobytes()) * (2 * g + 1)
+        total += zlib.crc32(action[r].tobytes()) * (2 * g + 2) * 0x9E3779B1
+    return total & 0xFFFFFFFFFFFFFFFF
+
+
 class _DevMem:
     """Expose raw device memory to torch through __cuda_array_interface__."""
 
@@ -114,19 +132,58 @@ class ShardedValueIteration:
         self.rows = self.bounds[self.rank]
         self.shard = shard_factory(grid, goal, gamma, self.rows)
         self.n_sweeps = 0
-        # Peer-to-peer ghost rows: default on when the shard supports it.
-        if p2p is None:
-            p2p = (self.world > 1 and hasattr(self.shard, "p2p_descriptor")
-                   and os.environ.get("PP2D_P2P", "1") != "0")
-        self.p2p = bool(p2p) and self.world > 1
+        self.converged = False
+        # Peer-to-peer ghost rows: on when the shard supports it AND every pair
+        # of neighbouring ranks sits on one host with peer access between the
+        # two devices; otherwise (other host, no NVLink/PCIe peer path, IPC
+        # mapping refused) every rank uses the send/recv exchange.  The decision
+        # is collective: a rank never waits for a flag its neighbour will not set.
+        want = p2p
+        if want is None:
+            want = (hasattr(self.shard, "p2p_descriptor")
+                    and os.environ.get("PP2D_P2P", "1") != "0")
+        self.p2p = False
         self._fused_pending = False     # fused P2P launches since the last barrier
-        if self.p2p:
-            descs = [None] * self.world
-            dist.all_gather_object(descs, self.shard.p2p_descriptor(), group=self.group)
-            up = descs[self.rank - 1] if self.rank > 0 else None
-            down = descs[self.rank + 1] if self.rank + 1 < self.world else None
-            self.shard.p2p_connect(up, down)
-            self._token = torch.zeros(1, device="cuda")
+        if want and self.world > 1:
+            import socket
+            info = [None] * self.world
+            mine = (socket.gethostname(), torch.cuda.current_device(),
+                    self.shard.p2p_descriptor())
+            dist.all_gather_object(info, mine, group=self.group)
+            ok = True
+            for nb in (self.rank - 1, self.rank + 1):
+                if 0 <= nb < self.world:
+                    same_host = info[nb][0] == mine[0]
+                    ok = ok and same_host and (
+                        info[nb][1] == mine[1] or
+                        torch.cuda.can_device_access_peer(mine[1], info[nb][1]))
+            up = info[self.rank - 1][2] if self.rank > 0 else None
+            down = info[self.rank + 1][2] if self.rank + 1 < self.world else None
+            if self._all_agree(ok):
+                try:
+                    self.shard.p2p_connect(up, down)
+                    connected = True
+                except Exception:
+                    connected = False
+                if not self._all_agree(connected):
+                    if connected:
+                        raise RuntimeError(
+                            "peer-to-peer ghost rows: a neighbour could not map this "
+                            "shard; rebuild the solver with p2p=False")
+                    if p2p:
+                        raise
+                else:
+                    self.p2p = True
+                    self._token = torch.zeros(1, device="cuda")
+            elif p2p:
+                raise RuntimeError("peer-to-peer ghost rows requested but the ranks are not "
+                                   "peer-capable neighbours on one host")
+
+    def _all_agree(self, flag):
+        """Logical AND of a per-rank flag (object all-gather: works on any backend)."""
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(flag), group=self.group)
+        return all(flags)
 
     def reset(self, grid=None, goal=None):
         """Re-solve from J = 0 with a new map (same shape) and/or goal."""
@@ -187,21 +244,31 @@ class ShardedValueIteration:
         self.n_sweeps += n
 
     def residual(self):
+        """max |J - J at the previous call| over all shards.  A shard whose
+        peer-to-peer hand-shake timed out reports +inf (mdp_residual_kernel):
+        every rank sees it after the MAX all-reduce and raises."""
         t = self.shard.residual_tensor()
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        return float(t.item())
+        r = float(t.item())
+        if self.p2p and r == float("inf"):
+            raise RuntimeError("peer-to-peer ghost-row exchange timed out on some rank; "
+                               "J is invalid (reset() clears the condition)")
+        return r
 
-    def value_iteration(self, max_batches=64):
-        """The reference's loop (path_planning_2d.cu:219-263) on the shards."""
+    def value_iteration(self, max_batches=None):
+        """The reference's loop (path_planning_2d.cu:219-263) on the shards:
+        batches of 100 sweeps until the inf-norm of a batch is <=
+        5/(1-gamma)*1e-3.  max_batches bounds the loop (tests); `converged`
+        tells whether the stopping rule was met."""
         max_optimal_cost = 5.0 / (1.0 - float(self.gamma))
         residuals = []
-        while True:
+        self.converged = False
+        while max_batches is None or len(residuals) < max_batches:
             self.sweeps(100)
             residuals.append(self.residual())
             if not (residuals[-1] > max_optimal_cost * 1e-3):
-                break
-            if len(residuals) >= max_batches:
+                self.converged = True
                 break
         return self.n_sweeps, residuals
 
@@ -217,13 +284,35 @@ class ShardedValueIteration:
         cost, action = self.download()
         if self.world == 1:
             return cost, action
-        parts = [None] * self.world if self.rank == 0 else None
-        dist.gather_object((cost, action), parts, dst=self._global(0),
-                           group=self.group)
+        # Tensor point-to-point transfers, shard by shard (no pickling of
+        # gigabyte arrays): device staging for NCCL, host tensors for gloo.
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
         if self.rank != 0:
+            for a in (cost, action):
+                dist.send(torch.from_numpy(np.ascontiguousarray(a)).to(dev),
+                          self._global(0), group=self.group)
             return None, None
-        return (np.concatenate([p[0] for p in parts]),
-                np.concatenate([p[1] for p in parts]))
+        costs, actions = [cost], [action]
+        for r in range(1, self.world):
+            rows = self.bounds[r][1] - self.bounds[r][0]
+            c = torch.empty((rows, self.width), dtype=torch.float32, device=dev)
+            a = torch.empty((rows, self.width), dtype=torch.uint8, device=dev)
+            dist.recv(c, self._global(r), group=self.group)
+            dist.recv(a, self._global(r), group=self.group)
+            costs.append(c.cpu().numpy())
+            actions.append(a.cpu().numpy())
+        return np.concatenate(costs), np.concatenate(actions)
+
+    def checksum(self):
+        """grid_checksum of the whole solution, identical on every rank and for
+        every number of shards."""
+        cost, action = self.download()
+        c = grid_checksum(cost, action, self.rows[0])
+        if self.world > 1:
+            parts = [None] * self.world
+            dist.all_gather_object(parts, c, group=self.group)
+            c = sum(parts) & 0xFFFFFFFFFFFFFFFF
+        return c
 
     def close(self):
         self.shard.close()

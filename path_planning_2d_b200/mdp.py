@@ -119,8 +119,8 @@ class MdpPathPlanning2d:
         res = np.zeros(cap, dtype=np.float64)
         chg = np.zeros(cap, dtype=np.uint32)
         _lib.check(self._lib.pp2d_mdp_policy_iteration(
-            self._h, ctypes.byref(n), res.ctypes.data, chg.ctypes.data, max_rounds))
-        rounds = n.value // 50
+            self._h, ctypes.byref(n), res.ctypes.data, chg.ctypes.data, cap, max_rounds))
+        rounds = min(n.value // 50, cap)
         return n.value, res[:rounds].copy(), chg[:rounds].copy()
 
     def download(self, cost=True, action=True):

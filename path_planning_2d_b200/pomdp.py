@@ -128,6 +128,21 @@ class PomdpPathPlanning2d:
                                                      mp.ctypes.data, sr.ctypes.data))
         return tp.reshape(n, 9, 9), mp.reshape(n, 16), sr.reshape(n, 9)
 
+    def set_model_tables(self, trans_prob=None, meas_prob=None, stage_reward=None):
+        """Upload half of loadModelDataFromFile (model_generation_cuda.cu:150-156)."""
+        n = self.map_height * self.map_width
+        arrs = []
+        for a, k in ((trans_prob, 81), (meas_prob, 16), (stage_reward, 9)):
+            if a is None:
+                arrs.append(None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+            if a.size != n * k:
+                raise ValueError(f"table must have {n}*{k} entries")
+            arrs.append(a)
+        _lib.check(self._lib.pp2d_pomdp_set_model_tables(
+            self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
+
     def sampling_uniforms(self):
         out = np.empty(100, np.float32)
         _lib.check(self._lib.pp2d_pomdp_sampling_uniforms(self._h, out.ctypes.data))

@@ -49,9 +49,23 @@ int main(int argc, char** argv) {
              {"discount_factor", argv[5]}, {"map_resolution", "0.2"},
              {"read_data_from_file", "true"}, {"data_dir", argv[6]},
              {"belief_set_size", argv[8]}, {"max_search_tree_depth", "50"},
-             {"max_online_iteration", argv[9]}};
+             {"max_online_iteration", argv[9]},
+             {"data_format", argc >= 11 ? argv[10] : "text"}};
     PomdpPathPlanning2d planner(p);
     if (!planner.initialize()) { std::printf("INIT_FAILED\n"); return 0; }
+    {
+      // what the planner now plans with: tables as uploaded, alphas as loaded
+      const size_t n = (size_t)planner.height() * planner.width();
+      std::vector<float> tp(n * 81), mp(n * 16), sr(n * 9);
+      PP2D_CHECK(pp2d_pomdp_model_tables(planner.handle(), tp.data(), mp.data(), sr.data()));
+      std::printf("TABLES tp=%016" PRIx64 " mp=%016" PRIx64 " sr=%016" PRIx64 " fib=%016" PRIx64
+                  " pbvi=%016" PRIx64 " acts=%016" PRIx64 "\n",
+                  fnv(tp.data(), tp.size() * 4), fnv(mp.data(), mp.size() * 4),
+                  fnv(sr.data(), sr.size() * 4),
+                  fnv(planner.fibAlphas().data(), planner.fibAlphas().size() * 4),
+                  fnv(planner.pbviAlphas().data(), planner.pbviAlphas().size() * 4),
+                  fnv(planner.pbviActions().data(), planner.pbviActions().size()));
+    }
     Belief b;
     std::vector<uint8_t> raw;
     if (!pp2d::read_file(argv[7], raw)) return 1;
@@ -74,7 +88,8 @@ int main(int argc, char** argv) {
     Params p{{"map_path", argv[2]}, {"goal_x", argv[3]}, {"goal_y", argv[4]},
              {"discount_factor", argv[5]}, {"map_resolution", "0.2"},
              {"read_data_from_file", "false"}, {"belief_set_size", argv[6]},
-             {"max_search_tree_depth", "50"}, {"max_online_iteration", argv[7]}};
+             {"max_search_tree_depth", "50"}, {"max_online_iteration", argv[7]},
+             {"data_format", argc >= 10 ? argv[9] : "text"}};
     PomdpPathPlanning2d planner(p);
     if (!planner.initialize()) { std::printf("INIT_FAILED\n"); return 0; }
     if (!planner.saveDataCallback(argv[8])) { std::printf("SAVE_FAILED\n"); return 0; }

@@ -234,6 +234,13 @@ if __name__ == "__main__":
         make_tree(sys.argv[2] if len(sys.argv) > 2 else
                   os.path.join(ROOT, "gpurun_out", "golden_ref"),
                   sys.argv[3] if len(sys.argv) > 3 else None)
+    elif len(sys.argv) >= 2 and sys.argv[1] == "tree_files":
+        # tree_files <outdir> <case>: the scenario on the reference started
+        # from its own text checkpoint written into <outdir>/data
+        import tree_scenario as ts
+        os.makedirs(os.path.join(sys.argv[2], "data"), exist_ok=True)
+        out = ts.run_reference_case(sys.argv[3], os.path.join(sys.argv[2], "data"))
+        np.savez_compressed(os.path.join(sys.argv[2], f"tree_files_{sys.argv[3]}.npz"), **out)
     elif len(sys.argv) >= 2 and sys.argv[1] == "maps":
         make_maps()
     elif len(sys.argv) >= 2 and sys.argv[1] == "pomdp":

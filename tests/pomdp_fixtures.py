@@ -77,3 +77,32 @@ def bundled_alphas(n_pbvi=500, seed=0):
     acts = np.concatenate([np.arange(9), w.argmax(1)]).astype(np.uint8)[:n_pbvi]
     return (np.ascontiguousarray(fib), np.ascontiguousarray(pbvi),
             np.arange(9, dtype=np.uint8), acts)
+
+
+def write_text_rows(path, arr):
+    """One row per line, "%15.8f" per value: the format of the reference's
+    save*DataToFile (model_generation_cuda.cu:74-107, fast_informed_bound_cuda.cu:
+    343-352, point_based_value_iteration_cuda.cu:747-756)."""
+    arr = np.asarray(arr, np.float32)
+    arr = arr.reshape(arr.shape[0], -1)
+    with open(path, "w") as f:
+        for row in arr:
+            f.write("".join(["%15.8f" % v for v in row.tolist()]) + "\n")
+
+
+def text_round(arr):
+    """What fscanf("%f") reads back from "%15.8f" text: the decimal string
+    converted to float32 by libc's strtof (one rounding, not via double)."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    libc.strtof.restype = ctypes.c_float
+    libc.strtof.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    a = np.asarray(arr, np.float32)
+    flat = a.reshape(-1).tolist()
+    out = np.array([libc.strtof(("%15.8f" % v).encode(), None) for v in flat], np.float32)
+    return out.reshape(a.shape)
+
+
+def write_actions(path, acts):
+    with open(path, "w") as f:
+        f.write("".join("%10u\n" % int(a) for a in acts))

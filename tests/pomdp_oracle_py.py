@@ -212,6 +212,9 @@ class RefFull:
         R.ref_full_tree_dump.restype = ctypes.c_int64
         R.ref_full_tree_dump.argtypes = [_vp, ctypes.c_uint64]
         R.ref_full_tree_root_belief.argtypes = [_vp]
+        R.ref_full_save_data.argtypes = [ctypes.c_char_p]
+        R.ref_full_load_data.argtypes = [ctypes.c_char_p]
+        R.ref_full_get_alphas.argtypes = [_vp, _vp, _vp, _vp]
         self.R = R
         self.grid = np.ascontiguousarray(grid, np.uint8)
         self.h, self.w = self.grid.shape
@@ -239,6 +242,22 @@ class RefFull:
         pa = None if pa is None else np.ascontiguousarray(pa, np.uint8)
         self.R.ref_full_set_alphas(fib.ctypes.data, fa.ctypes.data if fa is not None else None,
                                    pbvi.ctypes.data, pa.ctypes.data if pa is not None else None)
+
+    def save_data(self, directory):
+        """saveDataCallback: the reference's seven text files into `directory`."""
+        assert self.R.ref_full_save_data(str(directory).encode()) == 0
+
+    def load_data(self, directory):
+        """read_data_from_file=true: the reference's own loaders."""
+        assert self.R.ref_full_load_data(str(directory).encode()) == 0
+
+    def get_alphas(self):
+        fib = np.zeros((self.hw, 9), np.float32)
+        pbvi = np.zeros((self.n_pbvi, self.hw), np.float32)
+        fa, pa = np.zeros(9, np.uint8), np.zeros(self.n_pbvi, np.uint8)
+        self.R.ref_full_get_alphas(fib.ctypes.data, fa.ctypes.data, pbvi.ctypes.data,
+                                   pa.ctypes.data)
+        return fib, pbvi, fa, pa
 
     def solve_fib(self):
         al = np.zeros((self.hw, 9), np.float32)

@@ -33,7 +33,7 @@ def test_binding_table_covers_the_header():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.pp2d_abi_version() == 1
+    assert lib.pp2d_abi_version() == 2
     assert isinstance(lib.pp2d_last_error(), bytes)
 
 

@@ -15,7 +15,26 @@ import torch.multiprocessing as mp
 import cases
 import oracle_py
 from path_planning_2d_b200.distributed import (ShardedValueIteration,
-                                               partition_rows)
+                                               grid_checksum, partition_rows)
+
+
+def test_grid_checksum_is_partition_invariant_and_bit_sensitive():
+    rng = np.random.default_rng(0)
+    cost = rng.random((37, 53), dtype=np.float32)
+    act = rng.integers(9, size=(37, 53)).astype(np.uint8)
+    whole = grid_checksum(cost, act)
+    for cuts in ([0, 37], [0, 5, 37], [0, 2, 4, 30, 37]):
+        parts = sum(grid_checksum(cost[a:b], act[a:b], a) for a, b in zip(cuts[:-1], cuts[1:]))
+        assert parts & 0xFFFFFFFFFFFFFFFF == whole
+    c2 = cost.copy()
+    c2.view(np.uint32)[20, 7] ^= 1                  # one mantissa bit
+    assert grid_checksum(c2, act) != whole
+    a2 = act.copy()
+    a2[3, 3] = (a2[3, 3] + 1) % 9
+    assert grid_checksum(cost, a2) != whole
+    swapped = cost.copy()
+    swapped[[4, 5]] = swapped[[5, 4]]               # rows exchanged
+    assert grid_checksum(swapped, act) != whole
 
 
 def test_partition_rows():
@@ -50,10 +69,13 @@ def _worker(rank, world, port, name, out_dir):
         vi.sweeps(7, want_action=False)      # odd count: 2+2+2+1
         vi.sweeps(1)
         sweeps, residuals = vi.value_iteration()
+        assert vi.converged
+        checksum = vi.checksum()
         cost, action = vi.gather()
         if rank == 0:
             np.savez(os.path.join(out_dir, "out.npz"), cost=cost, action=action,
-                     sweeps=sweeps, residuals=np.array(residuals))
+                     sweeps=sweeps, residuals=np.array(residuals),
+                     checksum=np.uint64(checksum))
     finally:
         dist.destroy_process_group()
 
@@ -83,3 +105,4 @@ def test_sharded_value_iteration_gloo(tmp_path, world):
     assert np.array_equal(got["cost"].view(np.uint32), ora.cost.view(np.uint32))
     assert np.array_equal(got["action"], ora.act)
     assert not np.isnan(got["cost"]).any()
+    assert int(got["checksum"]) == grid_checksum(ora.cost, ora.act)

@@ -100,17 +100,21 @@ def test_cpp_pomdp_planner_matches_oracle(exe, tmp_path):
         pytest.skip("noise fixture blocked the goal")
     m, fib, pbvi, fa, pa = pf.alphas(grid, goal, n_pbvi=12)
     # the text round trip is lossy by format: the oracle gets the SAME rounded
-    # numbers the C++ planner reads back
-    def dump(path, arr):
-        with open(path, "w") as f:
-            for row in arr:
-                f.write("".join("%15.8f" % v for v in row) + "\n")
-        return np.array([[np.float32(float("%15.8f" % v)) for v in row] for row in arr],
-                        np.float32)
-    fib_r = dump(tmp_path / "fib_alphas", fib)
-    pbvi_r = dump(tmp_path / "pbvi_alphas", pbvi)
-    (tmp_path / "fib_actions").write_text("".join("%10u\n" % a for a in fa))
-    (tmp_path / "pbvi_actions").write_text("".join("%10u\n" % a for a in pa))
+    # numbers the C++ planner reads back -- alpha vectors AND model tables
+    # (read_data_from_file=true loads the model too, path_planning_2d.cu:127-143)
+    hw = grid.size
+    for fname, arr in (("fib_alphas", fib), ("pbvi_alphas", pbvi),
+                       ("model_data_trans_prob", m.tp.reshape(hw * 9, 9)),
+                       ("model_data_meas_prob", m.mp.reshape(hw, 16)),
+                       ("model_data_stage_reward", m.sr.reshape(hw, 9))):
+        pf.write_text_rows(tmp_path / fname, arr)
+    fib_r, pbvi_r = pf.text_round(fib), pf.text_round(pbvi)
+    m = po.Model(grid, goal)               # private copy with the rounded tables
+    m.tp[:] = pf.text_round(m.tp)
+    m.mp[:] = pf.text_round(m.mp)
+    m.sr[:] = pf.text_round(m.sr)
+    pf.write_actions(tmp_path / "fib_actions", fa)
+    pf.write_actions(tmp_path / "pbvi_actions", pa)
     b = pf.gaussian_beliefs(grid, 1, seed=5)[0]
     (tmp_path / "belief.bin").write_bytes(b.tobytes())
     out = subprocess.run([exe, "pomdp", png, str(goal[0]), str(goal[1]), "0.95",
@@ -118,6 +122,11 @@ def test_cpp_pomdp_planner_matches_oracle(exe, tmp_path):
                          capture_output=True, text=True)
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0]
     kv = dict(t.split("=") for t in line.split()[1:])
+    tab = dict(t.split("=") for t in
+               [l for l in out.stdout.splitlines() if l.startswith("TABLES")][0].split()[1:])
+    assert tab["tp"] == fnv(m.tp.tobytes()) and tab["mp"] == fnv(m.mp.tobytes())
+    assert tab["sr"] == fnv(m.sr.tobytes())
+    assert tab["fib"] == fnv(fib_r.tobytes()) and tab["pbvi"] == fnv(pbvi_r.tobytes())
     t = po.Tree(m, cases.GAMMA, fib_r, pbvi_r, pf.uniforms(), b, fa, pa)
     a0, r0, _, _ = t.plan(50, 6)
     assert t.update(a0, 0) == 0

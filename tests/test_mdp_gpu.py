@@ -242,6 +242,33 @@ def test_full_size_properties_4096():
     assert np.array_equal(ac[:256, :256][sel], ora.act[sel])
 
 
+@pytest.mark.parametrize("shape,goal", [((4096, 4096), (2048, 2048)),
+                                        ((2048, 16384), (8192, 1024))])
+def test_benchmarked_sizes_to_convergence_vs_the_reference_kernels(shape, goal):
+    """BASELINE.json configs[2] (the bench grid: 4096 x 4096, seed 12345, goal
+    at the centre) and one 2048 x 16384 shard-sized grid of configs[3], solved
+    to the reference's stopping rule by pp2d_mdp_solve and by the UNMODIFIED
+    reference kernels in the reference's own loop (oracle/_ref,
+    src/mdp/path_planning_2d.cu:223-263): same number of sweeps, same
+    residuals, J bit for bit, action byte for byte."""
+    import sys
+    so = os.path.join(cases.ROOT, "oracle", "_ref", "libpp2d_ref_mdp.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built")
+    sys.path.insert(0, os.path.join(cases.ROOT, "tests", "golden"))
+    import make_golden
+    h, w = shape
+    grid, goal = cases.synthetic_map(h, w, 0.20, seed=12345, goal=goal)
+    J, A, n, res = make_golden.ref_solve(make_golden.ref_lib(), grid, goal, cases.GAMMA)
+    with MdpPathPlanning2d(grid, goal, cases.GAMMA) as mdp:
+        sweeps, residuals = mdp.initialize()
+        assert sweeps == n
+        assert np.array_equal(residuals, res)
+        assert np.array_equal(_bits(mdp.optimal_cost), _bits(J))
+        assert np.array_equal(mdp.optimal_action, A)
+    assert n >= 300 and res[-1] <= 5.0 / (1.0 - np.float32(cases.GAMMA)) * 1e-3 < res[-2]
+
+
 def test_full_size_16384_row_shards_equal_the_unsharded_grid():
     """BASELINE.json configs[3] size (16384 x 16384, 2.7e8 cells) on one GPU:
     8 row shards of 2048 rows with ghost-row exchange after every launch must

@@ -171,6 +171,79 @@ def test_plan_batch_equals_independent_oracle_plans():
         assert stats[i, 2] == ostats[4], i
 
 
+def test_plan_batch_at_bench_scale_equals_single_query_trees(monkeypatch):
+    """BASELINE.json configs[4] as the bench runs it: 640 Gaussian start
+    beliefs on sparse_map_100x40, the REAL 9 FIB + 500 PBVI alpha vectors of
+    the GPU offline solvers, depth cap 50, 15 expansions.  Large enough for
+    the two staggered halves (>= 256 queries) and the OpenMP host loops (>= 64),
+    and the pool starts so small (64 slots per query for trees of ~470 V nodes)
+    that it grows in place several times mid-batch.  Every query must give the
+    action, value and depth of its own pp2d_tree_plan on a fresh SearchTree,
+    and -- for the first 32 -- of the CPU oracle, tree sizes included."""
+    monkeypatch.setenv("PP2D_POMDP_SLOTS_PER_QUERY", "64")
+    name, goal = "sparse_map_100x40", (95, 34)
+    grid = cases.load_bundled(name)
+    n = 640
+    beliefs = pf.gaussian_beliefs(grid, n, sigma=2.0, seed=0)
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        fib, fa, _ = p.fastInformedBound()
+        _, pbvi, pa = p.pointBasedValueIteration(p.initial_belief, 500, rand_seed=1)
+        p.set_alphas(fib, pbvi, fa, pa)
+        acts, vals, stats = p.plan_batch(beliefs, max_depth=50, max_iter=15, with_stats=True)
+        # a second batch on the grown pool (slots recycled) gives the same
+        acts2, vals2, stats2 = p.plan_batch(beliefs[::-1], max_depth=50, max_iter=15,
+                                            with_stats=True)
+        assert np.array_equal(acts2[::-1], acts) and np.array_equal(bits(vals2[::-1]), bits(vals))
+        assert np.array_equal(stats2[::-1], stats)
+        assert stats[:, 0].mean() > 200 and np.all(stats[:, 3] <= 15)
+        for i in range(n):
+            st = SearchTree(p, beliefs[i])
+            a, r = st.plan(50, 15)
+            d = st.getDepth()
+            st.close()
+            assert (a, bits(np.float32(r)), d) == (acts[i], bits(vals[i]), stats[i, 2]), i
+    m = po.Model(grid, goal)
+    for i in range(32):
+        ot = po.Tree(m, cases.GAMMA, fib, pbvi, pf.uniforms(), beliefs[i], fa, pa)
+        oa, orr, ostats, rc = ot.plan(50, 15)
+        ot.close()
+        assert rc == 0 and acts[i] == oa, i
+        assert bits(np.float32(vals[i])) == bits(np.float32(orr)), i
+        assert stats[i, 0] == ostats[0] and stats[i, 1] == ostats[1], i
+        assert stats[i, 2] == ostats[4], i
+
+
+def test_c_abi_rejects_out_of_range_actions_and_observations():
+    """pp2d_pomdp_bayes_update / pp2d_tree_update index the tables with the
+    action and observation: out-of-range values are refused before anything
+    is touched (the reference has no such check; it would read out of bounds)."""
+    name, goal = "map_10x10", (8, 7)
+    grid = cases.load_bundled(name)
+    m, fib, pbvi, fa, pa = pf.alphas(name, goal, n_pbvi=20)
+    b = pf.gaussian_beliefs(grid, 1, seed=0)[0]
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        p.set_alphas(fib, pbvi, fa, pa)
+        for a, z in ((9, 0), (0, 16), (255, 255)):
+            with pytest.raises(_lib.Pp2dError) as e:
+                p.bayes_update(b[None], a, z)
+            assert e.value.code == _lib.PP2D_ERR_INVALID
+        st = SearchTree(p, b)
+        st.expand()
+        before = st.dump()
+        for a, z in ((9, 0), (0, 16)):
+            with pytest.raises(_lib.Pp2dError):
+                st.update(a, z)
+        assert np.array_equal(bits(st.dump()), bits(before))     # tree untouched
+        st.expand()
+        # many re-roots: the node arrays are rebuilt, not grown without bound
+        for _ in range(12):
+            a, _r = st.getOptimalAction()
+            st.update(a, 3)
+            st.plan(50, 2)
+        assert st.dump().shape[0] < 2000
+        st.close()
+
+
 def test_reference_pomdp_kernels_vs_restatement():
     """Live pin of oracle/pomdp_oracle.c against the reference kernels."""
     so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),

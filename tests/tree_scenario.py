@@ -192,13 +192,32 @@ def same_record(got, want):
     return None
 
 
-def run_reference_case(case):
-    """GPU box: the whole case on the reference stack (one process per case)."""
+def run_reference_case(case, data_dir=None):
+    """GPU box: the whole case on the reference stack (one process per case).
+    data_dir: the reference first writes its seven text files there with its
+    own save*DataToFile and reads them back with its own load*DataFromFile
+    (the read_data_from_file=true start-up, src/pomdp/path_planning_2d.cu:
+    127-143), so that the scenario runs on the "%15.8f"-rounded tables and
+    alpha vectors; they are returned with the records."""
     import pomdp_oracle_py as po
     grid, goal, m, fib, pbvi, fa, pa, beliefs, n_expand = inputs(case)
     ref = po.RefFull(grid, goal, cases.GAMMA, pbvi.shape[0])
     ref.set_alphas(fib, pbvi, fa, pa)
     out = {"inputs_crc": checksum(grid, fib, pbvi, fa, pa, *beliefs)}
+    if data_dir is not None:
+        ref.save_data(data_dir)
+        ref.load_data(data_dir)
+        out["trans_prob"], out["meas_prob"], out["stage_reward"] = ref.model()
+        out["fib"], out["pbvi"], out["fib_actions"], out["pbvi_actions"] = ref.get_alphas()
+        # two belief callbacks as PomdpPathPlanning2d makes them
+        # (path_planning_2d.cu:199-241): fresh tree, then update(a0, z = 0)
+        be = RefBackend(ref)
+        be.create(beliefs[0])
+        a0, r0 = be.plan(50, n_expand)
+        assert be.update(int(a0), 0) == 0
+        a1, r1 = be.plan(50, n_expand)
+        out["callbacks"] = np.array([a0, np.float32(r0).view(np.uint32), a1,
+                                     np.float32(r1).view(np.uint32)], np.uint32)
     tp, mp, sr = ref.model()
     out["model_crc"] = checksum(tp, mp, sr)
     ev = [ref.evaluate(b) for b in beliefs]
