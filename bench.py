@@ -115,14 +115,21 @@ def make_grid(n_tiles):
 
 
 # --------------------------------------------------------------------------
+def host_cores():
+    return len(os.sched_getaffinity(0))
+
+
 def cpu_port_throughput(grid, goal, gamma, budget_s=12.0, sample=2048):
-    """Oracle port (OpenMP, all cores) on the top-left sample x sample crop."""
+    """Oracle port on the top-left sample x sample crop: OpenMP on all host
+    cores (thread count set explicitly and read back), plus the 1-thread
+    figure on a smaller sample."""
     import oracle_py
     crop = np.ascontiguousarray(grid[:sample, :sample])
     g = goal if (goal[0] < sample and goal[1] < sample) else None
     if g is None or crop[g[1], g[0]]:
         free = np.argwhere(crop == 0)[0]
         g = (int(free[1]), int(free[0]))
+    threads = oracle_py.set_threads(host_cores())
     ora = oracle_py.OracleMdp(crop, g, gamma)
     ora.sweeps(2)                                   # warm-up + calibration
     t0 = time.perf_counter()
@@ -132,30 +139,37 @@ def cpu_port_throughput(grid, goal, gamma, budget_s=12.0, sample=2048):
     t0 = time.perf_counter()
     ora.sweeps(n)
     dt = time.perf_counter() - t0
-    cores = len(os.sched_getaffinity(0))
-    return {"value": crop.size * n / dt, "unit": UNIT, "cores": cores,
-            "kind": "port",
+    oracle_py.set_threads(1)
+    t0 = time.perf_counter()
+    ora.sweeps(2)
+    one = crop.size * 2 / (time.perf_counter() - t0)
+    oracle_py.set_threads(threads)
+    return {"value": crop.size * n / dt, "unit": UNIT, "cores": threads,
+            "kind": "port", "value_1_thread": one,
             "sample": f"{n} sweeps of the {sample}x{sample} top-left crop of the "
-                      f"workload grid, oracle/mdp_oracle.c with OpenMP on {cores} threads"}
+                      f"workload grid, oracle/mdp_oracle.c with OpenMP on {threads} threads "
+                      f"(1-thread figure: 2 sweeps of the same crop)"}
 
 
 def run_reference_arm(args):
+    """The reference's CPU side of the path: it has no CPU solver (SURVEY.md
+    section 0), so this is the oracle port of its kernel arithmetic, OpenMP
+    over ALL host cores of the box (set explicitly: torchrun exports
+    OMP_NUM_THREADS=1), on the SAME grid and goal as the main arm's per-GPU
+    tile.  A step is a bounded sample of the main arm's step: S <= 100 sweeps
+    of the whole 4096 x 4096 grid, S sized so that the run ends in ~2 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import cases
-    grid, goal = make_grid(1)
     import oracle_py
-    sample = 2048
-    crop = np.ascontiguousarray(grid[:sample, :sample])
-    free = np.argwhere(crop == 0)[0]
-    g = (int(free[1]), int(free[0]))
-    ora = oracle_py.OracleMdp(crop, g, cases.GAMMA)
+    grid, goal = make_grid(1)
+    threads = oracle_py.set_threads(host_cores())
+    ora = oracle_py.OracleMdp(grid, goal, cases.GAMMA)
     ora.sweeps(1)
     t0 = time.perf_counter()
     ora.sweeps(1)
     per = time.perf_counter() - t0
-    # bounded: the whole run (warm-up + steps) stays within ~2 minutes
     total_steps = max(1, args.steps + args.warmup)
     sweeps_per_step = max(1, min(SWEEPS_PER_STEP, int(100.0 / total_steps / max(per, 1e-6))))
     for _ in range(args.warmup):
@@ -164,21 +178,23 @@ def run_reference_arm(args):
     for _ in range(args.steps):
         ora.sweeps(sweeps_per_step)
     dt = time.perf_counter() - t0
-    cores = len(os.sched_getaffinity(0))
-    value = crop.size * sweeps_per_step * args.steps / dt
-    sample_txt = (f"each step = {sweeps_per_step} sweeps of the {sample}x{sample} "
-                  f"top-left crop of the 4096x4096 workload grid")
+    value = grid.size * sweeps_per_step * args.steps / dt
+    sample_txt = (f"each step = {sweeps_per_step} of the 100 sweeps of a main-arm step, on the "
+                  f"whole {TILE}x{TILE} per-GPU grid with the main arm's goal {goal}; "
+                  f"OpenMP threads used: {threads} of {host_cores()} host cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "syn4k: 4096x4096 i.i.d. 20% occupied, seed 12345, "
-                               "9 actions, gamma 0.95f; " + sample_txt,
+        "config": {"workload": f"syn4k x{args.gpus}: {TILE}x{TILE} per GPU, i.i.d. 20% "
+                               f"occupied (PCG64 seed 12345), goal {goal}, 9 actions, "
+                               "gamma 0.95f, J0 = 0; " + sample_txt,
                    "note": "the reference has no CPU value-iteration path; this is "
-                           "the oracle port of its CUDA kernel arithmetic"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores,
+                           "the oracle port of its CUDA kernel arithmetic; the metric is "
+                           "per cell-update, so the per-GPU tile stands for the N-tile grid"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads,
                          "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -244,8 +260,23 @@ def syn16k_section(rank, world, barrier, steps=5):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     rows = vi.rows[1] - vi.rows[0]
+    # Evidence that the shards computed what one GPU computes (BASELINE.md
+    # config 4): a partition-invariant checksum of J and the action grid after
+    # the (3 + steps) x 100 sweeps every run of this section performs; it must
+    # print the same number for every N.  download() also fails the section if a
+    # peer-to-peer hand-shake timed out anywhere in the loop.
+    t0 = time.perf_counter()
+    checksum = vi.checksum()
+    checksum_s = time.perf_counter() - t0
+    sweeps_done = vi.n_sweeps
     vi.close()
     return {"cell_updates_per_sec": n * n * SWEEPS_PER_STEP * steps / (ms * 1e-3),
+            "solution_checksum": f"{checksum:016x}", "checksum_after_sweeps": sweeps_done,
+            "checksum_what": "sum over rows of crc32(J row) * (2r+1) + crc32(action row) * "
+                             "(2r+2) * 0x9E3779B1 mod 2^64 (distributed.grid_checksum); "
+                             "identical for every --gpus N iff the row shards are "
+                             "bit-identical to the single-GPU solve",
+            "checksum_seconds": checksum_s,
             "ms_per_step": ms / steps, "steps": steps, "scaling": "strong",
             "workload": f"syn16k: 16384x16384 grid, i.i.d. 20% occupied (PCG64 seed 12345), "
                         f"goal {goal}, row-sharded over {world} GPU(s), {rows} rows per GPU",
@@ -386,6 +417,9 @@ def run_main_arm(args):
     barrier()
     launches = lib.pp2d_kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if vi.p2p and vi.shard.p2p_timed_out():
+        raise SystemExit("peer-to-peer ghost-row hand-shake timed out inside the timed "
+                         "region: no valid number")
     ms = start.elapsed_time(end)
     fused_ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms, fused_ms], dtype=torch.float64, device="cuda")
@@ -415,6 +449,7 @@ def run_main_arm(args):
             pass
 
     # e2e: public API, host buffers, copies inside the timed region
+    p2p_used = vi.p2p
     vi.close()
     del vi
     from path_planning_2d_b200.distributed import partition_rows
@@ -479,6 +514,7 @@ def run_main_arm(args):
             "clocks": clocks,
             "residual_after_first_timed_step": residual_first,
             "residual_after_timed_steps": residual,
+            "p2p_ghost_rows": bool(p2p_used),
         }
         ref_cuda = reference_cuda_on_this_gpu(grid[:TILE], goal, gamma) \
             if world == 1 and not args.no_ref_cuda else None

@@ -26,7 +26,7 @@
  * This restatement is pinned against the UNMODIFIED reference kernels run on
  * a B200 (oracle/_ref, built by oracle/Makefile from the sources in
  * /root/reference); the outputs of that run are committed under
- * tests/golden/ and tests/test_oracle_golden.py checks this file against
+ * tests/golden/ and tests/test_oracle_cpu.py checks this file against
  * them bit for bit.
  */
 #include <float.h>
@@ -34,6 +34,28 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Thread count of the OpenMP loops below (bench.py: the reference arm sets it
+ * explicitly because torchrun exports OMP_NUM_THREADS=1).  n <= 0 leaves the
+ * setting alone.  Returns the number of threads a parallel region really gets. */
+int oracle_set_threads(int n) {
+  int got = 1;
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#pragma omp parallel
+  {
+#pragma omp single
+    got = omp_get_num_threads();
+  }
+#else
+  (void)n;
+#endif
+  return got;
+}
 
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(PP2D_ORACLE_NO_CLONES)
 #define ORACLE_CLONES __attribute__((target_clones("fma", "default")))

@@ -61,6 +61,8 @@ struct Tree {
   GlibcRand rng;
   uint32_t expansions = 0;
   bool dead = false;                  // reference would dereference nullptr
+  bool dense = false;                 // root belief not +0 on the dead cells: its
+                                      // descendants need the dense inner products
 };
 
 // search_tree_cuda.cu:251-286
@@ -237,9 +239,64 @@ int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows)
   return PP2D_OK;
 }
 
+// Live-cell list and compacted bound matrix (see pomdp_host.h).
+int refresh_live_cells(pp2d_pomdp* h) {
+  const int HW = h->HW;
+  uint8_t* d_dead = nullptr;
+  PP2D_CUDA(cudaMalloc(&d_dead, HW));
+  pomdp_dead_cells_kernel<<<(HW + 127) / 128, 128, 0, h->stream>>>(h->H, h->W, h->d_tp, d_dead);
+  count_launch();
+  h->dead.assign(HW, 0);
+  cudaError_t e = cudaMemcpyAsync(h->dead.data(), d_dead, HW, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_dead);
+  PP2D_CUDA(e);
+  std::vector<int> live, all(HW);
+  for (int s = 0; s < HW; ++s) {
+    all[s] = s;
+    if (!h->dead[s]) live.push_back(s);
+  }
+  if (live.empty()) live.push_back(0);           // degenerate map: keep the kernels in bounds
+  h->K = (int)live.size();
+  if (!h->d_kidx) PP2D_CUDA(cudaMalloc(&h->d_kidx, HW * sizeof(int)));
+  if (!h->d_kidx_all) PP2D_CUDA(cudaMalloc(&h->d_kidx_all, HW * sizeof(int)));
+  PP2D_CUDA(cudaMemcpy(h->d_kidx, live.data(), live.size() * sizeof(int), cudaMemcpyHostToDevice));
+  PP2D_CUDA(cudaMemcpy(h->d_kidx_all, all.data(), HW * sizeof(int), cudaMemcpyHostToDevice));
+  if (h->have_alphas) {
+    std::vector<float> rows((size_t)h->K * h->ld);
+    for (int k = 0; k < h->K; ++k)
+      memcpy(rows.data() + (size_t)k * h->ld, h->alpha_host.data() + (size_t)live[k] * h->ld,
+             (size_t)h->ld * sizeof(float));
+    if (h->d_alpha_live) cudaFree(h->d_alpha_live);
+    h->d_alpha_live = nullptr;
+    PP2D_CUDA(cudaMalloc(&h->d_alpha_live, rows.size() * sizeof(float)));
+    PP2D_CUDA(cudaMemcpy(h->d_alpha_live, rows.data(), rows.size() * sizeof(float),
+                         cudaMemcpyHostToDevice));
+  }
+  return PP2D_OK;
+}
+
+bool zero_on_dead_cells(const pp2d_pomdp* h, const float* belief) {
+  uint32_t any = 0;
+  for (int s = 0; s < h->HW; ++s) {
+    uint32_t bits;
+    memcpy(&bits, belief + s, sizeof(bits));
+    any |= h->dead[s] ? bits : 0u;               // -0 also forces the dense path
+  }
+  return any == 0;
+}
+
 }  // namespace pp2d
 
 namespace {
+
+// The inner dimension of the sequential products of one launch: the live
+// cells, or all cells when some belief involved may be non-zero elsewhere.
+struct InnerDim { const int* kidx; int K; const float* alpha; };
+InnerDim inner_dim(const pp2d_pomdp* h, bool dense) {
+  if (dense || !h->skip_dead) return {h->d_kidx_all, h->HW, h->d_alpha};
+  return {h->d_kidx, h->K, h->d_alpha_live};
+}
 
 // Host threads for the per-tree work of a batch: pp2d_set_host_threads, else
 // PP2D_HOST_THREADS, else the CPUs this process may run on divided by the
@@ -269,7 +326,7 @@ double now_s() {
 
 // Evaluate the beliefs in `slots`: per belief 4 floats {upper, lower, packed
 // indices, 0} into host `out` (B4, B5).
-int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
+int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out, bool dense) {
   const int n = (int)slots.size();
   if (n == 0) return PP2D_OK;
   PP2D_TRY(h->d_slots.ensure(n));
@@ -278,8 +335,9 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out) {
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((n + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
+  const InnerDim in = inner_dim(h, dense);
   pomdp_values_kernel<<<grid, 256, 0, h->stream>>>(
-      h->HW, h->cap, h->ld, h->ncol, h->d_slots.p, n, h->d_bel, h->d_alpha,
+      in.K, in.kidx, h->cap, h->ld, h->ncol, h->d_slots.p, n, h->d_bel, in.alpha,
       h->d_vals.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -323,6 +381,15 @@ int make_roots(pp2d_pomdp* h, std::vector<Tree*>& trees, const float* beliefs) {
   const int n = (int)trees.size();
   std::vector<int> slots(n);
   for (int i = 0; i < n; ++i) PP2D_TRY(alloc_slot(h, &slots[i]));
+  // Start beliefs that are not +0 on the dead cells (and everything grown from
+  // them) are evaluated with the dense inner products.
+  bool any_dense = false;
+#pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(|| : any_dense) \
+    if (n >= 64)
+  for (int i = 0; i < n; ++i) {
+    trees[i]->dense = !zero_on_dead_cells(h, beliefs + (size_t)i * h->HW);
+    any_dense = any_dense || trees[i]->dense;
+  }
   PP2D_TRY(h->d_slots.ensure(n));
   PP2D_TRY(h->d_rows.ensure((size_t)n * h->HW));
   PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, beliefs, (size_t)n * h->HW * sizeof(float),
@@ -335,7 +402,7 @@ int make_roots(pp2d_pomdp* h, std::vector<Tree*>& trees, const float* beliefs) {
   count_launch();
   PP2D_CUDA(cudaGetLastError());
   std::vector<float> ev((size_t)n * 4);
-  PP2D_TRY(evaluate_slots(h, slots, ev.data()));
+  PP2D_TRY(evaluate_slots(h, slots, ev.data(), any_dense));
   for (int i = 0; i < n; ++i) {
     Tree& t = *trees[i];
     t.v.emplace_back();
@@ -385,6 +452,7 @@ struct RoundCtx {
   struct Child { uint8_t a, z; float w; };
   std::vector<Job> jobs;
   int n = 0, nk = 0;
+  bool dense = false;                // some tree of this round needs the dense products
   PinnedBuf<int> slots, kslots, gfirst, kgroup;
   PinnedBuf<float> draws, rewards, ev;
   PinnedBuf<BayesItem> items;
@@ -437,8 +505,10 @@ RoundCtx* round_ctx(pp2d_pomdp* h, int which) {
 int round_stage1(pp2d_pomdp* h, RoundCtx& c, const std::vector<Tree*>& trees) {
   double t0 = now_s();
   c.jobs.clear();
+  c.dense = false;
   for (Tree* t : trees) {
     if (t->dead) continue;
+    c.dense = c.dense || t->dense;
     const int v = t->v[t->root].to_expand;
     if (v < 0) { t->dead = true; continue; }
     if (!t->v[v].children.empty()) {            // re-expansion (leak in the ref)
@@ -480,8 +550,9 @@ int round_stage1(pp2d_pomdp* h, RoundCtx& c, const std::vector<Tree*>& trees) {
       h->H, h->W, n, kSamples, h->d_tp, h->d_mp, c.d_prefix.p, c.d_draws.p,
       h->d_uniforms, c.d_obs.p);
   count_launch();
-  pomdp_rewards_kernel<<<(n * kActions + 3) / 4, 128, 0, c.stream_hi>>>(HW, h->cap, c.d_jobslots.p, n, h->d_bel,
-                                                     h->d_sr, c.d_rew.p);
+  const InnerDim in = inner_dim(h, c.dense);
+  pomdp_rewards_kernel<<<(n * kActions + 3) / 4, 128, 0, c.stream_hi>>>(
+      in.K, in.kidx, h->cap, c.d_jobslots.p, n, h->d_bel, h->d_sr, c.d_rew.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
   PP2D_CUDA(cudaMemcpyAsync(c.obs.p, c.d_obs.p, nd, cudaMemcpyDeviceToHost, c.stream_hi));
@@ -565,8 +636,9 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
                                                      c.d_pred.p);
   count_launch();
   h->n_bayes += nk;
+  const InnerDim in = inner_dim(h, c.dense);
   pomdp_child_sum_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(
-      HW, ngp, h->d_mp, c.d_items.p, c.d_kgroup.p, nk, c.d_pred.p, c.d_sums.p);
+      in.K, in.kidx, ngp, h->d_mp, c.d_items.p, c.d_kgroup.p, nk, c.d_pred.p, c.d_sums.p);
   count_launch();
   dim3 sgrid((nk + 31) / 32, (HW + 7) / 8);
   pomdp_child_write_kernel<<<sgrid, 256, 0, c.stream>>>(HW, h->cap, ngp, h->d_mp, c.d_items.p,
@@ -574,8 +646,9 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
                                                          c.d_sums.p, h->d_bel);
   count_launch();
   dim3 vgrid((nk + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
-  pomdp_values_kernel<<<vgrid, 256, 0, c.stream>>>(HW, h->cap, h->ld, h->ncol, c.d_kslots.p, nk,
-                                                    h->d_bel, h->d_alpha, c.d_vals.p);
+  pomdp_values_kernel<<<vgrid, 256, 0, c.stream>>>(in.K, in.kidx, h->cap, h->ld, h->ncol,
+                                                    c.d_kslots.p, nk, h->d_bel, in.alpha,
+                                                    c.d_vals.p);
   count_launch();
   pomdp_bounds_kernel<<<(nk + 3) / 4, 128, 0, c.stream>>>(nk, h->ncol, h->n_pbvi,
                                                                c.d_vals.p, c.d_out.p);
@@ -703,7 +776,9 @@ int pp2d_pomdp_create(uint32_t height, uint32_t width, const uint8_t* map,
     count_launch();
     PP2D_CUDA(cudaGetLastError());
     PP2D_CUDA(cudaDeviceSynchronize());
-    return PP2D_OK;
+    const char* dense_env = getenv("PP2D_POMDP_DENSE");
+    h->skip_dead = !(dense_env && atoi(dense_env) != 0);
+    return refresh_live_cells(h);
   }();
   if (rc != PP2D_OK) { pp2d_pomdp_destroy(h); return rc; }
   *out = h;
@@ -714,6 +789,7 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   if (!h) return;
   cudaFree(h->d_map); cudaFree(h->d_tp); cudaFree(h->d_mp); cudaFree(h->d_sr);
   cudaFree(h->d_uniforms); cudaFree(h->d_alpha); cudaFree(h->d_bel);
+  cudaFree(h->d_kidx); cudaFree(h->d_kidx_all); cudaFree(h->d_alpha_live);
   h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();
@@ -746,7 +822,8 @@ int pp2d_pomdp_set_model_tables(pp2d_pomdp* h, const float* trans_prob,
     PP2D_CUDA(cudaMemcpy(h->d_mp, meas_prob, n * 16 * sizeof(float), cudaMemcpyHostToDevice));
   if (stage_reward)
     PP2D_CUDA(cudaMemcpy(h->d_sr, stage_reward, n * 9 * sizeof(float), cudaMemcpyHostToDevice));
-  return PP2D_OK;
+  // the cells mass can enter are a property of the transition table
+  return trans_prob ? refresh_live_cells(h) : PP2D_OK;
 }
 
 int pp2d_pomdp_sampling_uniforms(pp2d_pomdp* h, float* out100) {
@@ -776,6 +853,9 @@ int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
   PP2D_CUDA(cudaMemcpy(h->d_alpha, mat.data(), mat.size() * sizeof(float),
                        cudaMemcpyHostToDevice));
   h->ld = ld; h->ncol = ncol; h->n_pbvi = (int)n_pbvi;
+  h->alpha_host.swap(mat);
+  h->have_alphas = true;
+  PP2D_TRY(refresh_live_cells(h));
   h->fib_actions.assign(9, 0);
   for (int a = 0; a < 9; ++a) h->fib_actions[a] = fib_actions ? fib_actions[a] : (uint8_t)a;
   h->pbvi_actions.assign(n_pbvi, 0);
@@ -921,9 +1001,13 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
                                                       h->d_rows.p, h->d_bel);
     count_launch();
     dim3 vgrid((n + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
-    pomdp_values_kernel<<<vgrid, 256, 0, h->stream>>>(HW, h->cap, h->ld, h->ncol,
+    bool dense = false;
+    for (uint32_t i = 0; i < n && !dense; ++i)
+      dense = !zero_on_dead_cells(h, beliefs + (size_t)i * HW);
+    const InnerDim in = inner_dim(h, dense);
+    pomdp_values_kernel<<<vgrid, 256, 0, h->stream>>>(in.K, in.kidx, h->cap, h->ld, h->ncol,
                                                       h->d_slots.p, n, h->d_bel,
-                                                      h->d_alpha, h->d_vals.p);
+                                                      in.alpha, h->d_vals.p);
     count_launch();
     pomdp_bounds_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(n, h->ncol, h->n_pbvi,
                                                                 h->d_vals.p, h->d_out.p);
@@ -1159,7 +1243,7 @@ int pp2d_tree_update(pp2d_tree* tt, uint8_t a, uint8_t z) {
                                 h->stream));
       PP2D_TRY(normalize_slots(h, 1, nullptr));
       std::vector<int> s1{new_slot};
-      return evaluate_slots(h, s1, ev);
+      return evaluate_slots(h, s1, ev, t.dense);
     }();
     if (rc != PP2D_OK) { h->free_slots.push_back(new_slot); return rc; }
   }
@@ -1175,6 +1259,7 @@ int pp2d_tree_update(pp2d_tree* tt, uint8_t a, uint8_t z) {
   Tree fresh;
   fresh.rng = t.rng;
   fresh.expansions = t.expansions;
+  fresh.dense = t.dense;
   if (root_v >= 0) {
     std::vector<int> vmap(t.v.size(), -1), qmap(t.q.size(), -1);
     struct Item { int idx; bool is_q; };

@@ -93,6 +93,19 @@ struct pp2d_pomdp {
   // bound matrix [HW][ld]: FIB | PBVI (zero padded to whole column tiles)
   float* d_alpha = nullptr;
   int ld = 0, ncol = 9, n_pbvi = 0;
+  // Live cells (pomdp_dead_cells_kernel): the cells probability mass can enter.
+  // d_kidx lists them in ascending order (K of them), d_alpha_live holds the
+  // matching rows of the bound matrix; d_kidx_all = 0..HW-1 is the dense case.
+  // The sequential inner products of a launch run over the live cells only
+  // when every belief of the launch is +0 elsewhere (roots are checked on
+  // upload, see Tree::dense in pomdp.cu).
+  std::vector<uint8_t> dead;               // host copy of the mask
+  std::vector<float> alpha_host;           // dense bound matrix [HW][ld] as uploaded
+  int* d_kidx = nullptr;
+  int* d_kidx_all = nullptr;
+  float* d_alpha_live = nullptr;
+  int K = 0;
+  bool skip_dead = true;                   // PP2D_POMDP_DENSE=1 turns the skipping off
   std::vector<uint8_t> fib_actions, pbvi_actions;
   bool have_alphas = false;
   // belief pool [HW][cap]
@@ -122,4 +135,9 @@ int launch_normalize(pp2d_pomdp* h, const std::vector<int>& slots);
 int launch_prefix(pp2d_pomdp* h, const std::vector<int>& slots);   // -> h->d_prefix [i*HW+s]
 int launch_scatter(pp2d_pomdp* h, const std::vector<int>& slots, const float* host_rows);
 int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows);
+// (re)derive the live-cell list from the transition table on the device and
+// rebuild the compacted bound matrix (pomdp.cu)
+int refresh_live_cells(pp2d_pomdp* h);
+// true when `belief` ([HW], host) is exactly +0 on every dead cell
+bool zero_on_dead_cells(const pp2d_pomdp* h, const float* belief);
 }  // namespace pp2d

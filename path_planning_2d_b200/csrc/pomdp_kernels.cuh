@@ -95,6 +95,34 @@ __global__ void pomdp_model_kernel(int H, int W, int gx, int gy,
   }
 }
 
+// Cells no probability mass can ENTER: dead[s'] = 1 when P(s, u, s') == 0 for
+// every action u and every neighbour s != s' inside the map (the only inflow
+// of such a cell is from itself).  For the generated model these are the
+// occupied cells (blocked mass is shifted to "stay", model_gen:213-233) plus
+// free cells walled in on all sides; the mask is derived from the TABLES, so
+// it also holds for tables loaded from a checkpoint.  A belief that is +0 on
+// the dead cells keeps exact +0 there through every Bayes update
+// (sum of +0 products, times the likelihood, divided by the sum), which is
+// what lets the sequential inner products below skip those cells bit-exactly:
+// acc + (+-0) == acc for an accumulator that starts at +0 (it can never become
+// -0 under round-to-nearest).
+__global__ void pomdp_dead_cells_kernel(int H, int W, const float* __restrict__ trans_prob,
+                                        uint8_t* __restrict__ dead) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= H * W) return;
+  const int x = cell % W, y = cell / W;
+  bool inflow = false;
+  for (int s = 0; s < 9; ++s) {
+    if (s == 4) continue;
+    const int sx = x + s % 3 - 1, sy = y + s / 3 - 1;
+    if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
+    const size_t sidx = (size_t)sy * W + sx;
+    for (int u = 0; u < 9; ++u)
+      inflow = inflow || (trans_prob[81 * sidx + 9 * u + (8 - s)] != 0.0f);
+  }
+  dead[cell] = inflow ? 0 : 1;
+}
+
 // ---------------------------------------------------------------- B2 -------
 // pbvi:88-133 cudaBayesBeliefUpdate, batched: child c is made from belief
 // column src[c] with action act[c] and observation obs[c] and written,
@@ -166,9 +194,13 @@ pomdp_predict_kernel(int H, int W, int cap, int ngp, const float* __restrict__ t
   pred[(size_t)cell * ngp + g] = p;
 }
 
-// sums[k] = accumulate over cells of pred * L(., z_k), in cell order.
+// sums[k] = accumulate over cells of pred * L(., z_k), in cell order.  Only
+// the K cells listed in kidx (ascending) are visited: the prediction is +0 on
+// the others and sum + (+0 * L) == sum (see pomdp_dead_cells_kernel); with
+// kidx = identity this is the plain loop over all HW cells.
 __global__ void __launch_bounds__(128)
-pomdp_child_sum_kernel(int HW, int ngp, const float* __restrict__ meas_prob,
+pomdp_child_sum_kernel(int K, const int* __restrict__ kidx, int ngp,
+                       const float* __restrict__ meas_prob,
                        const BayesItem* __restrict__ items, const int* __restrict__ kgroup,
                        int n, const float* __restrict__ pred, float* __restrict__ sums) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,19 +208,22 @@ pomdp_child_sum_kernel(int HW, int ngp, const float* __restrict__ meas_prob,
   const float* pc = pred + kgroup[k];
   const float* L = meas_prob + items[k].obs;
   float sum = 0.0f;
-  int s = 0;
-  for (; s + 32 <= HW; s += 32) {
+  int c = 0;
+  for (; c + 32 <= K; c += 32) {
     float v[32], l[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      v[j] = pc[(size_t)(s + j) * ngp];
-      l[j] = __ldg(L + (size_t)(s + j) * 16);
+      const int s = __ldg(kidx + c + j);
+      v[j] = pc[(size_t)s * ngp];
+      l[j] = __ldg(L + (size_t)s * 16);
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, mul_ftz(v[j], l[j]));
   }
-  for (; s < HW; ++s)
+  for (; c < K; ++c) {
+    const int s = __ldg(kidx + c);
     sum = __fadd_rn(sum, mul_ftz(pc[(size_t)s * ngp], __ldg(L + (size_t)s * 16)));
+  }
   sums[k] = sum;
 }
 
@@ -350,8 +385,13 @@ pomdp_sample_kernel(int H, int W, int n, int S,
 // shared-memory pipe), K chunks of 16 cells double-buffered with cp.async.
 constexpr int kEvM = 128, kEvN = 128, kEvK = 16, kEvPad = 4;
 
+// The inner dimension runs over the K cells listed in kidx (ascending cell
+// order); alpha holds the K matching rows.  K = HW with kidx = identity is the
+// dense product; with the live cells only (pomdp_dead_cells_kernel) every
+// belief of the launch must be +0 on the cells left out, and the result is
+// bit-identical: the skipped terms are acc + (+-0).
 __global__ void __launch_bounds__(256, 2)
-pomdp_values_kernel(int HW, int cap, int ld, int ncol,
+pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cap, int ld, int ncol,
                     const int* __restrict__ slots, int n,
                     const float* __restrict__ bel,
                     const float* __restrict__ alpha, float* __restrict__ out) {
@@ -369,15 +409,16 @@ pomdp_values_kernel(int HW, int cap, int ld, int ncol,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
 
-  // Tile loaders.  Rows past HW are clamped to the last row: they are never
-  // accumulated (the k loop stops at HW), only kept in bounds.  Columns past
-  // ncol read the zero padding of alpha (ld is a multiple of 128).
+  // Tile loaders (HW = the number K of inner-dimension rows of this launch).
+  // Rows past it are clamped to the last row: they are never accumulated (the
+  // k loop stops at HW), only kept in bounds.  Columns past ncol read the zero
+  // padding of alpha (ld is a multiple of 128).
   auto load_tiles = [&](int buf, int k0) {
 #pragma unroll
     for (int e = 0; e < (kEvK * kEvM) / 256; ++e) {
       const int idx = tid + e * 256;
       const int kk = idx / kEvM, mm = idx % kEvM;
-      const int s = min(k0 + kk, HW - 1);
+      const int s = __ldg(kidx + min(k0 + kk, HW - 1));
       cp_async<4>((uint32_t)__cvta_generic_to_shared(&sb[buf][kk][mm]),
                   bel + (size_t)s * cap + sslot[mm]);
     }
@@ -438,9 +479,12 @@ pomdp_values_kernel(int HW, int cap, int ld, int ncol,
 // (the same sequential multiply-then-add chain as pomdp_values_kernel).
 // stage_reward is the reference table [HW][9].
 __global__ void __launch_bounds__(128)
-pomdp_rewards_kernel(int HW, int cap, const int* __restrict__ slots, int n,
+pomdp_rewards_kernel(int K, const int* __restrict__ kidx, int cap,
+                     const int* __restrict__ slots, int n,
                      const float* __restrict__ bel, const float* __restrict__ stage_reward,
                      float* __restrict__ out) {
+  // cells kidx[0..K) only (ascending): the belief is +0 on the others and
+  // acc + (+0 * r) == acc (see pomdp_dead_cells_kernel)
   const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= n * 9) return;
@@ -448,14 +492,16 @@ pomdp_rewards_kernel(int HW, int cap, const int* __restrict__ slots, int n,
   const float* col = bel + slots[i];
   const float* r = stage_reward + a;
   float acc = 0.0f;
-  float nb = lane < HW ? col[(size_t)lane * cap] : 0.0f;
-  float nr = lane < HW ? __ldg(r + (size_t)lane * 9) : 0.0f;
-  for (int s0 = 0; s0 < HW; s0 += 32) {
+  int s = lane < K ? __ldg(kidx + lane) : 0;
+  float nb = lane < K ? col[(size_t)s * cap] : 0.0f;
+  float nr = lane < K ? __ldg(r + (size_t)s * 9) : 0.0f;
+  for (int c0 = 0; c0 < K; c0 += 32) {
     const float p = __fmul_rn(nb, nr);
-    const int sn = s0 + 32 + lane;
-    nb = sn < HW ? col[(size_t)sn * cap] : 0.0f;
-    nr = sn < HW ? __ldg(r + (size_t)sn * 9) : 0.0f;
-    const int cnt = min(32, HW - s0);
+    const int cn = c0 + 32 + lane;
+    s = cn < K ? __ldg(kidx + cn) : 0;
+    nb = cn < K ? col[(size_t)s * cap] : 0.0f;
+    nr = cn < K ? __ldg(r + (size_t)s * 9) : 0.0f;
+    const int cnt = min(32, K - c0);
     for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, j));
   }
   if (lane == 0) out[(size_t)i * 9 + a] = acc;

@@ -29,8 +29,15 @@ def lib():
         L.oracle_mdp_plan.argtypes = [ctypes.c_uint64, _vp, _vp]
         L.oracle_mdp_waypoints.restype = _u32
         L.oracle_mdp_waypoints.argtypes = [_u32, _u32, _vp, _u32, _u32, _vp, _u32]
+        L.oracle_set_threads.restype = ctypes.c_int
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
+
+
+def set_threads(n):
+    """OpenMP threads of the oracle's loops; returns the count really used."""
+    return lib().oracle_set_threads(int(n))
 
 
 class OracleMdp:

@@ -213,6 +213,40 @@ def test_plan_batch_at_bench_scale_equals_single_query_trees(monkeypatch):
         assert stats[i, 2] == ostats[4], i
 
 
+@pytest.mark.parametrize("dense_env", ["0", "1"])
+def test_beliefs_with_mass_on_dead_cells_take_the_dense_products(monkeypatch, dense_env):
+    """The sequential inner products skip the cells no probability mass can
+    enter (exact while the belief is +0 there).  A start belief that is NOT
+    zero on occupied cells -- or is -0 there -- must switch its whole tree to
+    the dense products; mixed with conforming queries in one batch, every
+    query still equals the oracle bit for bit.  PP2D_POMDP_DENSE=1 (skipping
+    off) gives the same bits."""
+    monkeypatch.setenv("PP2D_POMDP_DENSE", dense_env)
+    name, goal = "map_10x10", (8, 7)
+    grid = cases.load_bundled(name)
+    m, fib, pbvi, fa, pa = pf.alphas(name, goal, n_pbvi=20)
+    beliefs = pf.gaussian_beliefs(grid, 70, seed=21)
+    occ = np.flatnonzero(grid.reshape(-1) == 1)
+    rng = np.random.default_rng(5)
+    beliefs[3] = rng.random(grid.size, dtype=np.float32)
+    beliefs[3] /= beliefs[3].sum(dtype=np.float32)
+    beliefs[17, occ[:4]] = np.float32(1e-3)
+    beliefs[40, occ[1]] = np.float32(-0.0)
+    with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+        p.set_alphas(fib, pbvi, fa, pa)
+        acts, vals, stats = p.plan_batch(beliefs, max_depth=50, max_iter=4, with_stats=True)
+        st = SearchTree(p, beliefs[17])
+        a17, r17 = st.plan(50, 4)
+        st.close()
+    assert (a17, bits(np.float32(r17))) == (acts[17], bits(vals[17]))
+    for i in (0, 3, 17, 40, 69):
+        ot = po.Tree(m, cases.GAMMA, fib, pbvi, pf.uniforms(), beliefs[i], fa, pa)
+        oa, orr, ostats, rc = ot.plan(50, 4)
+        ot.close()
+        assert acts[i] == oa and same(np.float32(vals[i]), np.float32(orr)), i
+        assert stats[i, 0] == ostats[0] and stats[i, 1] == ostats[1], i
+
+
 def test_c_abi_rejects_out_of_range_actions_and_observations():
     """pp2d_pomdp_bayes_update / pp2d_tree_update index the tables with the
     action and observation: out-of-range values are refused before anything
