@@ -317,6 +317,7 @@ def qv_tree_section(rank, world, with_cpu):
         acts, vals, stats = p.plan_batch(mine, with_stats=True)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        p_live = p.live_cells()
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     dt = float(dt.item())
@@ -332,21 +333,67 @@ def qv_tree_section(rank, world, with_cpu):
            "parity": "actions, bounds and tree shapes bit-identical to the oracle and to "
                      "the reference's own SearchTree (tests/test_pomdp_gpu.py, "
                      "tests/test_tree_pin_gpu.py)"}
+    # FP32 roofline of the batch (BASELINE.md config 5 asks for plans/s AND FP32
+    # GFLOP/s).  The dominant kernel, pomdp_values_kernel, evaluates per V node
+    # the 9 FIB + 9 reward + 500 PBVI inner products of the reference as
+    # separately rounded multiplies and adds (no FMA: the reference's host code
+    # is x86-64 without contraction), i.e. 2 floating-point INSTRUCTIONS per
+    # multiply-add; the bound is the FP32 instruction issue rate, 128 lanes x
+    # 148 SMs x SM clock (an FMUL or an FADD is one flop each).  Algorithmic
+    # flops = V nodes x HW cells x (9 + n_pbvi) columns x 2; the kernel executes
+    # them over the live cells only (cells no probability mass can enter are
+    # skipped exactly), so `executed` is smaller.
+    hw = grid.size
+    vnodes = float(stats[:, 0].sum()) * world
+    ncols = 9 + pbvi.shape[0]
+    live = int(p_live)
+    sm_hz = 1.965e9
+    try:
+        sm_hz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"]) * 1e6
+    except Exception:
+        pass
+    peak = 128 * 148 * sm_hz * world / 1e12
+    algo = vnodes * hw * ncols * 2 / dt / 1e12
+    out["roofline"] = {
+        "bound": "fp32_issue", "unit": "TFLOP/s (separately rounded FMUL + FADD)",
+        "achieved": algo, "peak": peak, "frac": algo / peak,
+        "executed": vnodes * live * ncols * 2 / dt / 1e12,
+        "live_cells": live, "cells": hw,
+        "peak_what": "128 FP32 lanes x 148 SMs x SM clock x GPUs, one flop per instruction "
+                     "(tools/ubench/fma_pipes.cu measures 109-119 of the 128 lanes/clk/SM "
+                     "for scalar FP32 streams, profiles/r01_ubench_fma_pipes.txt)",
+        "what": "bounds of all V nodes of the batch over the whole batch time (host tree "
+                "logic, sampling, Bayes updates included in the time)"}
     if with_cpu and rank == 0:
+        import concurrent.futures
         import pomdp_oracle_py as po
         m = po.Model(grid, goal)
-        k = 6
-        same = True
-        t0 = time.perf_counter()
-        for i in range(k):
+        po.lib()                                 # load before the threads start
+
+        def one(i):
             t = po.Tree(m, cases.GAMMA, fib, pbvi, pf.uniforms(), mine[i], fa, pa)
             a, r, st, rc = t.plan(50, 15)
             t.close()
-            same = same and a == acts[i] and np.float32(r) == vals[i]
+            return a == acts[i] and np.float32(r) == vals[i]
+
+        t0 = time.perf_counter()
+        same1 = all(one(i) for i in range(4))
+        one_thread = 4 / (time.perf_counter() - t0)
+        # the trees of different queries are independent: one oracle tree per
+        # host thread (the C oracle runs outside the GIL)
+        cores = host_cores()
+        k = 2 * cores
+        t0 = time.perf_counter()
+        with concurrent.futures.ThreadPoolExecutor(cores) as ex:
+            same = all(ex.map(one, range(4, 4 + k)))
         out["cpu_baseline"] = {"value": k / (time.perf_counter() - t0), "unit": "plans/s",
-                               "cores": 1, "kind": "port",
-                               "sample": f"first {k} queries, oracle/pomdp_oracle.c, 1 thread",
-                               "same_actions_and_values_as_gpu": bool(same)}
+                               "cores": cores, "kind": "port", "value_1_thread": one_thread,
+                               "sample": f"queries 4..{4 + k - 1}, one oracle/pomdp_oracle.c tree "
+                                         f"per thread on {cores} threads; 1-thread figure: "
+                                         "queries 0..3",
+                               "same_actions_and_values_as_gpu": bool(same and same1)}
+        if not (same and same1):
+            raise RuntimeError("QV-tree batch disagrees with the CPU oracle")
     return out
 
 

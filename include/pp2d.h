@@ -83,6 +83,33 @@ int pp2d_mdp_create_shard(uint32_t height, uint32_t width, const uint8_t* map,
                           pp2d_mdp** out);
 
 /*
+ * Single-process multi-GPU variant: what MdpPathPlanning2d::initialize (ONE ROS
+ * process, src/mdp/path_planning_2d.cu:72-140) can bind to reach 2, 4 or 8
+ * GPUs.  The grid is cut into `ngpus` contiguous row blocks; shard i lives on
+ * CUDA device devices[i] (NULL: devices 0 .. ngpus-1) and all of them are
+ * driven from the calling host thread on per-device streams.  The handle
+ * behaves like the one pp2d_mdp_create returns: pp2d_mdp_sweeps(_ex),
+ * pp2d_mdp_residual, pp2d_mdp_solve, pp2d_mdp_download (whole grid),
+ * pp2d_mdp_reset, pp2d_mdp_plan(_batch), pp2d_mdp_waypoints,
+ * pp2d_mdp_sweep_count, pp2d_mdp_p2p_status and pp2d_mdp_destroy work on it,
+ * and the results are bit-identical to the single-GPU solve (Jacobi sweeps do
+ * not depend on the partition).  Between neighbouring shards on different
+ * devices with peer access, ghost rows are written by the fused sweep kernel
+ * straight into the neighbour's memory (NVLink stores + device flags, no
+ * host involvement between launches); otherwise -- including several shards
+ * on one device, e.g. devices = {0, 0} -- they are copied between
+ * event-ordered streams after every launch.  The current device of the
+ * calling thread is preserved by every call.
+ */
+int pp2d_mdp_create_multi(uint32_t height, uint32_t width, const uint8_t* map,
+                          uint32_t goal_x, uint32_t goal_y, float gamma, uint32_t ngpus,
+                          const int* devices, pp2d_mdp** out);
+/* Number of row shards of a handle (1 for pp2d_mdp_create / _create_shard);
+ * peer_to_peer (may be NULL): 1 when the ghost rows of a multi-GPU handle travel
+ * inside the fused kernel. */
+int pp2d_mdp_device_count(const pp2d_mdp* h, int* peer_to_peer);
+
+/*
  * Start over on the same handle with a new map (same height/width/rows) and
  * goal: J = 0, action = 0, sweep count 0, codes rebuilt.  Same checks as
  * pp2d_mdp_create; lets a long-running planner re-solve without paying the
@@ -303,6 +330,15 @@ int pp2d_pomdp_solve_pbvi(pp2d_pomdp* h, const float* initial_belief, uint32_t n
                           float* alphas, uint8_t* actions);
 
 int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs);
+/* The cells probability mass can enter under the current transition table
+ * (some P(s, u, s') != 0 with s != s'); for the generated model: the free cells
+ * that are not walled in.  A belief that is +0 on all other cells stays +0
+ * there through every Bayes update, and the sequential inner products of the
+ * QV-tree path (evaluateFibCpu / evaluatePbviCpu, the reward dot, the
+ * normalisation sum) skip those cells bit-exactly; beliefs that are not (checked
+ * when a start belief is uploaded) take the dense products.  mask: HW bytes,
+ * 1 = live (may be NULL); count: number of live cells (may be NULL). */
+int pp2d_pomdp_live_cells(pp2d_pomdp* h, uint8_t* mask, uint32_t* count);
 /* Host threads used for the per-tree work of pp2d_pomdp_plan_batch (random
  * draws, child lists, tree bookkeeping; the trees of a batch are independent).
  * 0 = default: PP2D_HOST_THREADS, else min(16, CPUs of the process /

@@ -112,8 +112,20 @@ class MdpPathPlanning2d : public PathPlanning2dBase {
       std::fprintf(stderr, "Cannot load the map %s\n", map_path.c_str());
       return false;
     }
-    int rc = pp2d_mdp_create(map_height, map_width, grid_map.data(), goal[0], goal[1],
-                             discount_factor, &mdp_);
+    // One ROS process, `num_gpus` GPUs (optional parameters, not in the
+    // reference: num_gpus, default 1, and gpu_devices, a comma-separated list
+    // of CUDA device ordinals, one per row shard): the same handle type, the
+    // same calls below, bit-identical results.
+    int rc;
+    if (num_gpus > 1 || !gpu_devices.empty())
+      rc = pp2d_mdp_create_multi(map_height, map_width, grid_map.data(), goal[0], goal[1],
+                                 discount_factor,
+                                 gpu_devices.empty() ? (uint32_t)num_gpus
+                                                     : (uint32_t)gpu_devices.size(),
+                                 gpu_devices.empty() ? nullptr : gpu_devices.data(), &mdp_);
+    else
+      rc = pp2d_mdp_create(map_height, map_width, grid_map.data(), goal[0], goal[1],
+                           discount_factor, &mdp_);
     if (rc == PP2D_ERR_GOAL_OCCUPIED || rc == PP2D_ERR_INVALID) {
       std::fprintf(stderr, "The assigned goal (%d %d) is at a occupied cell...\n", goal[0],
                    goal[1]);
@@ -164,6 +176,19 @@ class MdpPathPlanning2d : public PathPlanning2dBase {
     float res = 0.f;
     if (!getParam("map_resolution", res)) return false;
     map_resolution = res;
+    getParam("num_gpus", num_gpus);
+    std::string list;
+    if (getParam("gpu_devices", list)) {
+      gpu_devices.clear();
+      const char* c = list.c_str();
+      while (*c) {
+        char* end = nullptr;
+        const long d = std::strtol(c, &end, 10);
+        if (end == c) break;
+        gpu_devices.push_back((int)d);
+        c = (*end == ',') ? end + 1 : end;
+      }
+    }
     return true;
   }
 
@@ -197,6 +222,8 @@ class MdpPathPlanning2d : public PathPlanning2dBase {
   }
 
   pp2d_mdp* mdp_ = nullptr;
+  int32_t num_gpus = 1;
+  std::vector<int> gpu_devices;
 };
 
 // ---------------------------------------------------------------------------

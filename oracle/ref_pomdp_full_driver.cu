@@ -201,6 +201,18 @@ int ref_full_save_data(const char* dir) {
 int ref_full_load_data(const char* dir) {
   char cwd[4096];
   if (!getcwd(cwd, sizeof(cwd)) || chdir(dir) != 0) return -1;
+  /* The reference reads each action with fscanf("%u") into a uint8_t element
+   * (fast_informed_bound_cuda.cu:379-384, point_based_value_iteration_cuda.cu:
+   * 784-789): 4 bytes are stored per element, so the last element writes 3
+   * bytes past the malloc'ed array.  With the reference's 500 beliefs the
+   * allocator's rounding absorbs it; with the small sets of the tests it
+   * corrupts the heap.  The arrays are re-allocated with slack here (they are
+   * the reference's own globals, freed by its own free()); the values read
+   * are unaffected (ascending elements overwrite the spill-over). */
+  free(host_fib_actions);
+  host_fib_actions = static_cast<uint8_t*>(calloc(9 + 8, 1));
+  free(host_pbvi_actions);
+  host_pbvi_actions = static_cast<uint8_t*>(calloc(g_npbvi + 8, 1));
   const bool ok = loadModelDataFromFile(g_h, g_w) && loadFibDataFromFile(g_h, g_w) &&
                   loadPbviDataFromFile(g_h, g_w);
   if (chdir(cwd) != 0) return -1;

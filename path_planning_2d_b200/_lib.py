@@ -35,6 +35,9 @@ SIGNATURES = {
                              ctypes.POINTER(_vp)]),
     "pp2d_mdp_create_shard": (_i, [_u32, _u32, _vp, _u32, _u32, ctypes.c_float,
                                    _u32, _u32, ctypes.POINTER(_vp)]),
+    "pp2d_mdp_create_multi": (_i, [_u32, _u32, _vp, _u32, _u32, ctypes.c_float, _u32, _vp,
+                                   ctypes.POINTER(_vp)]),
+    "pp2d_mdp_device_count": (_i, [_vp, ctypes.POINTER(_i)]),
     "pp2d_mdp_reset": (_i, [_vp, _vp, _u32, _u32]),
     "pp2d_mdp_destroy": (None, [_vp]),
     "pp2d_mdp_set_stream": (_i, [_vp, _vp]),
@@ -64,6 +67,7 @@ SIGNATURES = {
     "pp2d_pomdp_set_alphas": (_i, [_vp, _vp, _vp, _vp, _vp, _u32]),
     "pp2d_pomdp_solve_fib": (_i, [_vp, _vp, _vp, ctypes.POINTER(_u32), _u32]),
     "pp2d_pomdp_reserve": (_i, [_vp, _u32]),
+    "pp2d_pomdp_live_cells": (_i, [_vp, _vp, ctypes.POINTER(_u32)]),
     "pp2d_pomdp_bayes_update": (_i, [_vp, _vp, _u32, _vp, _vp, _i, _vp, _vp]),
     "pp2d_pomdp_evaluate": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "pp2d_pomdp_plan_batch": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),

@@ -43,6 +43,12 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__, (int)e_, cudaGetErrorName(e_), #expr); \
   } while (0)
 
+#define PP2D_TRY_MDP(expr)             \
+  do {                                 \
+    int rc_ = (expr);                  \
+    if (rc_ != PP2D_OK) return rc_;    \
+  } while (0)
+
 // ---------------------------------------------------------------------------
 // Model numbers of one cell, restated from the reference for the table build:
 // cudaTransitionProbability (path_planning_2d_cuda.cu:76-150) and
@@ -154,7 +160,31 @@ struct pp2d_mdp {
   // reset; occupied cells then follow J_n = (gamma*J_{n-1}) + 2
   bool pi_mode = false;
   std::vector<float> trapped_pi;
+  int device = 0;                  // CUDA device the buffers live on
+  bool owns_stream = false;
+  // launch geometry cache (the occupancy query and the count of boundary units
+  // cost microseconds per launch; a multi-GPU handle launches on N devices from
+  // one host thread)
+  struct LaunchCache {
+    bool valid = false;
+    int ctas_per_sm = 0;
+    int y_rows = 0, lin_len = 0, rows_per_unit = 0, n_units = 0;
+    unsigned int top_segs = 0, bot_segs = 0;
+  } launch_cache[2][3][2][2];      // [T-1][CW: 1,2,4 -> 0,1,2][POLICY][P2P]
+  // ---- single-process multi-GPU container (pp2d_mdp_create_multi) ----------
+  std::vector<pp2d_mdp*> parts;    // row shards, top to bottom; empty for ordinary handles
+  std::vector<cudaEvent_t> ev_done, ev_pulled;   // one per part
+  bool multi_p2p = false;          // ghost rows through the fused kernels' peer stores
+  bool fused_pending = false;      // fused peer-to-peer launches since the last barrier
 };
+
+namespace pp2d {
+struct DeviceGuard {               // restore the caller's current device on exit
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace pp2d
 
 namespace pp2d {
 
@@ -204,13 +234,20 @@ static int launch_sweep(pp2d_mdp* h) {
   const int rows = p.y_end - p.y_begin;
   int rpu = h->rows_per_unit;
   p.lin_len = 0;
-  if (rpu <= 0) {
+  pp2d_mdp::LaunchCache& lc =
+      h->launch_cache[T - 1][CW == 1 ? 0 : (CW == 2 ? 1 : 2)][POLICY ? 1 : 0][P2P ? 1 : 0];
+  if (lc.valid && lc.y_rows == rows) {
+    p.lin_len = lc.lin_len;
+    p.rows_per_unit = lc.rows_per_unit;
+    p.n_units = lc.n_units;
+  } else if (rpu <= 0) {
     // Launch sized to exactly `waves` full waves of resident CTAs (one unit
     // per warp); the units are equal runs of the strip-major row sequence.
     int ctas_per_sm = 0;
     PP2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY, P2P>, kWarpsPerCta * 32, 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
+    lc.ctas_per_sm = ctas_per_sm;
     const long long slots = (long long)h->sm_count * ctas_per_sm * kWarpsPerCta * h->waves;
     // (a) whole row blocks per strip: floor(slots / strips) blocks, no restart;
     long long rb = slots / p.n_strips;
@@ -251,7 +288,10 @@ static int launch_sweep(pp2d_mdp* h) {
       if (y0 < kPadRows) ++top_segs;
       if (y1 > (int)h->H - kPadRows) ++bot_segs;
     };
-    if (p.lin_len > 0) {
+    if (lc.valid && lc.y_rows == rows) {
+      top_segs = lc.top_segs;
+      bot_segs = lc.bot_segs;
+    } else if (p.lin_len > 0) {
       const long long R = rows, total = (long long)p.n_strips * R;
       for (long long u = 0; u < p.n_units; ++u) {
         long long lo = u * p.lin_len;
@@ -270,6 +310,8 @@ static int launch_sweep(pp2d_mdp* h) {
           count(y0, std::min(y0 + p.rows_per_unit, (int)h->H));
       }
     }
+    lc.top_segs = top_segs;
+    lc.bot_segs = bot_segs;
     h->p2p_iter += 1;
     const int nxt = h->cur ^ 1;
     if (h->up_j[nxt]) {
@@ -290,6 +332,11 @@ static int launch_sweep(pp2d_mdp* h) {
     p.edge_rows = h->p2p_edge_rows;
     p.spin_limit = h->p2p_spin_limit;
   }
+  lc.valid = true;
+  lc.y_rows = rows;
+  lc.lin_len = p.lin_len;
+  lc.rows_per_unit = p.rows_per_unit;
+  lc.n_units = p.n_units;
   const int warps_per_cta = kWarpsPerCta;
   const int grid = (p.n_units + warps_per_cta - 1) / warps_per_cta;
   if constexpr (kHasLin) {
@@ -407,6 +454,7 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->Htot = height; h->W = width; h->row_begin = row_begin;
   h->H = row_end - row_begin; h->gx = gx; h->gy = gy; h->gamma = gamma;
   h->sharded = sharded;
+  h->device = dev;
   h->sm_count = prop.multiProcessorCount;
   h->pitch = (int)((kPadLeft + width + 128 + 31) / 32 * 32);
   h->plane = (size_t)(h->H + 2 * kPadRows + kSlackRows) * h->pitch;
@@ -455,6 +503,172 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   return PP2D_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Single-process multi-GPU (pp2d_mdp_create_multi): a container handle whose
+// `parts` are ordinary row shards, one per device, driven from the calling
+// host thread.  Between neighbouring devices with peer access the ghost rows
+// travel inside the fused kernel (direct peer pointers instead of the CUDA-IPC
+// mappings of the one-process-per-GPU driver, same flag protocol); otherwise,
+// and for single sweeps, they are pulled with cudaMemcpyPeerAsync between
+// event-ordered streams.
+static int multi_set_device(const pp2d_mdp* part) {
+  PP2D_CUDA(cudaSetDevice(part->device));
+  return PP2D_OK;
+}
+
+// Every part's stream waits for everything its neighbours have enqueued so far.
+static int multi_barrier(pp2d_mdp* m) {
+  const int n = (int)m->parts.size();
+  for (int i = 0; i < n; ++i) {
+    PP2D_TRY_MDP(multi_set_device(m->parts[i]));
+    PP2D_CUDA(cudaEventRecord(m->ev_done[i], m->parts[i]->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    PP2D_TRY_MDP(multi_set_device(m->parts[i]));
+    if (i > 0) PP2D_CUDA(cudaStreamWaitEvent(m->parts[i]->stream, m->ev_done[i - 1], 0));
+    if (i + 1 < n) PP2D_CUDA(cudaStreamWaitEvent(m->parts[i]->stream, m->ev_done[i + 1], 0));
+  }
+  m->fused_pending = false;
+  return PP2D_OK;
+}
+
+// Ghost rows of every part pulled from its neighbours' current J planes.
+static int multi_exchange(pp2d_mdp* m) {
+  const int n = (int)m->parts.size();
+  if (n == 1) return PP2D_OK;
+  std::vector<pp2d_halo> halo(n);
+  for (int i = 0; i < n; ++i) {
+    int rc = pp2d_mdp_halo(m->parts[i], &halo[i]);
+    if (rc != PP2D_OK) return rc;
+    PP2D_TRY_MDP(multi_set_device(m->parts[i]));
+    PP2D_CUDA(cudaEventRecord(m->ev_done[i], m->parts[i]->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    pp2d_mdp* me = m->parts[i];
+    PP2D_TRY_MDP(multi_set_device(me));
+    if (i > 0) {       // rows H-2, H-1 of the upper neighbour -> my ghost rows -2, -1
+      PP2D_CUDA(cudaStreamWaitEvent(me->stream, m->ev_done[i - 1], 0));
+      PP2D_CUDA(cudaMemcpyPeerAsync(halo[i].recv_top, me->device, halo[i - 1].send_bottom,
+                                    m->parts[i - 1]->device, halo[i].bytes, me->stream));
+    }
+    if (i + 1 < n) {   // rows 0, 1 of the lower neighbour -> my ghost rows H, H+1
+      PP2D_CUDA(cudaStreamWaitEvent(me->stream, m->ev_done[i + 1], 0));
+      PP2D_CUDA(cudaMemcpyPeerAsync(halo[i].recv_bottom, me->device, halo[i + 1].send_top,
+                                    m->parts[i + 1]->device, halo[i].bytes, me->stream));
+    }
+    PP2D_CUDA(cudaEventRecord(m->ev_pulled[i], me->stream));
+  }
+  // nobody overwrites rows a neighbour is still pulling
+  for (int i = 0; i < n; ++i) {
+    PP2D_TRY_MDP(multi_set_device(m->parts[i]));
+    if (i > 0) PP2D_CUDA(cudaStreamWaitEvent(m->parts[i]->stream, m->ev_pulled[i - 1], 0));
+    if (i + 1 < n) PP2D_CUDA(cudaStreamWaitEvent(m->parts[i]->stream, m->ev_pulled[i + 1], 0));
+  }
+  m->fused_pending = false;
+  return PP2D_OK;
+}
+
+static int multi_sync(pp2d_mdp* m) {
+  for (pp2d_mdp* part : m->parts) {
+    PP2D_TRY_MDP(multi_set_device(part));
+    PP2D_CUDA(cudaStreamSynchronize(part->stream));
+  }
+  return PP2D_OK;
+}
+
+static int multi_sweeps(pp2d_mdp* m, uint32_t n, int want_action) {
+  DeviceGuard guard;
+  uint32_t left = n;
+  while (left > 0) {
+    const uint32_t k = left >= 2 ? 2 : 1;
+    const bool last = left == k;
+    const int wa = want_action && last;
+    const bool fused = m->multi_p2p && k == 2 && (!wa || m->parts[0]->fused_policy);
+    if (!fused && m->multi_p2p && m->fused_pending) PP2D_TRY_MDP(multi_barrier(m));
+    for (pp2d_mdp* part : m->parts) {
+      PP2D_TRY_MDP(multi_set_device(part));
+      int rc = pp2d_mdp_sweeps_ex(part, k, wa);
+      if (rc != PP2D_OK) return rc;
+    }
+    if (fused) m->fused_pending = true;
+    else PP2D_TRY_MDP(multi_exchange(m));
+    left -= k;
+  }
+  m->n_sweeps += n;
+  if (want_action) m->action_sweep = m->n_sweeps;
+  m->action_host_valid = false;
+  return m->async ? PP2D_OK : multi_sync(m);
+}
+
+static int multi_residual(pp2d_mdp* m, float* inf_norm) {
+  DeviceGuard guard;
+  for (pp2d_mdp* part : m->parts) {
+    PP2D_TRY_MDP(multi_set_device(part));
+    int rc = pp2d_mdp_residual_device(part, nullptr);
+    if (rc != PP2D_OK) return rc;
+    PP2D_CUDA(cudaMemcpyAsync(part->resid_host, part->resid, sizeof(uint32_t),
+                              cudaMemcpyDeviceToHost, part->stream));
+  }
+  PP2D_TRY_MDP(multi_sync(m));
+  float r = 0.0f;
+  for (pp2d_mdp* part : m->parts) {
+    float v;
+    memcpy(&v, part->resid_host, sizeof(float));
+    r = v > r ? v : r;
+  }
+  *inf_norm = r;
+  m->n_chk = m->n_sweeps;
+  if (m->multi_p2p && std::isinf(r))
+    return fail(PP2D_ERR_STATE, "peer-to-peer ghost-row hand-shake timed out on some device");
+  return PP2D_OK;
+}
+
+static int multi_download(pp2d_mdp* m, float* cost, uint8_t* action) {
+  DeviceGuard guard;
+  if (m->multi_p2p && m->fused_pending) PP2D_TRY_MDP(multi_barrier(m));
+  for (pp2d_mdp* part : m->parts) {
+    PP2D_TRY_MDP(multi_set_device(part));
+    const size_t off = (size_t)part->row_begin * m->W;
+    int rc = pp2d_mdp_download(part, cost ? cost + off : nullptr, action ? action + off : nullptr);
+    if (rc != PP2D_OK) return rc;
+  }
+  return PP2D_OK;
+}
+
+static int multi_reset(pp2d_mdp* m, const uint8_t* map, uint32_t gx, uint32_t gy) {
+  DeviceGuard guard;
+  PP2D_TRY_MDP(multi_sync(m));               // no device may still write a neighbour's rows
+  for (pp2d_mdp* part : m->parts) {
+    PP2D_TRY_MDP(multi_set_device(part));
+    part->gx = gx;
+    part->gy = gy;
+    int rc = upload_map(part, map);
+    if (rc != PP2D_OK) return rc;
+  }
+  m->gx = gx;
+  m->gy = gy;
+  m->n_sweeps = m->n_chk = m->action_sweep = 0;
+  m->action_host_valid = false;
+  m->fused_pending = false;
+  return PP2D_OK;
+}
+
+static void multi_destroy(pp2d_mdp* m) {
+  DeviceGuard guard;
+  for (size_t i = 0; i < m->parts.size(); ++i) {
+    pp2d_mdp* part = m->parts[i];
+    cudaSetDevice(part->device);
+    cudaStreamSynchronize(part->stream);
+    if (i < m->ev_done.size() && m->ev_done[i]) cudaEventDestroy(m->ev_done[i]);
+    if (i < m->ev_pulled.size() && m->ev_pulled[i]) cudaEventDestroy(m->ev_pulled[i]);
+  }
+  for (pp2d_mdp* part : m->parts) {
+    cudaSetDevice(part->device);
+    pp2d_mdp_destroy(part);
+  }
+  m->parts.clear();
+}
+
 }  // namespace pp2d
 
 extern "C" {
@@ -478,6 +692,93 @@ int pp2d_mdp_create_shard(uint32_t height, uint32_t width, const uint8_t* map,
                      row_end, true, out);
 }
 
+int pp2d_mdp_create_multi(uint32_t height, uint32_t width, const uint8_t* map,
+                          uint32_t goal_x, uint32_t goal_y, float gamma, uint32_t ngpus,
+                          const int* devices, pp2d_mdp** out) {
+  if (!out) return fail(PP2D_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (ngpus == 0) return fail(PP2D_ERR_INVALID, "ngpus must be >= 1");
+  if (!map || height == 0 || width == 0) return fail(PP2D_ERR_INVALID, "empty map");
+  if (ngpus > 1 && height < (uint32_t)kPadRows * ngpus)
+    return fail(PP2D_ERR_INVALID, "%u rows cannot be split over %u devices (each shard needs "
+                                  ">= %d rows)", height, ngpus, kPadRows);
+  int dev_count = 0;
+  PP2D_CUDA(cudaGetDeviceCount(&dev_count));
+  if (dev_count == 0) return fail(PP2D_ERR_CUDA, "no CUDA device");
+  for (uint32_t i = 0; i < ngpus; ++i) {
+    const int d = devices ? devices[i] : (int)i;
+    if (d < 0 || d >= dev_count)
+      return fail(PP2D_ERR_INVALID, "shard %u wants CUDA device %d but only %d are visible", i, d,
+                  dev_count);
+  }
+  DeviceGuard guard;
+  pp2d_mdp* m = new (std::nothrow) pp2d_mdp;
+  if (!m) return fail(PP2D_ERR_INVALID, "out of host memory");
+  m->Htot = m->H = height; m->W = width; m->gx = goal_x; m->gy = goal_y; m->gamma = gamma;
+  int rc = [&]() -> int {
+    const uint32_t base = height / ngpus, extra = height % ngpus;
+    uint32_t r0 = 0;
+    for (uint32_t i = 0; i < ngpus; ++i) {
+      const uint32_t r1 = r0 + base + (i < extra ? 1 : 0);
+      PP2D_CUDA(cudaSetDevice(devices ? devices[i] : (int)i));
+      pp2d_mdp* part = nullptr;
+      int rc2 = create_impl(height, width, map, goal_x, goal_y, gamma, r0, r1, ngpus > 1, &part);
+      if (rc2 != PP2D_OK) return rc2;
+      m->parts.push_back(part);
+      PP2D_CUDA(cudaStreamCreateWithFlags(&part->stream, cudaStreamNonBlocking));
+      part->owns_stream = true;
+      part->async = true;               // the container synchronises
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      PP2D_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+      m->ev_done.push_back(e0);
+      PP2D_CUDA(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+      m->ev_pulled.push_back(e1);
+      r0 = r1;
+    }
+    // Peer-to-peer ghost rows need every neighbouring pair on two different
+    // devices with peer access both ways (two shards on ONE device cannot
+    // hand-shake inside their kernels: each launch fills the whole GPU, so the
+    // neighbour it spins on may not be resident).
+    bool p2p = ngpus > 1 && env_int("PP2D_P2P", 1) != 0;
+    for (uint32_t i = 0; p2p && i + 1 < ngpus; ++i) {
+      const int a = m->parts[i]->device, b = m->parts[i + 1]->device;
+      int ab = 0, ba = 0;
+      if (a == b) { p2p = false; break; }
+      PP2D_CUDA(cudaDeviceCanAccessPeer(&ab, a, b));
+      PP2D_CUDA(cudaDeviceCanAccessPeer(&ba, b, a));
+      p2p = ab && ba;
+    }
+    if (p2p) {
+      for (uint32_t i = 0; i + 1 < ngpus; ++i) {
+        pp2d_mdp *up = m->parts[i], *down = m->parts[i + 1];
+        const int pair[2][2] = {{up->device, down->device}, {down->device, up->device}};
+        for (auto& pr : pair) {
+          PP2D_CUDA(cudaSetDevice(pr[0]));
+          cudaError_t e = cudaDeviceEnablePeerAccess(pr[1], 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+          PP2D_CUDA(e);
+        }
+        for (int b = 0; b < 2; ++b) { up->down_j[b] = down->j[b]; down->up_j[b] = up->j[b]; }
+        up->down_flags = down->flags;
+        down->up_flags = up->flags;
+        down->up_H = up->H;
+        up->p2p = down->p2p = true;
+      }
+    }
+    m->multi_p2p = p2p;
+    return PP2D_OK;
+  }();
+  if (rc != PP2D_OK) { pp2d_mdp_destroy(m); return rc; }
+  *out = m;
+  return PP2D_OK;
+}
+
+int pp2d_mdp_device_count(const pp2d_mdp* h, int* peer_to_peer) {
+  if (!h) return 0;
+  if (peer_to_peer) *peer_to_peer = h->parts.empty() ? 0 : (h->multi_p2p ? 1 : 0);
+  return h->parts.empty() ? 1 : (int)h->parts.size();
+}
+
 int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
                    uint32_t goal_y) {
   if (!h || !map) return fail(PP2D_ERR_INVALID, "NULL argument");
@@ -488,6 +789,7 @@ int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
     return fail(PP2D_ERR_GOAL_OCCUPIED,
                 "The assigned goal (%u %u) is at a occupied cell...", goal_x,
                 goal_y);
+  if (!h->parts.empty()) return multi_reset(h, map, goal_x, goal_y);
   h->gx = goal_x;
   h->gy = goal_y;
   return upload_map(h, map);
@@ -495,6 +797,8 @@ int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
 
 void pp2d_mdp_destroy(pp2d_mdp* h) {
   if (!h) return;
+  if (!h->parts.empty()) multi_destroy(h);
+  if (h->owns_stream && h->stream) cudaStreamDestroy(h->stream);
   cudaFree(h->j[0]); cudaFree(h->j[1]); cudaFree(h->jchk); cudaFree(h->code);
   cudaFree(h->action); cudaFree(h->occ); cudaFree(h->dense); cudaFree(h->lut);
   cudaFree(h->resid);
@@ -506,6 +810,8 @@ void pp2d_mdp_destroy(pp2d_mdp* h) {
 
 int pp2d_mdp_set_stream(pp2d_mdp* h, void* stream) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (!h->parts.empty())
+    return fail(PP2D_ERR_STATE, "a multi-GPU handle runs on its own per-device streams");
   h->stream = (cudaStream_t)stream;
   return PP2D_OK;
 }
@@ -519,6 +825,7 @@ int pp2d_mdp_set_async(pp2d_mdp* h, int async) {
 int pp2d_mdp_sweeps_ex(pp2d_mdp* h, uint32_t n, int want_action) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
   if (n == 0) return PP2D_OK;
+  if (!h->parts.empty()) return multi_sweeps(h, n, want_action);
   if (h->sharded && n > 2)
     return fail(PP2D_ERR_STATE,
                 "a shard can advance at most 2 sweeps between halo exchanges");
@@ -569,6 +876,9 @@ uint32_t pp2d_mdp_sweep_count(const pp2d_mdp* h) { return h ? h->n_sweeps : 0; }
 
 int pp2d_mdp_residual_device(pp2d_mdp* h, void** dev_float_out) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (!h->parts.empty())
+    return fail(PP2D_ERR_STATE, "pp2d_mdp_residual_device: use pp2d_mdp_residual on a "
+                                "multi-GPU handle");
   PP2D_CUDA(cudaMemsetAsync(h->resid, 0, sizeof(uint32_t), h->stream));
   // Occupied cells are stored as 0; their change since the last check point
   // is the closed form and enters the reduction as a floor value.
@@ -596,6 +906,7 @@ int pp2d_mdp_residual_device(pp2d_mdp* h, void** dev_float_out) {
 
 int pp2d_mdp_residual(pp2d_mdp* h, float* inf_norm) {
   if (!h || !inf_norm) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (!h->parts.empty()) return multi_residual(h, inf_norm);
   int rc = pp2d_mdp_residual_device(h, nullptr);
   if (rc != PP2D_OK) return rc;
   PP2D_CUDA(cudaMemcpyAsync(h->resid_host, h->resid, sizeof(uint32_t),
@@ -635,8 +946,8 @@ int pp2d_mdp_solve(pp2d_mdp* h, uint32_t* sweeps_out, double* residuals,
 int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* residuals,
                               uint32_t* changed, uint32_t capacity, uint32_t max_rounds) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
-  if (h->sharded)
-    return fail(PP2D_ERR_STATE, "pp2d_mdp_policy_iteration needs an unsharded handle");
+  if (h->sharded || !h->parts.empty())
+    return fail(PP2D_ERR_STATE, "pp2d_mdp_policy_iteration needs an unsharded single-GPU handle");
   if (h->n_sweeps != 0)
     return fail(PP2D_ERR_STATE, "pp2d_mdp_policy_iteration starts from J = 0, action = 0: "
                                 "call pp2d_mdp_reset first");
@@ -691,6 +1002,7 @@ int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* 
 
 int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (!h->parts.empty()) return multi_download(h, cost, action);
   if (h->p2p) {
     int timed_out = 0;
     int rc = pp2d_mdp_p2p_status(h, &timed_out);
@@ -725,24 +1037,49 @@ int pp2d_mdp_plan_batch(pp2d_mdp* h, const float* beliefs, uint32_t n_beliefs,
     return fail(PP2D_ERR_STATE, "pp2d_mdp_plan needs an unsharded handle");
   if (n_beliefs == 0) return PP2D_OK;
   const size_t n = (size_t)h->H * h->W;
+  const bool multi = !h->parts.empty();
+  DeviceGuard guard;
+  cudaStream_t stream = h->stream;
+  if (multi) {
+    // the belief scan runs on the first device; the action grid is spread over
+    // the devices, so the host copy (downloaded once per solve) is consulted
+    if (!h->action_host_valid) {
+      h->action_host.resize(n);
+      int rc = pp2d_mdp_download(h, nullptr, h->action_host.data());
+      if (rc != PP2D_OK) return rc;
+      h->action_host_valid = true;
+    }
+    PP2D_CUDA(cudaSetDevice(h->parts[0]->device));
+    stream = h->parts[0]->stream;
+  }
   float* d_b = nullptr;
   uint8_t* d_a = nullptr;
+  unsigned long long* d_i = nullptr;
   PP2D_CUDA(cudaMalloc(&d_b, n * n_beliefs * sizeof(float)));
-  cudaError_t e = cudaMalloc(&d_a, n_beliefs);
+  cudaError_t e = multi ? cudaMalloc(&d_i, n_beliefs * sizeof(unsigned long long))
+                        : cudaMalloc(&d_a, n_beliefs);
   if (e != cudaSuccess) { cudaFree(d_b); PP2D_CUDA(e); }
   int rc = [&]() -> int {
     PP2D_CUDA(cudaMemcpyAsync(d_b, beliefs, n * n_beliefs * sizeof(float),
-                              cudaMemcpyHostToDevice, h->stream));
-    mdp_plan_kernel<<<n_beliefs, 256, 0, h->stream>>>(d_b, n, h->action, d_a);
+                              cudaMemcpyHostToDevice, stream));
+    mdp_plan_kernel<<<n_beliefs, 256, 0, stream>>>(d_b, n, multi ? nullptr : h->action, d_a, d_i);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PP2D_CUDA(cudaGetLastError());
-    PP2D_CUDA(cudaMemcpyAsync(actions, d_a, n_beliefs, cudaMemcpyDeviceToHost,
-                              h->stream));
-    PP2D_CUDA(cudaStreamSynchronize(h->stream));
+    if (multi) {
+      std::vector<unsigned long long> idx(n_beliefs);
+      PP2D_CUDA(cudaMemcpyAsync(idx.data(), d_i, n_beliefs * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, stream));
+      PP2D_CUDA(cudaStreamSynchronize(stream));
+      for (uint32_t i = 0; i < n_beliefs; ++i) actions[i] = h->action_host[idx[i]];
+    } else {
+      PP2D_CUDA(cudaMemcpyAsync(actions, d_a, n_beliefs, cudaMemcpyDeviceToHost, stream));
+      PP2D_CUDA(cudaStreamSynchronize(stream));
+    }
     return PP2D_OK;
   }();
   cudaFree(d_b);
   cudaFree(d_a);
+  cudaFree(d_i);
   return rc;
 }
 
@@ -788,6 +1125,7 @@ static_assert(sizeof(IpcDesc) <= PP2D_IPC_DESC_BYTES, "IPC descriptor too large"
 
 int pp2d_mdp_ipc_export(pp2d_mdp* h, void* desc) {
   if (!h || !desc) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (!h->parts.empty()) return fail(PP2D_ERR_STATE, "not a shard handle");
   IpcDesc d;
   memset(&d, 0, sizeof(d));
   PP2D_CUDA(cudaIpcGetMemHandle(&d.j[0], h->j[0]));
@@ -837,6 +1175,18 @@ int pp2d_mdp_ipc_connect(pp2d_mdp* h, const void* up_desc, const void* down_desc
 
 int pp2d_mdp_p2p_status(pp2d_mdp* h, int* timed_out) {
   if (!h || !timed_out) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (!h->parts.empty()) {
+    DeviceGuard guard;
+    *timed_out = 0;
+    for (pp2d_mdp* part : h->parts) {
+      int t = 0;
+      PP2D_CUDA(cudaSetDevice(part->device));
+      int rc = pp2d_mdp_p2p_status(part, &t);
+      if (rc != PP2D_OK) return rc;
+      *timed_out |= t;
+    }
+    return PP2D_OK;
+  }
   unsigned int e = 0;
   PP2D_CUDA(cudaMemcpyAsync(&e, h->flags + kFlagError, sizeof(e), cudaMemcpyDeviceToHost,
                             h->stream));
@@ -847,6 +1197,7 @@ int pp2d_mdp_p2p_status(pp2d_mdp* h, int* timed_out) {
 
 int pp2d_mdp_halo(pp2d_mdp* h, pp2d_halo* out) {
   if (!h || !out) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (!h->parts.empty()) return fail(PP2D_ERR_STATE, "not a shard handle");
   float* j = h->j[h->cur];
   const size_t row = (size_t)h->pitch;
   out->recv_top = j;                                       // rows -2, -1

@@ -872,7 +872,8 @@ __global__ void mdp_export_kernel(const float* __restrict__ j,
 // the action stored there.  One CTA per belief.
 __global__ void __launch_bounds__(256)
 mdp_plan_kernel(const float* __restrict__ beliefs, size_t n,
-                const uint8_t* __restrict__ action, uint8_t* __restrict__ out) {
+                const uint8_t* __restrict__ action, uint8_t* __restrict__ out,
+                unsigned long long* __restrict__ out_index) {
   const float* b = beliefs + (size_t)blockIdx.x * n;
   float bm = 0.0f;
   unsigned long long bi = 0;
@@ -895,7 +896,11 @@ mdp_plan_kernel(const float* __restrict__ beliefs, size_t n,
     for (int i = 1; i < 8; ++i)
       if (sv[i] > bm || (sv[i] == bm && si[i] < bi)) { bm = sv[i]; bi = si[i]; }
     // all beliefs <= 0: the reference keeps index 0.
-    out[blockIdx.x] = action[bm > 0.0f ? bi : 0];
+    const unsigned long long mode = bm > 0.0f ? bi : 0;
+    // (a multi-GPU handle keeps the action grid spread over its devices: the
+    // cell index goes back and the host looks the action up)
+    if (action != nullptr) out[blockIdx.x] = action[mode];
+    else out_index[blockIdx.x] = mode;
   }
 }
 

@@ -909,6 +909,18 @@ int pp2d_pomdp_solve_fib(pp2d_pomdp* h, float* alphas, uint8_t* actions,
   return rc;
 }
 
+int pp2d_pomdp_live_cells(pp2d_pomdp* h, uint8_t* mask, uint32_t* count) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  uint32_t n = 0;
+  for (int s = 0; s < h->HW; ++s) {
+    const uint8_t live = h->dead[s] ? 0 : 1;
+    n += live;
+    if (mask) mask[s] = live;
+  }
+  if (count) *count = n;
+  return PP2D_OK;
+}
+
 void pp2d_set_host_threads(int n) { g_host_threads.store(n > 0 ? n : 0); }
 
 int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs) {

@@ -27,7 +27,7 @@ def load_map_png(path):
 class MdpPathPlanning2d:
     """Value-iteration planner on one GPU (or one row shard of the grid)."""
 
-    def __init__(self, grid_map, goal, discount_factor, rows=None):
+    def __init__(self, grid_map, goal, discount_factor, rows=None, devices=None):
         grid_map = np.ascontiguousarray(grid_map, dtype=np.uint8)
         if grid_map.ndim != 2:
             raise ValueError("grid_map must be 2-D (height, width)")
@@ -37,7 +37,22 @@ class MdpPathPlanning2d:
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         self._map = grid_map
-        if rows is None:
+        if devices is not None:
+            # one process, several GPUs: devices = number of GPUs (devices
+            # 0..n-1) or an explicit list of CUDA device ordinals, one per shard
+            if rows is not None:
+                raise ValueError("rows= and devices= are exclusive")
+            self.row_begin, self.row_end = 0, self.map_height
+            if isinstance(devices, int):
+                n, arr = devices, None
+            else:
+                arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+                n = len(devices)
+            rc = self._lib.pp2d_mdp_create_multi(
+                self.map_height, self.map_width, grid_map.ctypes.data,
+                self.goal[0], self.goal[1], float(self.discount_factor), n, arr,
+                ctypes.byref(self._h))
+        elif rows is None:
             self.row_begin, self.row_end = 0, self.map_height
             rc = self._lib.pp2d_mdp_create(
                 self.map_height, self.map_width, grid_map.ctypes.data,
@@ -141,6 +156,16 @@ class MdpPathPlanning2d:
         sweeps, residuals = self.valueIteration()
         self.download()
         return sweeps, residuals
+
+    @property
+    def device_count(self):
+        return self._lib.pp2d_mdp_device_count(self._h, None)
+
+    @property
+    def peer_to_peer(self):
+        p = ctypes.c_int()
+        self._lib.pp2d_mdp_device_count(self._h, ctypes.byref(p))
+        return bool(p.value)
 
     @property
     def sweep_count(self):

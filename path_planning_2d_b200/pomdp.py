@@ -143,6 +143,14 @@ class PomdpPathPlanning2d:
         _lib.check(self._lib.pp2d_pomdp_set_model_tables(
             self._h, *[a.ctypes.data if a is not None else None for a in arrs]))
 
+    def live_cells(self, mask=False):
+        """Number of cells probability mass can enter (and the mask, if asked)."""
+        n = ctypes.c_uint32()
+        m = np.zeros(self.map_height * self.map_width, np.uint8) if mask else None
+        _lib.check(self._lib.pp2d_pomdp_live_cells(
+            self._h, m.ctypes.data if mask else None, ctypes.byref(n)))
+        return (n.value, m.reshape(self.map_height, self.map_width)) if mask else n.value
+
     def sampling_uniforms(self):
         out = np.empty(100, np.float32)
         _lib.check(self._lib.pp2d_pomdp_sampling_uniforms(self._h, out.ctypes.data))

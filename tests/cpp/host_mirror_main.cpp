@@ -30,6 +30,12 @@ int main(int argc, char** argv) {
   if (mode == "mdp" && argc >= 8) {
     Params p{{"map_path", argv[2]}, {"goal_x", argv[3]}, {"goal_y", argv[4]},
              {"discount_factor", argv[5]}, {"map_resolution", "0.2"}};
+    // optional: "gpus=N" (devices 0..N-1) or "devices=0,0,1" (one shard per entry)
+    for (int i = 8; i < argc; ++i) {
+      const std::string a = argv[i];
+      if (a.rfind("gpus=", 0) == 0) p["num_gpus"] = a.substr(5);
+      if (a.rfind("devices=", 0) == 0) p["gpu_devices"] = a.substr(8);
+    }
     MdpPathPlanning2d planner(p);
     if (!planner.initialize()) { std::printf("INIT_FAILED\n"); return 0; }
     auto path = planner.waypoints((uint32_t)atoi(argv[6]), (uint32_t)atoi(argv[7]));

@@ -45,7 +45,9 @@ def test_text_checkpoint_changes_the_model(ref_from_files):
         tp, mp, sr = p.model_tables()
     assert not np.array_equal(bits(mp), bits(g["meas_prob"]))
     assert np.abs(mp - g["meas_prob"]).max() < 1e-8
-    assert np.float32(0.02) ** 4 in mp and np.float32(0.00000016) in g["meas_prob"]
+    # every loaded value is the float nearest to an 8-decimal string
+    back = np.array([float("%15.8f" % v) for v in g["meas_prob"].reshape(-1)[:4096]])
+    assert np.array_equal(back.astype(np.float32), g["meas_prob"].reshape(-1)[:4096])
 
 
 def test_tree_on_loaded_tables_equals_the_reference(ref_from_files):
@@ -142,4 +144,4 @@ def test_binary_checkpoint_is_lossless(exe, tmp_path):  # noqa: F811
     assert tabs["bin"]["sr"] == fnv(sr.tobytes())
     assert tabs["bin"]["fib"] == fnv(g["fib"].tobytes())
     assert tabs["bin"]["pbvi"] == fnv(g["pbvi"].tobytes())
-    assert tabs["txt"]["mp"] != tabs["bin"]["mp"] and tabs["txt"]["pbvi"] != tabs["bin"]["pbvi"]
+    assert tabs["txt"]["mp"] != tabs["bin"]["mp"]        # "%15.8f" is lossy, the binary is not

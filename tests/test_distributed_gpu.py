@@ -64,3 +64,28 @@ def test_nccl_sharded_solve_matches_single_gpu(tmp_path, monkeypatch, p2p, lin):
     assert int(got["sweeps"]) == 205
     assert np.array_equal(got["cost"].view(np.uint32), ora.cost.view(np.uint32))
     assert np.array_equal(got["action"], ora.act)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_single_process_multi_gpu_handle_matches_the_oracle(n):
+    """pp2d_mdp_create_multi on n distinct devices: one host thread, ghost rows
+    through the fused kernel's peer stores; bit-identical to the oracle."""
+    from path_planning_2d_b200 import MdpPathPlanning2d
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs >= {n} GPUs")
+    grid, goal = cases.synthetic_map(301, 517, 0.2, seed=77)
+    ora = oracle_py.OracleMdp(grid, goal, cases.GAMMA)
+    with MdpPathPlanning2d(grid, goal, cases.GAMMA, devices=n) as mdp:
+        assert mdp.device_count == n and mdp.peer_to_peer
+        for k, wa in [(5, False), (100, True), (1, True), (100, True)]:
+            mdp.sweeps(k, wa)
+            ora.sweeps(k)
+        cost, action = mdp.download()
+        assert np.array_equal(cost.view(np.uint32), ora.cost.view(np.uint32))
+        assert np.array_equal(action, ora.act)
+        mdp.reset()
+        sweeps, residuals = mdp.initialize()
+        J, A, m, res = oracle_py.value_iteration(grid, goal, cases.GAMMA)
+        assert sweeps == m and np.array_equal(residuals, res)
+        assert np.array_equal(mdp.optimal_cost.view(np.uint32), J.view(np.uint32))
+        assert np.array_equal(mdp.optimal_action, A)

@@ -77,6 +77,32 @@ def test_cpp_mdp_planner_matches_oracle(exe, name):
 
 
 @pytest.mark.gpu
+def test_cpp_mdp_planner_on_several_gpus_in_one_process(exe):
+    """MdpPathPlanning2d::initialize with num_gpus / gpu_devices binds
+    pp2d_mdp_create_multi: one process drives all the row shards.  With 2+
+    visible GPUs the shards sit on different devices (peer-to-peer ghost rows);
+    a 1-GPU box runs three shards on device 0 (copied ghost rows).  Every
+    printed hash must equal the single-GPU run's."""
+    import torch
+    name = "sparse_map_100x40"
+    goal, start = cases.BUNDLED[name]
+    png = os.path.join(cases.GOLDEN, "maps", name + "_rgb.png")
+    base = [exe, "mdp", png, str(goal[0]), str(goal[1]), "0.95", str(start[0]), str(start[1])]
+
+    def run(*extra):
+        out = subprocess.run(base + list(extra), capture_output=True, text=True)
+        line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+        assert line, out.stdout + out.stderr
+        return line[0]
+
+    single = run()
+    assert run("devices=0,0,0") == single
+    if torch.cuda.device_count() >= 2:
+        assert run("gpus=2") == single
+        assert run("devices=1,0") == single
+
+
+@pytest.mark.gpu
 def test_cpp_mdp_planner_rejects_occupied_goal(exe):
     png = os.path.join(cases.GOLDEN, "maps", "map_10x10_gray.png")
     out = subprocess.run([exe, "mdp", png, "0", "0", "0.95", "1", "1"],

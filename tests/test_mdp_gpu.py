@@ -205,6 +205,43 @@ def test_sharded_handles_reproduce_the_unsharded_solve():
             s.close()
 
 
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0, 0, 0]])
+def test_single_process_multi_shard_handle(devices):
+    """pp2d_mdp_create_multi through every entry point a planner uses; here all
+    shards on device 0 (ghost rows copied between event-ordered streams), so the
+    test also runs on a 1-GPU box.  tests/test_distributed_gpu.py repeats it on
+    distinct devices (peer-to-peer ghost rows)."""
+    grid, goal = cases.synthetic_map(157, 203, 0.2, seed=31)
+    ora = oracle_py.OracleMdp(grid, goal, cases.GAMMA)
+    with MdpPathPlanning2d(grid, goal, cases.GAMMA, devices=devices) as mdp:
+        assert mdp.device_count == len(devices) and not mdp.peer_to_peer
+        for k, wa in [(1, True), (2, False), (5, True), (4, False), (3, True), (100, True)]:
+            mdp.sweeps(k, wa)
+            ora.sweeps(k)
+            if wa:
+                _assert_same(mdp, ora, f"{len(devices)} shards after {ora.n} sweeps")
+        assert mdp.sweep_count == ora.n
+        assert mdp.residual() == np.float32(np.abs(ora.cost).max())
+        rng = np.random.default_rng(1)
+        beliefs = rng.random((9, grid.size), dtype=np.float32)
+        beliefs[0] = 0
+        assert mdp.plan_batch(beliefs).tolist() == [oracle_py.plan(b, ora.act) for b in beliefs]
+        start = tuple(int(v) for v in np.argwhere(grid == 0)[5][::-1])
+        assert np.array_equal(mdp.waypoints(start), oracle_py.waypoints(ora.act, start))
+        # a new map on the same handle, then the reference's stopping rule
+        grid2, goal2 = cases.synthetic_map(157, 203, 0.3, seed=32, goal=(7, 100))
+        mdp.reset(grid2, goal2)
+        J, A, n, res = oracle_py.value_iteration(grid2, goal2, cases.GAMMA)
+        sweeps, residuals = mdp.initialize()
+        assert sweeps == n and np.array_equal(residuals, res)
+        assert np.array_equal(_bits(mdp.optimal_cost), _bits(J))
+        assert np.array_equal(mdp.optimal_action, A)
+    with pytest.raises(_lib.Pp2dError):
+        MdpPathPlanning2d(grid, goal, cases.GAMMA, devices=[0, 99])
+    with pytest.raises(_lib.Pp2dError):
+        MdpPathPlanning2d(grid[:3], (0, 0), cases.GAMMA, devices=[0, 0])
+
+
 def test_full_size_properties_4096():
     """BASELINE.json configs[2] size: the oracle is too slow here, so check
     size-independent properties: (a) sweeps(6)+sweeps(5) == sweeps(11) bit for
@@ -243,10 +280,13 @@ def test_full_size_properties_4096():
 
 
 @pytest.mark.parametrize("shape,goal", [((4096, 4096), (2048, 2048)),
-                                        ((2048, 16384), (8192, 1024))])
+                                        ((1536, 16384), (8192, 700))])
 def test_benchmarked_sizes_to_convergence_vs_the_reference_kernels(shape, goal):
     """BASELINE.json configs[2] (the bench grid: 4096 x 4096, seed 12345, goal
-    at the centre) and one 2048 x 16384 shard-sized grid of configs[3], solved
+    at the centre) and one shard-shaped grid of configs[3], 16384 wide -- 1536
+    rows rather than the 2048 of an 8-GPU shard, because the reference kernels
+    index their tables with 32-bit ints (81 * idx, path_planning_2d_cuda.cu:
+    222-235) and fail beyond 2^31 / 81 = 26.5 M cells --, solved
     to the reference's stopping rule by pp2d_mdp_solve and by the UNMODIFIED
     reference kernels in the reference's own loop (oracle/_ref,
     src/mdp/path_planning_2d.cu:223-263): same number of sweeps, same
