@@ -395,6 +395,39 @@ int pp2d_tree_plan(pp2d_tree* t, uint32_t max_depth, uint32_t max_iter,
  * returns the number of nodes in the tree (negative on error). */
 int64_t pp2d_tree_dump(const pp2d_tree* t, float* out, uint64_t cap_nodes);
 
+/* ------------------------------------------------------------------------
+ * dummy_simulator's Bayes filter
+ * ------------------------------------------------------------------------ */
+typedef struct pp2d_sim pp2d_sim;
+
+/* The simulator's own copy of the map (dummy_simulator.cpp:399-410: the same
+ * threshold as the planners, 1 = occupied). */
+int pp2d_sim_create(uint32_t height, uint32_t width, const uint8_t* map, pp2d_sim** out);
+void pp2d_sim_destroy(pp2d_sim* s);
+/*
+ * DummySimulator::updateBelief(const uint8_t& u) (dummy_simulator.cpp:671-718,
+ * with transitionProbability, :440-522): prediction with the motion model --
+ * blocked and out-of-map mass stays, NO trapped-cell override, unlike the
+ * planners' tables -- then the sequential-sum normalisation.  n independent
+ * beliefs [n][HW] in host memory, updated in place, belief i with actions[i].
+ * Same bits as the reference's scatter loop (summation order per target cell
+ * reproduced).
+ */
+int pp2d_sim_update_belief_action(pp2d_sim* s, float* beliefs, uint32_t n,
+                                  const uint8_t* actions);
+/*
+ * DummySimulator::updateBelief(const std::vector<uint8_t>& meas)
+ * (dummy_simulator.cpp:720-773): likelihood of the four cell measurements
+ * {up, left, right, down} (0.98 / 0.02, out of map = occupied) times the prior,
+ * normalised.  measurements: [n][4] bytes.
+ */
+int pp2d_sim_update_belief_measurement(pp2d_sim* s, float* beliefs, uint32_t n,
+                                       const uint8_t* measurements);
+/* controlCallback's filter part (dummy_simulator.cpp:174-181): action update,
+ * then measurement update, one round trip. */
+int pp2d_sim_step(pp2d_sim* s, float* beliefs, uint32_t n, const uint8_t* actions,
+                  const uint8_t* measurements);
+
 #ifdef __cplusplus
 }
 #endif

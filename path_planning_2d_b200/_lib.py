@@ -75,6 +75,11 @@ SIGNATURES = {
     "pp2d_pomdp_backup_alphas": (_i, [_vp, _vp, _u32, _u32, _vp, _vp]),
     "pp2d_pomdp_solve_pbvi": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
     "pp2d_set_host_threads": (None, [_i]),
+    "pp2d_sim_create": (_i, [_u32, _u32, _vp, ctypes.POINTER(_vp)]),
+    "pp2d_sim_destroy": (None, [_vp]),
+    "pp2d_sim_update_belief_action": (_i, [_vp, _vp, _u32, _vp]),
+    "pp2d_sim_update_belief_measurement": (_i, [_vp, _vp, _u32, _vp]),
+    "pp2d_sim_step": (_i, [_vp, _vp, _u32, _vp, _vp]),
     "pp2d_tree_create": (_i, [_vp, _vp, ctypes.POINTER(_vp)]),
     "pp2d_tree_destroy": (None, [_vp]),
     "pp2d_tree_expand": (_i, [_vp]),

@@ -22,6 +22,11 @@
       (GPU box)  Reference POMDP kernels: tables, Bayes updates, FIB sweeps,
       cuRAND uniforms, forward sampling -> pomdp_<name>.npz.
 
+  python tests/golden/make_golden.py sim [outdir]
+      (build container: CPU only)  The three filter methods of the reference's
+      dummy_simulator, compiled from its own source lines (oracle/Makefile:
+      ref_sim), on the scenarios of tests/sim_oracle_py.py -> sim_<name>.npz.
+
   python tests/golden/make_golden.py tree [outdir]
       (GPU box)  The reference's own QV-tree host code (SearchTree, VNode,
       QNode, evaluateFibCpu, evaluatePbviCpu) -> tree_<case>.npz.
@@ -241,6 +246,19 @@ if __name__ == "__main__":
         os.makedirs(os.path.join(sys.argv[2], "data"), exist_ok=True)
         out = ts.run_reference_case(sys.argv[3], os.path.join(sys.argv[2], "data"))
         np.savez_compressed(os.path.join(sys.argv[2], f"tree_files_{sys.argv[3]}.npz"), **out)
+    elif len(sys.argv) >= 2 and sys.argv[1] == "sim":
+        # sim [outdir]: the reference's own filter methods (oracle/_ref/
+        # libpp2d_ref_sim.so, CPU only -- runs in the build container) on the
+        # scenarios of tests/sim_oracle_py.py -> sim_<name>.npz
+        import sim_oracle_py as so
+        outdir = sys.argv[2] if len(sys.argv) > 2 else HERE
+        for name in so.SCENARIOS:
+            out = so.run_scenario(name, "ref")
+            data = {"crc": so.crc_rows(out), "last": out[:, -1]}
+            if out.shape[2] <= 1000:            # small maps: every intermediate belief
+                data["beliefs"] = out
+            np.savez_compressed(os.path.join(outdir, f"sim_{name}.npz"), **data)
+            print(name, out.shape, "NaNs:", int(np.isnan(out).sum()))
     elif len(sys.argv) >= 2 and sys.argv[1] == "maps":
         make_maps()
     elif len(sys.argv) >= 2 and sys.argv[1] == "pomdp":
