@@ -88,21 +88,31 @@ static const int kRingSlot[10] = {0, 1, 2, 5, 8, 7, 6, 3, 0, 1};
 static const int kPairAction[4][2] = {{1, 2}, {5, 8}, {7, 6}, {3, 0}};
 
 static void build_lut(float gamma, std::vector<float4>& lut) {
-  lut.assign(kLutFloat4, make_float4(0, 0, 0, 0));
-  for (int p = 0; p < 4; ++p) {
-    for (int f = 0; f < 16; ++f) {
-      uint8_t occ[9] = {0};
-      for (int b = 0; b < 4; ++b)
-        if (f >> b & 1) occ[kRingSlot[2 * p + b]] = 1;
-      float g[9], p4[9];
-      cell_model(occ, g, p4);
-      const int u0 = kPairAction[p][0], u1 = kPairAction[p][1];
-      // gamma*tp[i] is rounded to float before the FFMA (SASS of the
-      // reference kernel: FMUL then FFMA).
-      float4 row = make_float4(g[u0], gamma * p4[u0], g[u1], gamma * p4[u1]);
-      for (int c = 0; c < 8; ++c) lut[(p * 16 + f) * 8 + c] = row;
-    }
-  }
+  lut.assign(kLutFloat4 / 8, make_float4(0, 0, 0, 0));   // one copy per row
+  // row of action pair p for the 4-bit ring field f
+  auto pair_row = [&](int p, int f) {
+    uint8_t occ[9] = {0};
+    for (int b = 0; b < 4; ++b)
+      if (f >> b & 1) occ[kRingSlot[2 * p + b]] = 1;
+    float g[9], p4[9];
+    cell_model(occ, g, p4);
+    const int u0 = kPairAction[p][0], u1 = kPairAction[p][1];
+    // gamma*tp[i] is rounded to float before the FFMA (SASS of the
+    // reference kernel: FMUL then FFMA).
+    return make_float4(g[u0], gamma * p4[u0], g[u1], gamma * p4[u1]);
+  };
+#if PP2D_LUT6
+  // table (q, half): pair 2q + half, indexed by the 6 ring bits 4q .. 4q+5 of
+  // which the pair reads bits 2*half .. 2*half+3
+  for (int q = 0; q < 2; ++q)
+    for (int half = 0; half < 2; ++half)
+      for (int f6 = 0; f6 < 64; ++f6) {
+        lut[(q * 2 + half) * 64 + f6] = pair_row(2 * q + half, (f6 >> (2 * half)) & 15);
+      }
+#else
+  for (int p = 0; p < 4; ++p)
+    for (int f = 0; f < 16; ++f) lut[p * 16 + f] = pair_row(p, f);
+#endif
 }
 
 }  // namespace pp2d
@@ -155,6 +165,7 @@ struct pp2d_mdp {
   // tuning knobs (environment overridable, see mdp_config)
   int cw2 = 2, cw1 = 4, rows_per_unit = 0, prefetch_rows = 6, waves = 1;
   bool fused_policy = true;   // arg-min sweep as the second half of a fused pair
+  bool pdl = true;            // programmatic dependent launch of the sweep kernels
   int linear_units = -1;      // -1 = choose per launch, 0 = row blocks, 1 = strip-major runs
   // policy iteration (pp2d_mdp_policy_iteration): evaluation sweeps since the
   // reset; occupied cells then follow J_n = (gamma*J_{n-1}) + 2
@@ -236,6 +247,15 @@ static int launch_sweep(pp2d_mdp* h) {
   p.lin_len = 0;
   pp2d_mdp::LaunchCache& lc =
       h->launch_cache[T - 1][CW == 1 ? 0 : (CW == 2 ? 1 : 2)][POLICY ? 1 : 0][P2P ? 1 : 0];
+  if (!lc.valid && sweep_smem_bytes<T, CW>() > 0) {
+    PP2D_CUDA(cudaFuncSetAttribute(mdp_sweep_kernel<T, CW, POLICY, P2P, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sweep_smem_bytes<T, CW>()));
+    if (kHasLin)
+      PP2D_CUDA(cudaFuncSetAttribute(mdp_sweep_kernel<T, CW, POLICY, P2P, kHasLin>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sweep_smem_bytes<T, CW>()));
+  }
   if (lc.valid && lc.y_rows == rows) {
     p.lin_len = lc.lin_len;
     p.rows_per_unit = lc.rows_per_unit;
@@ -245,7 +265,8 @@ static int launch_sweep(pp2d_mdp* h) {
     // per warp); the units are equal runs of the strip-major row sequence.
     int ctas_per_sm = 0;
     PP2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY, P2P>, kWarpsPerCta * 32, 0));
+        &ctas_per_sm, mdp_sweep_kernel<T, CW, POLICY, P2P>, kWarpsPerCta * 32,
+        sweep_smem_bytes<T, CW>()));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     lc.ctas_per_sm = ctas_per_sm;
     const long long slots = (long long)h->sm_count * ctas_per_sm * kWarpsPerCta * h->waves;
@@ -339,13 +360,26 @@ static int launch_sweep(pp2d_mdp* h) {
   lc.n_units = p.n_units;
   const int warps_per_cta = kWarpsPerCta;
   const int grid = (p.n_units + warps_per_cta - 1) / warps_per_cta;
+  // Fused launches follow each other back to back: with programmatic dependent
+  // launch the prologue of the next one overlaps the tail of this one.
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(warps_per_cta * 32);
+  cfg.dynamicSmemBytes = sweep_smem_bytes<T, CW>();
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = h->pdl ? 1 : 0;
   if constexpr (kHasLin) {
     if (p.lin_len > 0)
-      mdp_sweep_kernel<T, CW, POLICY, P2P, true><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+      PP2D_CUDA(cudaLaunchKernelEx(&cfg, mdp_sweep_kernel<T, CW, POLICY, P2P, true>, p));
     else
-      mdp_sweep_kernel<T, CW, POLICY, P2P, false><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+      PP2D_CUDA(cudaLaunchKernelEx(&cfg, mdp_sweep_kernel<T, CW, POLICY, P2P, false>, p));
   } else {
-    mdp_sweep_kernel<T, CW, POLICY, P2P><<<grid, warps_per_cta * 32, 0, h->stream>>>(p);
+    PP2D_CUDA(cudaLaunchKernelEx(&cfg, mdp_sweep_kernel<T, CW, POLICY, P2P>, p));
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   PP2D_CUDA(cudaGetLastError());
@@ -463,6 +497,7 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->cw1 = env_int("PP2D_MDP_CW1", 4);
   h->fused_policy = env_int("PP2D_MDP_FUSED_POLICY", 1) != 0;
   h->linear_units = env_int("PP2D_MDP_LINEAR_UNITS", -1);
+  h->pdl = env_int("PP2D_MDP_PDL", 1) != 0;
   h->rows_per_unit = env_int("PP2D_MDP_ROWS_PER_UNIT", 0);
   h->prefetch_rows = env_int("PP2D_MDP_PREFETCH_ROWS", 6);
   h->waves = env_int("PP2D_MDP_WAVES", 1);
@@ -487,14 +522,14 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
     PP2D_CUDA(cudaMalloc(&h->code, h->plane * sizeof(uint16_t)));
     PP2D_CUDA(cudaMalloc(&h->action, owned));
     PP2D_CUDA(cudaMalloc(&h->occ, (size_t)occ_rows * width));
-    PP2D_CUDA(cudaMalloc(&h->lut, kLutFloat4 * sizeof(float4)));
+    PP2D_CUDA(cudaMalloc(&h->lut, kLutFloat4 / 8 * sizeof(float4)));
     PP2D_CUDA(cudaMalloc(&h->resid, sizeof(uint32_t)));
     PP2D_CUDA(cudaMalloc(&h->flags, kFlagWords * sizeof(unsigned int)));
     PP2D_CUDA(cudaMemset(h->flags, 0, kFlagWords * sizeof(unsigned int)));
     PP2D_CUDA(cudaMallocHost(&h->resid_host, sizeof(uint32_t)));
     std::vector<float4> lut;
     build_lut(gamma, lut);
-    PP2D_CUDA(cudaMemcpy(h->lut, lut.data(), kLutFloat4 * sizeof(float4),
+    PP2D_CUDA(cudaMemcpy(h->lut, lut.data(), kLutFloat4 / 8 * sizeof(float4),
                          cudaMemcpyHostToDevice));
     return upload_map(h, map);
   }();

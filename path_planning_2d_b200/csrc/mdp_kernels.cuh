@@ -53,7 +53,28 @@ constexpr int kPrefetch = 2;  // CW == 1 path: rows held in registers ahead of u
 #endif
 constexpr int kRing = PP2D_KRING;  // CW >= 2 path: cp.async ring slots per lane (1, 2, 3 or 6)
 constexpr int kPadLeft = 8;   // zero columns left of x = 0 (32 B)
+// Table layouts (build-time choice, both give the same bits):
+//   PP2D_LUT6 = 0: 4 tables (one per action pair) x 16 rows (4 ring bits) x 8
+//     lane replicas of one float4 = 8 KB; a cell needs 4 row addresses.
+//   PP2D_LUT6 = 1: two ring-adjacent action pairs share 6 ring bits, so ONE row
+//     address serves both: 2 super-pairs x 2 halves x 64 rows x 8 replicas =
+//     32 KB, 2 row addresses per cell (each SHF + LOP3) instead of 4.
+#ifndef PP2D_LUT6
+#define PP2D_LUT6 0
+#endif
+// PP2D_UWARP = 1: the warp index is read through a shuffle from lane 0, which
+// tells the compiler it is warp-uniform (unit, row counts and loop exits then
+// are, too: no divergence guard in front of the shuffles of the marching loop).
+#ifndef PP2D_UWARP
+#define PP2D_UWARP 1
+#endif
+#if PP2D_LUT6
+constexpr int kLutFloat4 = 2 * 2 * 64 * 8;
+constexpr int kLutAlign = 8192;         // row bits 7..12 + replica bits 4..6 are OR-ed in
+#else
 constexpr int kLutFloat4 = 4 * 16 * 8;  // 4 action pairs x 16 rows x 8 copies
+constexpr int kLutAlign = 2048;
+#endif
 // Tuning knobs (tools/sweep_variants.py builds alternates): how the minimum
 // over the 9 actions is taken, warps per CTA and resident CTAs per SM of the
 // fused kernel.
@@ -78,7 +99,7 @@ struct SweepParams {
   float* jout;
   const uint16_t* code;  // same geometry as J
   uint8_t* action;       // dense [H][W] (POLICY only)
-  const float4* lut;     // kLutFloat4 entries, already lane-replicated
+  const float4* lut;     // kLutFloat4 / 8 rows (the kernel writes the 8 lane replicas)
   int W, H, pitch;
   int n_strips, rows_per_unit, n_units;
   int y_begin, y_end;    // rows to produce (may extend 1 row into the ghosts)
@@ -267,10 +288,23 @@ __device__ __forceinline__ float4 lut_row(uint32_t lane_base, uint32_t word) {
 template <bool HI>
 __device__ __forceinline__ void lut_fetch(uint32_t lane_base, uint32_t word,
                                           float4 (&t)[4], float& g4) {
+#if PP2D_LUT6
+  // super-pair 0: ring bits 0..5 (pairs 0 and 1), super-pair 1: ring bits 4..9
+  // (pairs 2 and 3); row offset = 6 bits << 7, the two halves 8 KB apart
+  const uint32_t s0 = HI ? (word >> 9) : (word << 7);
+  const uint32_t a0 = (s0 & 0x1F80u) | lane_base;
+  t[0] = lds128<0>(a0);
+  t[1] = lds128<8192>(a0);
+  const uint32_t s1 = HI ? (word >> 13) : (word << 3);
+  const uint32_t a1 = (s1 & 0x1F80u) | lane_base;
+  t[2] = lds128<16384>(a1);
+  t[3] = lds128<24576>(a1);
+#else
   t[0] = lut_row<HI, 0>(lane_base, word);
   t[1] = lut_row<HI, 1>(lane_base, word);
   t[2] = lut_row<HI, 2>(lane_base, word);
   t[3] = lut_row<HI, 3>(lane_base, word);
+#endif
   // live bit (14 of the code) -> 2.0f (0x40000000); goal, occupied cells and
   // padding -> 0.0f, which makes "stay" cost exactly 0 there (their J is 0).
   g4 = __uint_as_float((HI ? word : (word << 16)) & 0x40000000u);
@@ -638,9 +672,24 @@ struct Sweeper {
   }
 };
 
+// Dynamic shared memory of a launch (PP2D_LUT6 builds; the 8 KB table keeps
+// its static buffer so that the default build's code is untouched).
+template <int T, int CW>
+constexpr size_t sweep_smem_bytes() {
+#if PP2D_LUT6
+  return (size_t)kLutFloat4 * 16 + kLutAlign + (size_t)kWarpsPerCta * StripGeom<T, CW>::kRingBytesPerWarp;
+#else
+  return 0;
+#endif
+}
+
 // One warp per (column strip, row block) unit; kWarpsPerCta warps per CTA.
 template <int T, int CW, bool POLICY, bool P2P = false, bool LIN = false>
+#ifdef PP2D_MAXNREG
+__global__ void __maxnreg__(PP2D_MAXNREG)
+#else
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (T == 2 && CW == 2) ? PP2D_MINCTAS : 1)
+#endif
 mdp_sweep_kernel(const SweepParams p) {
   // The table must start on a 2 KB boundary of the shared window so that the
   // row offset (bits 7..10) and the lane replica (bits 4..6) can be OR-ed
@@ -648,15 +697,37 @@ mdp_sweep_kernel(const SweepParams p) {
   // the alignment is done at run time on an over-allocated buffer.
   using G = StripGeom<T, CW>;
   constexpr int kWarps = kWarpsPerCta;
+  // Programmatic dependent launch: the next launch of the stream may start its
+  // prologue (the table copy below, which reads nothing a sweep writes) while
+  // this one is still running; it blocks in griddepcontrol.wait until this grid
+  // has completed and its writes are visible.  Both are no-ops for a launch
+  // without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#if PP2D_LUT6
+  extern __shared__ __align__(16) unsigned char lut_raw[];   // sweep_smem_bytes<T, CW>()
+#else
   __shared__ __align__(16) unsigned char
-      lut_raw[kLutFloat4 * 16 + 2048 + kWarps * G::kRingBytesPerWarp];
+      lut_raw[kLutFloat4 * 16 + kLutAlign + kWarps * G::kRingBytesPerWarp];
+#endif
   const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(lut_raw);
-  const uint32_t lut_addr = (raw_addr + 2047u) & ~2047u;
+  const uint32_t lut_addr = (raw_addr + (uint32_t)(kLutAlign - 1)) & ~(uint32_t)(kLutAlign - 1);
   float4* lut_s = reinterpret_cast<float4*>(lut_raw + (lut_addr - raw_addr));
-  for (int i = threadIdx.x; i < kLutFloat4; i += blockDim.x) lut_s[i] = p.lut[i];
+  // p.lut holds ONE copy of every row (kLutFloat4 / 8 rows); the 8 lane
+  // replicas are written here: one global load and 8 shared stores per row.
+  for (int i = threadIdx.x; i < kLutFloat4 / 8; i += blockDim.x) {
+    const float4 row = p.lut[i];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) lut_s[i * 8 + c] = row;
+  }
   __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+#if PP2D_UWARP
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+#else
+  const int warp = (int)(threadIdx.x >> 5);
+#endif
+  const int unit = blockIdx.x * (blockDim.x >> 5) + warp;
   if (unit >= p.n_units) return;
   // Produced by a volatile asm after the barrier: the table loads (plain asm,
   // free to be scheduled) depend on it and so cannot move above the barrier.
@@ -664,7 +735,7 @@ mdp_sweep_kernel(const SweepParams p) {
   asm volatile("or.b32 %0, %1, %2;"
                : "=r"(lane_base) : "r"(lut_addr), "r"((lane & 7) << 4) : "memory");
   const uint32_t ring_warp =
-      lut_addr + kLutFloat4 * 16 + (threadIdx.x >> 5) * G::kRingBytesPerWarp;
+      lut_addr + kLutFloat4 * 16 + warp * G::kRingBytesPerWarp;
   Sweeper<T, CW, POLICY, P2P, LIN> s(p, lane_base, ring_warp);
   s.run(unit, lane);
 }

@@ -8,7 +8,7 @@ for spec in "$@"; do
   /usr/local/cuda/bin/nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
     -Xcompiler -fPIC -Xcompiler -fopenmp -shared -I include $flags -Xptxas -v \
     -o build/variants/libpp2d_$name.so path_planning_2d_b200/csrc/mdp.cu \
-    path_planning_2d_b200/csrc/pomdp.cu path_planning_2d_b200/csrc/pbvi.cu -ldl -lgomp 2> build/variants/$name.ptxas.log &
+    path_planning_2d_b200/csrc/pomdp.cu path_planning_2d_b200/csrc/pbvi.cu path_planning_2d_b200/csrc/sim.cu -ldl -lgomp 2> build/variants/$name.ptxas.log &
 done
 wait
 for spec in "$@"; do name=${spec%%=*}; echo "== $name"; grep -A2 "mdp_sweep_kernelILi2ELi2ELb0ELb0" build/variants/$name.ptxas.log | grep -E "registers|spill"; done

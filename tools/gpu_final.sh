@@ -1,11 +1,11 @@
 #!/bin/bash
 # Round-end evidence on one B200: tests, bench (both arms), ncu launch lists and
 # one full capture of the fused sweep kernel and of the QV-tree values kernel.
-TAG=${1:-r01z}
+TAG=${1:-r02z}
 OUT=gpurun_out; mkdir -p $OUT
 echo "== smoke"; python __graft_entry__.py smoke 2>&1 | tail -1
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -q -m gpu --timeout=900 > $OUT/pytest_$TAG.log 2>&1; echo "exit $?"; tail -3 $OUT/pytest_$TAG.log
-echo "== bench reference arm"; python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "exit $?"
+echo "== bench reference arm"; python bench.py --impl reference --steps 10 --warmup 3 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "exit $?"
 echo "== bench"; python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "exit $?"; cut -c1-400 $OUT/bench_$TAG.json
 echo "== ncu launch list (MDP step)"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
@@ -19,3 +19,5 @@ ncu --set full --import-source on --clock-control none -k regex:mdp_sweep_kernel
 echo "== ncu full: values kernel"
 ncu --set full --import-source on --clock-control none -k regex:pomdp_values -s 20 -c 1 -o $OUT/prof_values_$TAG -f \
   python tools/bench_pomdp.py 1250 --fixture > $OUT/ncu_full_values_$TAG.log 2>&1; echo "exit $?"
+echo "== SASS of the fused kernel (instruction histogram + one marching step)"
+python tools/sass_summary.py > $OUT/sass_fused_$TAG.txt 2>&1; echo "exit $?"

@@ -1,5 +1,6 @@
 """Turn the raw ncu outputs of tools/gpu_final.sh (gpurun_out/, scratch) into the
-committed summaries under profiles/.  usage: python tools/summarize_profiles.py <tag>"""
+committed summaries under profiles/.  usage: python tools/summarize_profiles.py <gpurun tag> [round prefix]
+Every header names the gpurun call the numbers of THAT file come from."""
 import collections
 import csv
 import json
@@ -12,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 tag = sys.argv[1]
-rnd = "r01"
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r02"   # prefix of the files under profiles/
 
 
 def launch_summary(src, dst, header):
@@ -91,14 +92,15 @@ def to_bytes(v, unit):
 
 launch_summary(os.path.join(OUT, f"launches_{tag}.csv"), os.path.join(PROF, f"{rnd}_launches_summary.txt"),
                "# ncu --metrics gpu__time_duration.sum --clock-control none -c 400 on: python bench.py --steps 2 "
-               "--warmup 3 --no-cpu --no-ref-cuda --no-qv\n# (round 1, B200, gpurun call %s; first 400 launches; "
+               "--warmup 3 --no-cpu --no-ref-cuda --no-qv\n# (B200, gpurun call %s; first 400 launches; "
                "per-launch times are cold-cache and serialised: compare SHARES)\n" % tag)
 shutil.copy(os.path.join(OUT, f"launches_{tag}.csv"), os.path.join(PROF, f"{rnd}_launches.csv"))
 launch_summary(os.path.join(OUT, f"pomdp_launches_{tag}.csv"),
                os.path.join(PROF, f"{rnd}_pomdp_launches_summary.txt"),
                "# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:pomdp_ -c 600 on: python "
                "tools/bench_pomdp.py 1250 --fixture\n# (QV-tree batch of 1250 plans x 3 calls: 32-query warm-up + two "
-               "full batches; the offline solvers are skipped with --fixture: they are 29 000 launches)\n")
+               "full batches; the offline solvers are skipped with --fixture: they are 29 000 launches; gpurun "
+               "call %s)\n" % tag)
 vals, units = kernel_summary(os.path.join(OUT, f"prof_fused_{tag}.ncu-rep"),
                              os.path.join(PROF, f"{rnd}_ncu_fused_kernel.txt"),
                              "# ncu --set full --clock-control none --import-source on, fused kernel "
