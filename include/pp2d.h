@@ -182,6 +182,18 @@ int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* 
  * action: rows*width bytes (rows = owned rows); either may be NULL.
  */
 int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action);
+/*
+ * The same download in two halves, for a planner that re-solves while the
+ * previous solution is still on its way to the host: _begin snapshots J (cost
+ * of occupied cells filled in) and the action grid into device staging buffers
+ * in stream order and starts the device-to-host copies on a separate copy
+ * stream, then returns; the handle may be swept or reset immediately.  _wait
+ * blocks until the host buffers are complete (page-locked host buffers are
+ * needed for the copies to overlap device work).  A second _begin before the
+ * _wait of the first waits for it on the device.
+ */
+int pp2d_mdp_download_begin(pp2d_mdp* h, float* cost, uint8_t* action);
+int pp2d_mdp_download_wait(pp2d_mdp* h);
 
 /*
  * MdpPathPlanning2d::beliefCallback (src/mdp/path_planning_2d.cu:168-189):

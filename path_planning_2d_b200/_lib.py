@@ -49,6 +49,8 @@ SIGNATURES = {
     "pp2d_mdp_solve": (_i, [_vp, ctypes.POINTER(_u32), _vp, _u32]),
     "pp2d_mdp_policy_iteration": (_i, [_vp, _vp, _vp, _vp, _u32, _u32]),
     "pp2d_mdp_download": (_i, [_vp, _vp, _vp]),
+    "pp2d_mdp_download_begin": (_i, [_vp, _vp, _vp]),
+    "pp2d_mdp_download_wait": (_i, [_vp]),
     "pp2d_mdp_plan": (_i, [_vp, _vp, _vp]),
     "pp2d_mdp_plan_batch": (_i, [_vp, _vp, _u32, _vp]),
     "pp2d_mdp_waypoints": (_i, [_vp, _u32, _u32, _vp, _u32,

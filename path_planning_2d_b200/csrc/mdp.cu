@@ -133,6 +133,10 @@ struct pp2d_mdp {
   uint8_t* action = nullptr;       // dense [H][W]
   uint8_t* occ = nullptr;          // dense rows [occ_row0, occ_row0+occ_rows)
   float* dense = nullptr;          // export staging [H][W]
+  uint8_t* dense_action = nullptr; // action snapshot of an asynchronous download
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_snapshot = nullptr, ev_copied = nullptr;
+  bool download_pending = false;
   float4* lut = nullptr;
   uint32_t* resid = nullptr;       // device float bits
   uint32_t* resid_host = nullptr;  // pinned
@@ -658,18 +662,6 @@ static int multi_residual(pp2d_mdp* m, float* inf_norm) {
   return PP2D_OK;
 }
 
-static int multi_download(pp2d_mdp* m, float* cost, uint8_t* action) {
-  DeviceGuard guard;
-  if (m->multi_p2p && m->fused_pending) PP2D_TRY_MDP(multi_barrier(m));
-  for (pp2d_mdp* part : m->parts) {
-    PP2D_TRY_MDP(multi_set_device(part));
-    const size_t off = (size_t)part->row_begin * m->W;
-    int rc = pp2d_mdp_download(part, cost ? cost + off : nullptr, action ? action + off : nullptr);
-    if (rc != PP2D_OK) return rc;
-  }
-  return PP2D_OK;
-}
-
 static int multi_reset(pp2d_mdp* m, const uint8_t* map, uint32_t gx, uint32_t gy) {
   DeviceGuard guard;
   PP2D_TRY_MDP(multi_sync(m));               // no device may still write a neighbour's rows
@@ -833,6 +825,11 @@ int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
 void pp2d_mdp_destroy(pp2d_mdp* h) {
   if (!h) return;
   if (!h->parts.empty()) multi_destroy(h);
+  if (h->download_pending) cudaEventSynchronize(h->ev_copied);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
+  if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+  cudaFree(h->dense_action);
   if (h->owns_stream && h->stream) cudaStreamDestroy(h->stream);
   cudaFree(h->j[0]); cudaFree(h->j[1]); cudaFree(h->jchk); cudaFree(h->code);
   cudaFree(h->action); cudaFree(h->occ); cudaFree(h->dense); cudaFree(h->lut);
@@ -1035,18 +1032,28 @@ int pp2d_mdp_policy_iteration(pp2d_mdp* h, uint32_t* evaluation_sweeps, double* 
   return sync_if_needed(h);
 }
 
-int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action) {
+int pp2d_mdp_download_begin(pp2d_mdp* h, float* cost, uint8_t* action) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
-  if (!h->parts.empty()) return multi_download(h, cost, action);
-  if (h->p2p) {
-    int timed_out = 0;
-    int rc = pp2d_mdp_p2p_status(h, &timed_out);
-    if (rc != PP2D_OK) return rc;
-    if (timed_out)
-      return fail(PP2D_ERR_STATE, "peer-to-peer ghost-row hand-shake timed out: J and the "
-                                  "action grid of this shard are invalid");
+  if (!h->parts.empty()) {
+    DeviceGuard guard;
+    if (h->multi_p2p && h->fused_pending) PP2D_TRY_MDP(multi_barrier(h));
+    for (pp2d_mdp* part : h->parts) {
+      PP2D_TRY_MDP(multi_set_device(part));
+      const size_t off = (size_t)part->row_begin * h->W;
+      int rc = pp2d_mdp_download_begin(part, cost ? cost + off : nullptr,
+                                       action ? action + off : nullptr);
+      if (rc != PP2D_OK) return rc;
+    }
+    return PP2D_OK;
   }
   const size_t owned = (size_t)h->H * h->W;
+  if (!h->copy_stream) {
+    PP2D_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    PP2D_CUDA(cudaEventCreateWithFlags(&h->ev_snapshot, cudaEventDisableTiming));
+    PP2D_CUDA(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+  }
+  // the staging buffers may still be feeding an earlier download
+  if (h->download_pending) PP2D_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
   if (cost) {
     if (!h->dense) PP2D_CUDA(cudaMalloc(&h->dense, owned * sizeof(float)));
     dim3 grid((h->W + 255) / 256, h->H);
@@ -1055,14 +1062,55 @@ int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action) {
         occupied_cost(h, h->n_sweeps));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PP2D_CUDA(cudaGetLastError());
-    PP2D_CUDA(cudaMemcpyAsync(cost, h->dense, owned * sizeof(float),
-                              cudaMemcpyDeviceToHost, h->stream));
   }
-  if (action)
-    PP2D_CUDA(cudaMemcpyAsync(action, h->action, owned, cudaMemcpyDeviceToHost,
+  if (action) {
+    if (!h->dense_action) PP2D_CUDA(cudaMalloc(&h->dense_action, owned));
+    PP2D_CUDA(cudaMemcpyAsync(h->dense_action, h->action, owned, cudaMemcpyDeviceToDevice,
                               h->stream));
-  PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  PP2D_CUDA(cudaEventRecord(h->ev_snapshot, h->stream));
+  PP2D_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_snapshot, 0));
+  if (cost)
+    PP2D_CUDA(cudaMemcpyAsync(cost, h->dense, owned * sizeof(float), cudaMemcpyDeviceToHost,
+                              h->copy_stream));
+  if (action)
+    PP2D_CUDA(cudaMemcpyAsync(action, h->dense_action, owned, cudaMemcpyDeviceToHost,
+                              h->copy_stream));
+  PP2D_CUDA(cudaEventRecord(h->ev_copied, h->copy_stream));
+  h->download_pending = true;
   return PP2D_OK;
+}
+
+int pp2d_mdp_download_wait(pp2d_mdp* h) {
+  if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
+  if (!h->parts.empty()) {
+    DeviceGuard guard;
+    for (pp2d_mdp* part : h->parts) {
+      PP2D_TRY_MDP(multi_set_device(part));
+      int rc = pp2d_mdp_download_wait(part);
+      if (rc != PP2D_OK) return rc;
+    }
+    return PP2D_OK;
+  }
+  if (h->download_pending) {
+    PP2D_CUDA(cudaEventSynchronize(h->ev_copied));
+    h->download_pending = false;
+  }
+  if (h->p2p) {
+    int timed_out = 0;
+    int rc = pp2d_mdp_p2p_status(h, &timed_out);
+    if (rc != PP2D_OK) return rc;
+    if (timed_out)
+      return fail(PP2D_ERR_STATE, "peer-to-peer ghost-row hand-shake timed out: J and the "
+                                  "action grid of this shard are invalid");
+  }
+  return PP2D_OK;
+}
+
+int pp2d_mdp_download(pp2d_mdp* h, float* cost, uint8_t* action) {
+  int rc = pp2d_mdp_download_begin(h, cost, action);
+  if (rc != PP2D_OK) return rc;
+  return pp2d_mdp_download_wait(h);
 }
 
 int pp2d_mdp_plan_batch(pp2d_mdp* h, const float* beliefs, uint32_t n_beliefs,

@@ -22,11 +22,19 @@
 //     reproduced with explicit PTX (fp_exact.cuh);
 //   * rand() is glibc's TYPE_3 generator (GlibcRand), one global stream in the
 //     reference's call order (belief-major, action-minor, three draws each);
-//   * the one dense contraction, Gamma_ao^T * B (set x set x HW), is a plain
-//     library GEMM in the reference (cublasSgemm, pbvi:505-513) and stays one:
-//     the same call with the same shapes, so the arg-max it feeds sees the
-//     same rounding.  cuBLAS is bound at run time (dlopen), nothing else in
-//     the library depends on it.
+//   * the one dense contraction, Gamma_ao^T * B (set x set x HW; cublasSgemm in
+//     the reference, pbvi:505-513), is the hand-written pbvi_sgemm_tn_kernel
+//     with a DEFINED summation order (one sequential FMA chain over the cells
+//     per output).  Its result R only feeds an arg-max -- which Gamma_ao vector
+//     each belief picks --; the alpha vectors are gathered from Gamma_ao, not
+//     computed from R.  The contract is therefore: identical alpha vectors
+//     whenever no arg-max is decided by the last bits of two near-equal R
+//     entries (cuBLAS's blocking order is unspecified, so the reference itself
+//     is only defined up to that).  On every fixture of the reference's own
+//     solver, including the 500-belief bundled-map case, the alpha vectors are
+//     bit-identical (tests/test_pbvi_gpu.py).  PP2D_PBVI_CUBLAS=1 switches to
+//     the library call (bound at run time with dlopen) as a checker for tests;
+//     nothing else in the library depends on cuBLAS.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -39,6 +47,7 @@
 #include <cublas_v2.h>
 #include <dlfcn.h>
 
+#include "async_copy.cuh"
 #include "fp_exact.cuh"
 #include "pomdp_host.h"
 
@@ -224,6 +233,92 @@ pbvi_gamma_ao_kernel(int H, int W, int n_set, float gamma, int a,
     for (int k = 0; k < 9; ++k)
       if (nidx[k] >= 0) acc = fma_ftz(__ldg(al + nidx[k]), tm[k], acc);
     G[((size_t)o * n_set + i) * HW + s] = mul_ftz(acc, gamma);
+  }
+}
+
+// pbvi:505-513: the one dense contraction of the reference, cublasSgemm(T, N):
+//   R[o][b][i] = sum_s Gamma_ao[o][i][s] * B[b][s]        (n x n x HW, 16 of them)
+// as a hand-written FP32 kernel.  R only feeds the arg-max over i below (which
+// Gamma_ao vector a belief picks); the alpha vectors themselves are gathered
+// from Gamma_ao and never see R.  Definition of the arithmetic (documented
+// because it is NOT cuBLAS's unspecified blocking): every R[o][b][i] is ONE
+// sequential FMA chain over the cells in ascending order, acc = fma(G, B, acc)
+// from +0.  Cells on which every belief of the set is +0 (kidx lists the
+// others) are skipped, which leaves the chain's value unchanged.
+// Both operands are K-contiguous ("TN"); tiles are transposed on the way into
+// shared memory with 4-byte cp.async (16 consecutive lanes = one 64-byte row
+// segment).  CTA tile 128 x 128, 256 threads, 8 x 8 accumulators per thread,
+// K chunks of 16 double-buffered.
+constexpr int kGmM = 128, kGmN = 128, kGmK = 16, kGmPad = 4;
+
+__global__ void __launch_bounds__(256, 2)
+pbvi_sgemm_tn_kernel(int n, int HW, int K, const int* __restrict__ kidx,
+                     const float* __restrict__ G, const float* __restrict__ B,
+                     float* __restrict__ R) {
+  __shared__ __align__(16) float sg[2][kGmK][kGmM + kGmPad];
+  __shared__ __align__(16) float sb[2][kGmK][kGmN + kGmPad];
+  const int o = blockIdx.z;
+  const int i0 = blockIdx.x * kGmM, b0 = blockIdx.y * kGmN;
+  const float* Go = G + (size_t)o * n * HW;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  auto load_tiles = [&](int buf, int k0) {
+#pragma unroll
+    for (int e = 0; e < (kGmK * kGmM) / 256; ++e) {
+      const int idx = tid + e * 256;
+      const int kk = idx % kGmK, row = idx / kGmK;
+      const int s = __ldg(kidx + min(k0 + kk, K - 1));     // clamped rows are never accumulated
+      cp_async<4>((uint32_t)__cvta_generic_to_shared(&sg[buf][kk][row]),
+                  Go + (size_t)min(i0 + row, n - 1) * HW + s);
+      cp_async<4>((uint32_t)__cvta_generic_to_shared(&sb[buf][kk][row]),
+                  B + (size_t)min(b0 + row, n - 1) * HW + s);
+    }
+    cp_async_commit();
+  };
+
+  const int nchunks = (K + kGmK - 1) / kGmK;
+  load_tiles(0, 0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunks) {
+      load_tiles(buf ^ 1, (c + 1) * kGmK);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int kend = min(kGmK, K - c * kGmK);
+#pragma unroll 4
+    for (int kk = 0; kk < kend; ++kk) {
+      const float4 g0 = *reinterpret_cast<const float4*>(&sg[buf][kk][tx * 4]);
+      const float4 g1 = *reinterpret_cast<const float4*>(&sg[buf][kk][64 + tx * 4]);
+      const float4 q0 = *reinterpret_cast<const float4*>(&sb[buf][kk][ty * 4]);
+      const float4 q1 = *reinterpret_cast<const float4*>(&sb[buf][kk][64 + ty * 4]);
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(gv[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* Ro = R + (size_t)o * n * n;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = b0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + (j - 4));
+    if (b >= n) continue;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int a = i0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
+      if (a < n) Ro[(size_t)b * n + a] = acc[i][j];
+    }
   }
 }
 
@@ -428,10 +523,20 @@ uint32_t reference_backup_iterations(float gamma) {
 // backupAlphaVectors (pbvi:344-641) on device buffers: d_B [n][HW] beliefs,
 // d_alphas [n][HW] (in: start vectors, out: result), d_actions [n].
 int backup_on_device(pp2d_pomdp* h, int n, const float* d_B, float* d_alphas,
-                     uint8_t* d_actions, uint32_t iterations) {
-  if (!g_cublas.load())
+                     uint8_t* d_actions, uint32_t iterations,
+                     bool beliefs_zero_on_dead_cells) {
+  // PP2D_PBVI_CUBLAS=1 (tests only): the reference's library call instead of
+  // pbvi_sgemm_tn_kernel, to show that both pick the same Gamma_ao vectors.
+  const char* cb_env = getenv("PP2D_PBVI_CUBLAS");
+  const bool use_cublas = cb_env && atoi(cb_env) != 0;
+  if (use_cublas && !g_cublas.load())
     return fail(PP2D_ERR_STATE, "cuBLAS (libcublas.so.12) could not be loaded: %s", dlerror());
   const int HW = h->HW;
+  // cells on which some belief of the set may be non-zero (the set grows from a
+  // belief by Bayes updates, so normally the live cells)
+  const bool dense = !h->skip_dead || !beliefs_zero_on_dead_cells;
+  const int* kidx = dense ? h->d_kidx_all : h->d_kidx;
+  const int K = dense ? HW : h->K;
   float *G = nullptr, *GA = nullptr, *R = nullptr, *rew = nullptr;
   int* idx = nullptr;
   cublasHandle_t cb = nullptr;
@@ -441,10 +546,12 @@ int backup_on_device(pp2d_pomdp* h, int n, const float* d_B, float* d_alphas,
     PP2D_CUDA(cudaMalloc(&R, (size_t)16 * n * n * sizeof(float)));
     PP2D_CUDA(cudaMalloc(&rew, (size_t)9 * n * sizeof(float)));
     PP2D_CUDA(cudaMalloc(&idx, (size_t)16 * n * sizeof(int)));
-    if (g_cublas.create(&cb) != CUBLAS_STATUS_SUCCESS)
-      return fail(PP2D_ERR_CUDA, "cublasCreate failed");
-    if (g_cublas.set_stream(cb, h->stream) != CUBLAS_STATUS_SUCCESS)
-      return fail(PP2D_ERR_CUDA, "cublasSetStream failed");
+    if (use_cublas) {
+      if (g_cublas.create(&cb) != CUBLAS_STATUS_SUCCESS)
+        return fail(PP2D_ERR_CUDA, "cublasCreate failed");
+      if (g_cublas.set_stream(cb, h->stream) != CUBLAS_STATUS_SUCCESS)
+        return fail(PP2D_ERR_CUDA, "cublasSetStream failed");
+    }
     const float one = 1.0f, zero = 0.0f;
     for (uint32_t it = 0; it < iterations; ++it) {
       for (int a = 0; a < 9; ++a) {
@@ -452,12 +559,18 @@ int backup_on_device(pp2d_pomdp* h, int n, const float* d_B, float* d_alphas,
         pbvi_gamma_ao_kernel<<<ggrid, 128, 0, h->stream>>>(h->H, h->W, n, h->gamma, a, h->d_tp,
                                                            h->d_mp, d_alphas, G);
         count_launch();
-        for (int o = 0; o < 16; ++o) {
-          // pbvi:505-513, same call: C(n x n, col-major) = Gamma_ao^T * B
-          if (g_cublas.sgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, n, n, HW, &one,
-                             G + (size_t)o * n * HW, HW, d_B, HW, &zero,
-                             R + (size_t)o * n * n, n) != CUBLAS_STATUS_SUCCESS)
-            return fail(PP2D_ERR_CUDA, "cublasSgemm failed");
+        if (use_cublas) {
+          for (int o = 0; o < 16; ++o) {
+            // pbvi:505-513, same call: C(n x n, col-major) = Gamma_ao^T * B
+            if (g_cublas.sgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, n, n, HW, &one,
+                               G + (size_t)o * n * HW, HW, d_B, HW, &zero,
+                               R + (size_t)o * n * n, n) != CUBLAS_STATUS_SUCCESS)
+              return fail(PP2D_ERR_CUDA, "cublasSgemm failed");
+          }
+        } else {
+          dim3 mgrid((n + kGmM - 1) / kGmM, (n + kGmN - 1) / kGmN, 16);
+          pbvi_sgemm_tn_kernel<<<mgrid, 256, 0, h->stream>>>(n, HW, K, kidx, G, d_B, R);
+          count_launch();
         }
         pbvi_argmax_kernel<<<(16 * n + 3) / 4, 128, 0, h->stream>>>(n, 16 * n, R, idx);
         count_launch();
@@ -518,7 +631,10 @@ int pp2d_pomdp_backup_alphas(pp2d_pomdp* h, const float* belief_set, uint32_t n,
     PP2D_CUDA(cudaMemcpyAsync(d_B, belief_set, bytes, cudaMemcpyHostToDevice, h->stream));
     PP2D_CUDA(cudaMemsetAsync(d_al, 0, bytes, h->stream));     // pbvi:658-659
     PP2D_CUDA(cudaMemsetAsync(d_ac, 0, n, h->stream));
-    PP2D_TRY(backup_on_device(h, (int)n, d_B, d_al, d_ac, iterations));
+    bool zero = true;
+    for (uint32_t i = 0; i < n && zero; ++i)
+      zero = zero_on_dead_cells(h, belief_set + (size_t)i * h->HW);
+    PP2D_TRY(backup_on_device(h, (int)n, d_B, d_al, d_ac, iterations, zero));
     PP2D_CUDA(cudaMemcpyAsync(alphas, d_al, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (actions)
       PP2D_CUDA(cudaMemcpyAsync(actions, d_ac, n, cudaMemcpyDeviceToHost, h->stream));
@@ -547,7 +663,9 @@ int pp2d_pomdp_solve_pbvi(pp2d_pomdp* h, const float* initial_belief, uint32_t n
     PP2D_TRY(launch_gather(h, set, d_B));
     PP2D_CUDA(cudaMemsetAsync(d_al, 0, bytes, h->stream));
     PP2D_CUDA(cudaMemsetAsync(d_ac, 0, n, h->stream));
-    PP2D_TRY(backup_on_device(h, (int)n, d_B, d_al, d_ac, iterations));
+    // every belief of the set descends from initial_belief by Bayes updates
+    PP2D_TRY(backup_on_device(h, (int)n, d_B, d_al, d_ac, iterations,
+                              zero_on_dead_cells(h, initial_belief)));
     if (belief_set)
       PP2D_CUDA(cudaMemcpyAsync(belief_set, d_B, bytes, cudaMemcpyDeviceToHost, h->stream));
     PP2D_CUDA(cudaMemcpyAsync(alphas, d_al, bytes, cudaMemcpyDeviceToHost, h->stream));

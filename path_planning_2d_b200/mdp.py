@@ -151,6 +151,14 @@ class MdpPathPlanning2d:
             self.optimal_action = a.reshape(self.rows, self.map_width)
         return self.optimal_cost, self.optimal_action
 
+    def download_begin(self, cost_ptr, action_ptr):
+        """Asynchronous download into caller-owned (page-locked) host memory given
+        by raw addresses (either may be None); pair with download_wait()."""
+        _lib.check(self._lib.pp2d_mdp_download_begin(self._h, cost_ptr, action_ptr))
+
+    def download_wait(self):
+        _lib.check(self._lib.pp2d_mdp_download_wait(self._h))
+
     def initialize(self):
         """initialize() minus ROS: solve and download (path_planning_2d.cu:72-140)."""
         sweeps, residuals = self.valueIteration()

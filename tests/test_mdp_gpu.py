@@ -351,6 +351,34 @@ def test_full_size_16384_row_shards_equal_the_unsharded_grid():
     assert np.all(action[grid == 1] == 0)
 
 
+def test_asynchronous_download_overlaps_the_next_solve():
+    """pp2d_mdp_download_begin snapshots the solution; the handle is reset and
+    swept on another map right away; _wait then delivers the FIRST solution.
+    Also on a multi-shard handle."""
+    import torch
+    grid, goal = cases.synthetic_map(301, 257, 0.2, seed=41)
+    grid2, goal2 = cases.synthetic_map(301, 257, 0.35, seed=42, goal=(9, 200))
+    ora = oracle_py.OracleMdp(grid, goal, cases.GAMMA)
+    ora.sweeps(37)
+    ora2 = oracle_py.OracleMdp(grid2, goal2, cases.GAMMA)
+    ora2.sweeps(12)
+    for devices in (None, [0, 0, 0]):
+        cost = torch.empty(grid.size, dtype=torch.float32).pin_memory()
+        act = torch.empty(grid.size, dtype=torch.uint8).pin_memory()
+        cost2 = torch.empty(grid.size, dtype=torch.float32).pin_memory()
+        with MdpPathPlanning2d(grid, goal, cases.GAMMA, devices=devices) as mdp:
+            mdp.sweeps(37)
+            mdp.download_begin(cost.data_ptr(), act.data_ptr())
+            mdp.reset(grid2, goal2)
+            mdp.sweeps(12)
+            mdp.download_begin(cost2.data_ptr(), None)      # second one queues behind the first
+            mdp.download_wait()
+            assert np.array_equal(_bits(cost.numpy().reshape(grid.shape)), _bits(ora.cost))
+            assert np.array_equal(act.numpy().reshape(grid.shape), ora.act)
+            assert np.array_equal(_bits(cost2.numpy().reshape(grid.shape)), _bits(ora2.cost))
+            _assert_same(mdp, ora2, "after the overlapped downloads")
+
+
 def test_reset_reuses_the_handle():
     grid, goal = cases.synthetic_map(97, 143, 0.25, seed=21)
     grid2, goal2 = cases.synthetic_map(97, 143, 0.1, seed=22, goal=(5, 90))

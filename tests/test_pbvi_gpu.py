@@ -68,6 +68,33 @@ def test_pbvi_bundled_map_500_beliefs_equals_reference_solver():
     assert np.array_equal(ac, g["pbvi_actions"])
 
 
+@pytest.mark.parametrize("name", ["pbvi_ref_map_10x10_g0.95_n60"])
+def test_handwritten_gemm_picks_the_same_vectors_as_the_library_call(monkeypatch, name):
+    """pbvi_sgemm_tn_kernel (the product) vs the reference's cublasSgemm call
+    (PP2D_PBVI_CUBLAS=1, checker only): the contraction only feeds an arg-max,
+    so both must end with bit-identical alpha vectors and actions; a belief
+    with mass on an occupied cell switches the kernel to the dense inner
+    dimension and must still agree."""
+    g = np.load(os.path.join(cases.GOLDEN, name + ".npz"))
+    goal = tuple(int(v) for v in g["goal"])
+    bs = g["belief_set"].copy()
+    res = {}
+    for variant in ("kernel", "cublas", "kernel_dense"):
+        monkeypatch.setenv("PP2D_PBVI_CUBLAS", "1" if variant == "cublas" else "0")
+        with PomdpPathPlanning2d(g["grid"], goal, float(g["gamma"])) as p:
+            if variant == "kernel_dense":
+                b2 = bs.copy()
+                occ = np.flatnonzero(g["grid"].reshape(-1) == 1)[0]
+                b2[3, occ] = np.float32(0.0)          # still zero: same problem ...
+                b2[3, occ] = np.float32(-0.0)         # ... but -0 forces the dense path
+                res[variant] = p.backupAlphaVectors(b2, iterations=12)
+            else:
+                res[variant] = p.backupAlphaVectors(bs, iterations=12)
+    for variant in ("cublas", "kernel_dense"):
+        assert np.array_equal(bits(res[variant][0]), bits(res["kernel"][0])), variant
+        assert np.array_equal(res[variant][1], res["kernel"][1]), variant
+
+
 def test_pbvi_single_belief_and_other_seed():
     grid, goal = cases.synthetic_map(7, 9, 0.2, seed=4)
     free = (grid.reshape(-1) == 0).astype(np.float32)
