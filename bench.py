@@ -326,8 +326,9 @@ def qv_tree_section(rank, world, with_cpu):
            "offline_solve_seconds": offline_s,
            "config": "sparse_map_100x40, goal (95,34), Gaussian start beliefs "
                      "(sigma 2 cells), 9 FIB + 500 PBVI alpha vectors from the GPU "
-                     "offline solvers (untimed; bit-identical to the reference's, "
-                     "tests/test_pbvi_gpu.py), depth cap 50, 15 expansions, 50 samples "
+                     "offline solvers (untimed; FIB bit-identical to the reference's, PBVI "
+                     "per the contract of DESIGN.md 7a, tests/test_pbvi_gpu.py), depth cap "
+                     "50, 15 expansions, 50 samples "
                      "per Q node; host beliefs in, actions out; queries sharded per "
                      "GPU, no data-path collective",
            "parity": "actions, bounds and tree shapes bit-identical to the oracle and to "
