@@ -373,6 +373,7 @@ struct Sweeper {
   float* pout;               // row written at step y (y for T=1, y-1 for T=2)
   uint8_t* pact;             // action row y (POLICY)
   float *pup, *pdn;          // P2P: this lane's column in the neighbours' ghost rows
+  bool peer_top, peer_bot;   // P2P: this segment feeds the upper / lower neighbour (warp-uniform)
   int yout;                  // P2P: row index of pout
   size_t l1_ahead;           // CW == 1: rows ahead for prefetch.global.L1
   uint32_t ring_j, ring_c;   // CW >= 2: shared addresses of this lane's ring slots
@@ -472,13 +473,17 @@ struct Sweeper {
               }
             }
           }
-          if constexpr (PEER) {
-            // The first / last two owned rows are also the neighbours' ghost
-            // rows: written straight into their HBM over NVLink.
-            if (pup != nullptr && yout < kPadRows && !(p.p2p_debug & 2u))
-              store_own<CW>(pup + (size_t)yout * p.pitch, v2);
-            if (pdn != nullptr && yout >= p.H - kPadRows && !(p.p2p_debug & 2u))
-              store_own<CW>(pdn + (size_t)(yout - (p.H - kPadRows)) * p.pitch, v2);
+        }
+        if constexpr (PEER) {
+          // The first / last two owned rows are also the neighbours' ghost
+          // rows: written straight into their HBM over NVLink.  peer_top /
+          // peer_bot and yout are warp-uniform, `valid` only predicates the
+          // store (no divergent region in front of the next shuffle).
+          if (peer_top && yout < kPadRows) {
+            if (valid) store_own<CW>(pup + (size_t)yout * p.pitch, v2);
+          }
+          if (peer_bot && yout >= p.H - kPadRows) {
+            if (valid) store_own<CW>(pdn + (size_t)(yout - (p.H - kPadRows)) * p.pitch, v2);
           }
         }
         if constexpr (POLICY) pact += p.W;
@@ -611,8 +616,10 @@ struct Sweeper {
       const bool top = p.peer_up_out != nullptr && y0 < kPadRows;
       const bool bot = p.peer_down_out != nullptr && y1 > p.H - kPadRows;
       if (top || bot) {
-        pup = top ? p.peer_up_out + col : nullptr;
-        pdn = bot ? p.peer_down_out + col : nullptr;
+        pup = p.peer_up_out + col;       // only dereferenced under peer_top / peer_bot
+        pdn = p.peer_down_out + col;
+        peer_top = top && !(p.p2p_debug & 2u);
+        peer_bot = bot && !(p.p2p_debug & 2u);
         int e0 = y0, e1 = y1;
         const int e = p.edge_rows;
         if (top != bot && y1 - y0 > e) {
@@ -621,12 +628,18 @@ struct Sweeper {
         } else {
           r1 = r0;                     // the whole unit is the edge segment
         }
-        if (lane == 0 && !(p.p2p_debug & 1u)) {
+        if (!(p.p2p_debug & 1u)) {
           // Wait until the neighbour's previous launch has (a) written my
           // ghost rows of this buffer parity and (b) finished reading its own
           // ghost rows that I am about to overwrite; both are implied by its
           // flag, published after ALL its edge segments facing me are done.
+          // Every lane polls (one broadcast transaction per poll) and the
+          // value is taken from lane 0 through a shuffle: the loop exit is
+          // then warp-uniform FOR THE COMPILER, which keeps the marching code
+          // below free of divergence guards (a lane-0-only spin loop cost the
+          // whole kernel its uniformity: 63 -> 82 us per launch).
           const unsigned int want = p.iter - 1;
+#pragma unroll
           for (int side = 0; side < 2; ++side) {
             if (!(side == 0 ? top : bot)) continue;
             const unsigned int* f = p.flags + (side == 0 ? kFlagFromUp : kFlagFromDown);
@@ -637,35 +650,39 @@ struct Sweeper {
             // into an infinite residual and every host entry point that returns
             // results checks it, so the failure cannot pass silently.
             unsigned int spins = 0;
-            while ((int)(ld_acquire_sys(f) - want) < 0) {
-              if (++spins > p.spin_limit) { atomicExch(p.flags + kFlagError, 1u); break; }
+            while (true) {
+              const unsigned int v = __shfl_sync(0xffffffffu, ld_acquire_sys(f), 0);
+              if ((int)(v - want) >= 0) break;
+              if (++spins > p.spin_limit) {
+                if (lane == 0) atomicExch(p.flags + kFlagError, 1u);
+                break;
+              }
               __nanosleep(spins < 64u ? 32u : 256u);
             }
           }
         }
-        __syncwarp();
         march<true>(e0, e1, col);
         // Publish: the last edge segment on each side to finish writes this
-        // launch's number into the neighbour's flag.
-        __syncwarp();
-        if (lane == 0 && !(p.p2p_debug & 4u)) {
-          __threadfence_system();
-          if (top) {
-            const unsigned int c = atomicAdd(p.flags + kFlagCountTop, 1u) + 1u;
-            if (c == p.expect_top) {
+        // launch's number into the neighbour's flag.  (All lanes fence; lane 0
+        // counts; the count comes back through a shuffle so that the decision
+        // is warp-uniform.)
+        if (!(p.p2p_debug & 4u)) {
+          __threadfence_system();        // every lane: its peer stores before the count
+          __syncwarp();                  // ... and all of them before lane 0 counts
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            if (!(side == 0 ? top : bot)) continue;
+            unsigned int c = 0;
+            if (lane == 0)
+              c = atomicAdd(p.flags + (side == 0 ? kFlagCountTop : kFlagCountBot), 1u) + 1u;
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c == (side == 0 ? p.expect_top : p.expect_bot)) {
               __threadfence_system();
-              st_release_sys(p.up_flag_remote, p.iter);
-            }
-          }
-          if (bot) {
-            const unsigned int c = atomicAdd(p.flags + kFlagCountBot, 1u) + 1u;
-            if (c == p.expect_bot) {
-              __threadfence_system();
-              st_release_sys(p.down_flag_remote, p.iter);
+              if (lane == 0)
+                st_release_sys(side == 0 ? p.up_flag_remote : p.down_flag_remote, p.iter);
             }
           }
         }
-        __syncwarp();
       }
     }
     if (r1 > r0) march<false>(r0, r1, col);

@@ -242,15 +242,12 @@ int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows)
 // Live-cell list and compacted bound matrix (see pomdp_host.h).
 int refresh_live_cells(pp2d_pomdp* h) {
   const int HW = h->HW;
-  uint8_t* d_dead = nullptr;
-  PP2D_CUDA(cudaMalloc(&d_dead, HW));
-  pomdp_dead_cells_kernel<<<(HW + 127) / 128, 128, 0, h->stream>>>(h->H, h->W, h->d_tp, d_dead);
+  if (!h->d_dead) PP2D_CUDA(cudaMalloc(&h->d_dead, HW));
+  pomdp_dead_cells_kernel<<<(HW + 127) / 128, 128, 0, h->stream>>>(h->H, h->W, h->d_tp, h->d_dead);
   count_launch();
   h->dead.assign(HW, 0);
-  cudaError_t e = cudaMemcpyAsync(h->dead.data(), d_dead, HW, cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(d_dead);
-  PP2D_CUDA(e);
+  PP2D_CUDA(cudaMemcpyAsync(h->dead.data(), h->d_dead, HW, cudaMemcpyDeviceToHost, h->stream));
+  PP2D_CUDA(cudaStreamSynchronize(h->stream));
   std::vector<int> live, all(HW);
   for (int s = 0; s < HW; ++s) {
     all[s] = s;
@@ -292,10 +289,10 @@ namespace {
 
 // The inner dimension of the sequential products of one launch: the live
 // cells, or all cells when some belief involved may be non-zero elsewhere.
-struct InnerDim { const int* kidx; int K; const float* alpha; };
+struct InnerDim { const int* kidx; int K; const float* alpha; const uint8_t* dead; };
 InnerDim inner_dim(const pp2d_pomdp* h, bool dense) {
-  if (dense || !h->skip_dead) return {h->d_kidx_all, h->HW, h->d_alpha};
-  return {h->d_kidx, h->K, h->d_alpha_live};
+  if (dense || !h->skip_dead) return {h->d_kidx_all, h->HW, h->d_alpha, nullptr};
+  return {h->d_kidx, h->K, h->d_alpha_live, h->d_dead};
 }
 
 // Host threads for the per-tree work of a batch: pp2d_set_host_threads, else
@@ -630,20 +627,20 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
   PP2D_TRY(c.d_pred.ensure((size_t)HW * ngp));
   PP2D_CUDA(cudaMemcpyAsync(c.d_kgroup.p, c.kgroup.p, nk * sizeof(int), cudaMemcpyHostToDevice,
                             c.stream));
-  dim3 bgrid((ng + 31) / 32, (HW + 7) / 8);
-  pomdp_predict_kernel<<<bgrid, 256, 0, c.stream>>>(h->H, h->W, h->cap, ngp, h->d_tp,
-                                                     c.d_items.p, c.d_gfirst.p, ng, h->d_bel,
-                                                     c.d_pred.p);
+  const InnerDim in = inner_dim(h, c.dense);
+  dim3 bgrid((ng + 31) / 32, (in.K + 7) / 8);
+  pomdp_predict_kernel<<<bgrid, 256, 0, c.stream>>>(h->H, h->W, in.K, in.kidx, h->cap, ngp,
+                                                     h->d_tp, c.d_items.p, c.d_gfirst.p, ng,
+                                                     h->d_bel, c.d_pred.p);
   count_launch();
   h->n_bayes += nk;
-  const InnerDim in = inner_dim(h, c.dense);
   pomdp_child_sum_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(
       in.K, in.kidx, ngp, h->d_mp, c.d_items.p, c.d_kgroup.p, nk, c.d_pred.p, c.d_sums.p);
   count_launch();
   dim3 sgrid((nk + 31) / 32, (HW + 7) / 8);
-  pomdp_child_write_kernel<<<sgrid, 256, 0, c.stream>>>(HW, h->cap, ngp, h->d_mp, c.d_items.p,
-                                                         c.d_kgroup.p, nk, c.d_pred.p,
-                                                         c.d_sums.p, h->d_bel);
+  pomdp_child_write_kernel<<<sgrid, 256, 0, c.stream>>>(HW, h->cap, ngp, h->d_mp, in.dead,
+                                                         c.d_items.p, c.d_kgroup.p, nk,
+                                                         c.d_pred.p, c.d_sums.p, h->d_bel);
   count_launch();
   dim3 vgrid((nk + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
   pomdp_values_kernel<<<vgrid, 256, 0, c.stream>>>(in.K, in.kidx, h->cap, h->ld, h->ncol,
@@ -789,7 +786,7 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   if (!h) return;
   cudaFree(h->d_map); cudaFree(h->d_tp); cudaFree(h->d_mp); cudaFree(h->d_sr);
   cudaFree(h->d_uniforms); cudaFree(h->d_alpha); cudaFree(h->d_bel);
-  cudaFree(h->d_kidx); cudaFree(h->d_kidx_all); cudaFree(h->d_alpha_live);
+  cudaFree(h->d_kidx); cudaFree(h->d_kidx_all); cudaFree(h->d_alpha_live); cudaFree(h->d_dead);
   h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();

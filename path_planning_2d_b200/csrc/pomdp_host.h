@@ -103,6 +103,7 @@ struct pp2d_pomdp {
   std::vector<float> alpha_host;           // dense bound matrix [HW][ld] as uploaded
   int* d_kidx = nullptr;
   int* d_kidx_all = nullptr;
+  uint8_t* d_dead = nullptr;               // device copy of the mask
   float* d_alpha_live = nullptr;
   int K = 0;
   bool skip_dead = true;                   // PP2D_POMDP_DENSE=1 turns the skipping off

@@ -172,12 +172,18 @@ pomdp_bayes_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
 // IEEE division), so the bits are the same; the traffic drops from
 // 4 x |children| to 2 x |Q nodes| + 1 x |children| belief-sized passes.
 __global__ void __launch_bounds__(256)
-pomdp_predict_kernel(int H, int W, int cap, int ngp, const float* __restrict__ trans_prob,
+pomdp_predict_kernel(int H, int W, int K, const int* __restrict__ kidx, int cap, int ngp,
+                     const float* __restrict__ trans_prob,
                      const BayesItem* __restrict__ items, const int* __restrict__ first,
                      int n_groups, const float* __restrict__ bel, float* __restrict__ pred) {
+  // Only the K target cells listed in kidx are predicted: on the others (cells
+  // no mass can enter, belief +0) the prediction is +0 and nobody reads it --
+  // pomdp_child_sum_kernel walks the same list and pomdp_child_write_kernel
+  // writes those cells without it.  kidx = identity: every cell.
   const int g = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int cell = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (g >= n_groups || cell >= H * W) return;
+  const int kc = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (g >= n_groups || kc >= K) return;
+  const int cell = __ldg(kidx + kc);
   const BayesItem it = items[first[g]];
   const int x = cell % W, y = cell / W;
   float p = 0.0f;
@@ -227,9 +233,12 @@ pomdp_child_sum_kernel(int K, const int* __restrict__ kidx, int ngp,
   sums[k] = sum;
 }
 
-// child belief = (pred * L) / sum, written once into its pool column.
+// child belief = (pred * L) / sum, written once into its pool column.  dead
+// (may be NULL = no cell is skipped): cells whose prediction is +0 by
+// construction and was not computed: (+0 * L) / sum.
 __global__ void __launch_bounds__(256)
 pomdp_child_write_kernel(int HW, int cap, int ngp, const float* __restrict__ meas_prob,
+                         const uint8_t* __restrict__ dead,
                          const BayesItem* __restrict__ items, const int* __restrict__ kgroup,
                          int n, const float* __restrict__ pred, const float* __restrict__ sums,
                          float* __restrict__ bel) {
@@ -237,8 +246,8 @@ pomdp_child_write_kernel(int HW, int cap, int ngp, const float* __restrict__ mea
   const int cell = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (k >= n || cell >= HW) return;
   const BayesItem it = items[k];
-  const float v = mul_ftz(pred[(size_t)cell * ngp + kgroup[k]],
-                          __ldg(meas_prob + 16 * (size_t)cell + it.obs));
+  const float p = (dead != nullptr && dead[cell]) ? 0.0f : pred[(size_t)cell * ngp + kgroup[k]];
+  const float v = mul_ftz(p, __ldg(meas_prob + 16 * (size_t)cell + it.obs));
   bel[(size_t)cell * cap + it.dst] = __fdiv_rn(v, sums[k]);
 }
 
