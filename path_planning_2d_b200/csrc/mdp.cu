@@ -162,6 +162,7 @@ struct pp2d_mdp {
   void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned int p2p_iter = 0, p2p_expect_top = 0, p2p_expect_bot = 0;
   int p2p_debug = 0, p2p_edge_rows = 16;
+  int p2p_edge_short = 20;         // rows the boundary row blocks are shorter (hand-shake cost)
   unsigned int p2p_spin_limit = 1u << 24;   // polls (32-256 ns apart) before kFlagError
   // ghost-row contract of a shard without peer-to-peer rows: sweeps that may
   // still run before the caller has to refresh the ghost rows (pp2d_mdp_halo)
@@ -183,7 +184,7 @@ struct pp2d_mdp {
   struct LaunchCache {
     bool valid = false;
     int ctas_per_sm = 0;
-    int y_rows = 0, lin_len = 0, rows_per_unit = 0, n_units = 0;
+    int y_rows = 0, lin_len = 0, rows_per_unit = 0, n_units = 0, rows_edge = 0, rows_inner = 0;
     unsigned int top_segs = 0, bot_segs = 0;
   } launch_cache[2][3][2][2];      // [T-1][CW: 1,2,4 -> 0,1,2][POLICY][P2P]
   // ---- single-process multi-GPU container (pp2d_mdp_create_multi) ----------
@@ -316,6 +317,8 @@ static int launch_sweep(pp2d_mdp* h) {
     if (lc.valid && lc.y_rows == rows) {
       top_segs = lc.top_segs;
       bot_segs = lc.bot_segs;
+      p.rows_edge = lc.rows_edge;
+      p.rows_inner = lc.rows_inner;
     } else if (p.lin_len > 0) {
       const long long R = rows, total = (long long)p.n_strips * R;
       for (long long u = 0; u < p.n_units; ++u) {
@@ -329,12 +332,28 @@ static int launch_sweep(pp2d_mdp* h) {
       }
     } else {
       const int n_rb = (rows + p.rows_per_unit - 1) / p.rows_per_unit;
+      // Edge blocks pay for the hand-shake: make them shorter (same formulas as
+      // Sweeper::run).  Needs interior blocks to take up the rows.
+      p.rows_edge = p.rows_inner = 0;
+      const int m = n_rb - 2, re = p.rows_per_unit - h->p2p_edge_short;
+      if (h->p2p_edge_short > 0 && m >= 1 && re > m + 2 * kPadRows + 8 && 2 * re < rows) {
+        p.rows_edge = re;
+        p.rows_inner = (rows - 2 * re + m - 1) / m;
+      }
       for (int rb = 0; rb < n_rb; ++rb) {
-        const int y0 = rb * p.rows_per_unit;
-        for (int k = 0; k < p.n_strips; ++k)
-          count(y0, std::min(y0 + p.rows_per_unit, (int)h->H));
+        int y0, y1;
+        if (p.rows_edge > 0) {
+          y0 = rb == 0 ? 0 : p.rows_edge + (rb - 1) * p.rows_inner;
+          y1 = std::min(p.rows_edge + rb * p.rows_inner, (int)h->H);
+        } else {
+          y0 = rb * p.rows_per_unit;
+          y1 = std::min(y0 + p.rows_per_unit, (int)h->H);
+        }
+        for (int k = 0; k < p.n_strips; ++k) count(y0, y1);
       }
     }
+    lc.rows_edge = p.rows_edge;
+    lc.rows_inner = p.rows_inner;
     lc.top_segs = top_segs;
     lc.bot_segs = bot_segs;
     h->p2p_iter += 1;
@@ -512,6 +531,7 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
     h->p2p_spin_limit = lim > 0 ? (unsigned int)lim : 1u;
   }
   if (h->p2p_edge_rows < kPadRows) h->p2p_edge_rows = kPadRows;
+  h->p2p_edge_short = env_int("PP2D_P2P_EDGE_SHORT", 20);
   if (h->waves < 1) h->waves = 1;
   if (h->prefetch_rows < kPrefetch) h->prefetch_rows = kPrefetch;
   if (h->prefetch_rows > kSlackRows) h->prefetch_rows = kSlackRows;

@@ -117,6 +117,11 @@ struct SweepParams {
   int edge_rows;                        // rows of a boundary unit processed first
   int lin_len;           // LIN kernels: units are runs of lin_len rows of the strip-major sequence
   unsigned int spin_limit;  // P2P: polls of a neighbour flag before giving up (kFlagError)
+  // P2P row-block units: the first and last row block of a strip also do the
+  // hand-shake (system fences wait for NVLink write acknowledgements), so they
+  // get rows_edge < rows_per_unit rows and the blocks between them rows_inner;
+  // rows_edge == 0: all blocks have rows_per_unit rows.
+  int rows_edge, rows_inner;
 };
 
 // Flag block of a shard (uint32 each, cudaMalloc'ed, IPC-shared).
@@ -588,8 +593,14 @@ struct Sweeper {
     } else {
       const int k = unit % p.n_strips;
       const int rb = unit / p.n_strips;
-      const int y0 = p.y_begin + rb * p.rows_per_unit;      // rows [y0, y1)
-      const int y1 = min(y0 + p.rows_per_unit, p.y_end);
+      int y0, y1;                                             // rows [y0, y1)
+      if (P2P && p.rows_edge > 0) {
+        y0 = rb == 0 ? p.y_begin : p.y_begin + p.rows_edge + (rb - 1) * p.rows_inner;
+        y1 = min(p.y_begin + p.rows_edge + rb * p.rows_inner, p.y_end);
+      } else {
+        y0 = p.y_begin + rb * p.rows_per_unit;
+        y1 = min(y0 + p.rows_per_unit, p.y_end);
+      }
       run_segment(k, y0, y1, lane);
     }
   }

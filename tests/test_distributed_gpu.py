@@ -89,3 +89,26 @@ def test_single_process_multi_gpu_handle_matches_the_oracle(n):
         assert sweeps == m and np.array_equal(residuals, res)
         assert np.array_equal(mdp.optimal_cost.view(np.uint32), J.view(np.uint32))
         assert np.array_equal(mdp.optimal_action, A)
+
+
+@pytest.mark.parametrize("short", [0, 12, 40])
+def test_shorter_boundary_row_blocks_keep_the_bits(monkeypatch, short):
+    """The row blocks that do the peer-to-peer hand-shake are made shorter than
+    the others (PP2D_P2P_EDGE_SHORT) so that their extra work does not delay
+    the launch; the partition of the rows must not change a bit."""
+    from path_planning_2d_b200 import MdpPathPlanning2d
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("PP2D_MDP_ROWS_PER_UNIT", "100")
+    monkeypatch.setenv("PP2D_MDP_LINEAR_UNITS", "0")
+    monkeypatch.setenv("PP2D_P2P_EDGE_SHORT", str(short))
+    grid, goal = cases.synthetic_map(3000, 300, 0.2, seed=78)
+    ora = oracle_py.OracleMdp(grid, goal, cases.GAMMA)
+    with MdpPathPlanning2d(grid, goal, cases.GAMMA, devices=2) as mdp:
+        assert mdp.peer_to_peer
+        for k, wa in [(6, False), (20, True), (3, True)]:
+            mdp.sweeps(k, wa)
+            ora.sweeps(k)
+        cost, action = mdp.download()
+    assert np.array_equal(cost.view(np.uint32), ora.cost.view(np.uint32))
+    assert np.array_equal(action, ora.act)
