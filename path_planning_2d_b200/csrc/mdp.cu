@@ -184,7 +184,9 @@ struct pp2d_mdp {
   struct LaunchCache {
     bool valid = false;
     int ctas_per_sm = 0;
-    int y_rows = 0, lin_len = 0, rows_per_unit = 0, n_units = 0, rows_edge = 0, rows_inner = 0;
+    int y_rows = 0, lin_len = 0, rows_per_unit = 0, n_units = 0;
+    int* d_unit_lo = nullptr;            // cost-balanced unit boundaries (P2P LIN kernels)
+    std::vector<int> unit_lo_host;
     unsigned int top_segs = 0, bot_segs = 0;
   } launch_cache[2][3][2][2];      // [T-1][CW: 1,2,4 -> 0,1,2][POLICY][P2P]
   // ---- single-process multi-GPU container (pp2d_mdp_create_multi) ----------
@@ -265,6 +267,7 @@ static int launch_sweep(pp2d_mdp* h) {
     p.lin_len = lc.lin_len;
     p.rows_per_unit = lc.rows_per_unit;
     p.n_units = lc.n_units;
+    p.unit_lo = lc.d_unit_lo;
   } else if (rpu <= 0) {
     // Launch sized to exactly `waves` full waves of resident CTAs (one unit
     // per warp); the units are equal runs of the strip-major row sequence.
@@ -296,6 +299,55 @@ static int launch_sweep(pp2d_mdp* h) {
       p.rows_per_unit = (int)rpu_blocks;
       p.n_units = p.n_strips * (int)((rows + rpu_blocks - 1) / rpu_blocks);
     }
+    if (P2P && kHasLin && h->p2p_edge_short > 0 && h->linear_units != 0 && rows >= 64) {
+      // Cost-balanced units for the peer-to-peer kernels: rows cost 1, every
+      // segment start ~3 rows of pipeline priming, every hand-shake (a segment
+      // that touches the first / last two rows of a strip next to a neighbour)
+      // p2p_edge_short rows.  Smallest cost target that fits the warp slots.
+      const bool up = h->up_j[0] != nullptr, down = h->down_j[0] != nullptr;
+      const double c_seg = 3.0, c_edge = (double)h->p2p_edge_short;
+      std::vector<int>& lo_out = lc.unit_lo_host;
+      auto build = [&](double target) -> long long {
+        lo_out.clear();
+        lo_out.push_back(0);
+        double acc = 0.0;
+        for (int k = 0; k < p.n_strips; ++k)
+          for (int y = 0; y < rows; ++y) {
+            double c = 1.0;
+            if (y == 0 && up) c += c_edge;
+            if (y == rows - 1 && down) c += c_edge;
+            const bool may_cut = y != 1 && y != rows - 1;     // both edge rows stay together
+            if (acc > 0.0 && may_cut && acc + c + (y == 0 ? c_seg : 0.0) > target) {
+              lo_out.push_back(k * rows + y);
+              acc = 0.0;
+            }
+            if (acc == 0.0 || y == 0) c += c_seg;
+            acc += c;
+          }
+        lo_out.push_back(p.n_strips * rows);
+        return (long long)lo_out.size() - 1;
+      };
+      double lo_t = (double)total / (double)slots, hi_t = 4.0 * lo_t + 4.0 * (c_edge + c_seg) + 16.0;
+      for (int it = 0; it < 24; ++it) {
+        const double mid = 0.5 * (lo_t + hi_t);
+        if (build(mid) <= slots) hi_t = mid; else lo_t = mid;
+      }
+      const long long nu = build(hi_t);
+      if (nu <= slots) {
+        if (lc.d_unit_lo) cudaFree(lc.d_unit_lo);
+        lc.d_unit_lo = nullptr;
+        PP2D_CUDA(cudaMalloc(&lc.d_unit_lo, lo_out.size() * sizeof(int)));
+        PP2D_CUDA(cudaMemcpy(lc.d_unit_lo, lo_out.data(), lo_out.size() * sizeof(int),
+                             cudaMemcpyHostToDevice));
+        p.unit_lo = lc.d_unit_lo;
+        p.n_units = (int)nu;
+        int longest = 1;
+        for (size_t u = 0; u + 1 < lo_out.size(); ++u)
+          longest = std::max(longest, lo_out[u + 1] - lo_out[u]);
+        p.lin_len = longest;              // > 0 selects the LIN instantiation
+        p.rows_per_unit = longest;
+      }
+    }
   } else {
     p.rows_per_unit = rpu;
     const int n_rb = (rows + rpu - 1) / rpu;
@@ -317,8 +369,17 @@ static int launch_sweep(pp2d_mdp* h) {
     if (lc.valid && lc.y_rows == rows) {
       top_segs = lc.top_segs;
       bot_segs = lc.bot_segs;
-      p.rows_edge = lc.rows_edge;
-      p.rows_inner = lc.rows_inner;
+    } else if (p.unit_lo != nullptr) {
+      const long long R = rows;
+      for (int u = 0; u < p.n_units; ++u) {
+        long long lo = lc.unit_lo_host[u];
+        const long long hi = lc.unit_lo_host[u + 1];
+        while (lo < hi) {
+          const long long k = lo / R, a = lo - k * R, b = std::min(R, a + (hi - lo));
+          count(p.y_begin + (int)a, p.y_begin + (int)b);
+          lo += b - a;
+        }
+      }
     } else if (p.lin_len > 0) {
       const long long R = rows, total = (long long)p.n_strips * R;
       for (long long u = 0; u < p.n_units; ++u) {
@@ -332,28 +393,12 @@ static int launch_sweep(pp2d_mdp* h) {
       }
     } else {
       const int n_rb = (rows + p.rows_per_unit - 1) / p.rows_per_unit;
-      // Edge blocks pay for the hand-shake: make them shorter (same formulas as
-      // Sweeper::run).  Needs interior blocks to take up the rows.
-      p.rows_edge = p.rows_inner = 0;
-      const int m = n_rb - 2, re = p.rows_per_unit - h->p2p_edge_short;
-      if (h->p2p_edge_short > 0 && m >= 1 && re > m + 2 * kPadRows + 8 && 2 * re < rows) {
-        p.rows_edge = re;
-        p.rows_inner = (rows - 2 * re + m - 1) / m;
-      }
       for (int rb = 0; rb < n_rb; ++rb) {
-        int y0, y1;
-        if (p.rows_edge > 0) {
-          y0 = rb == 0 ? 0 : p.rows_edge + (rb - 1) * p.rows_inner;
-          y1 = std::min(p.rows_edge + rb * p.rows_inner, (int)h->H);
-        } else {
-          y0 = rb * p.rows_per_unit;
-          y1 = std::min(y0 + p.rows_per_unit, (int)h->H);
-        }
-        for (int k = 0; k < p.n_strips; ++k) count(y0, y1);
+        const int y0 = rb * p.rows_per_unit;
+        for (int k = 0; k < p.n_strips; ++k)
+          count(y0, std::min(y0 + p.rows_per_unit, (int)h->H));
       }
     }
-    lc.rows_edge = p.rows_edge;
-    lc.rows_inner = p.rows_inner;
     lc.top_segs = top_segs;
     lc.bot_segs = bot_segs;
     h->p2p_iter += 1;
@@ -845,6 +890,8 @@ int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
 void pp2d_mdp_destroy(pp2d_mdp* h) {
   if (!h) return;
   if (!h->parts.empty()) multi_destroy(h);
+  for (auto& a : h->launch_cache) for (auto& b : a) for (auto& c : b) for (auto& lc : c)
+    if (lc.d_unit_lo) { cudaFree(lc.d_unit_lo); lc.d_unit_lo = nullptr; }
   if (h->download_pending) cudaEventSynchronize(h->ev_copied);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);

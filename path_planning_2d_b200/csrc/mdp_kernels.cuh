@@ -117,11 +117,12 @@ struct SweepParams {
   int edge_rows;                        // rows of a boundary unit processed first
   int lin_len;           // LIN kernels: units are runs of lin_len rows of the strip-major sequence
   unsigned int spin_limit;  // P2P: polls of a neighbour flag before giving up (kFlagError)
-  // P2P row-block units: the first and last row block of a strip also do the
-  // hand-shake (system fences wait for NVLink write acknowledgements), so they
-  // get rows_edge < rows_per_unit rows and the blocks between them rows_inner;
-  // rows_edge == 0: all blocks have rows_per_unit rows.
-  int rows_edge, rows_inner;
+  // P2P LIN kernels: unit u covers rows [unit_lo[u], unit_lo[u+1]) of the
+  // strip-major sequence.  The host balances COST, not rows: a unit that
+  // touches the first / last two rows of a strip also does the hand-shake
+  // (system fences wait for NVLink write acknowledgements) and gets fewer rows,
+  // so that it does not finish after everybody else.  NULL: runs of lin_len.
+  const int* unit_lo;
 };
 
 // Flag block of a shard (uint32 each, cudaMalloc'ed, IPC-shared).
@@ -581,8 +582,15 @@ struct Sweeper {
         ring_c += lane * (CW * 2);
       }
       const int R = p.y_end - p.y_begin;
-      int lo = unit * p.lin_len;
-      const int hi = min(lo + p.lin_len, p.n_strips * R);
+      int lo, hi;
+      if (P2P && p.unit_lo != nullptr) {
+        // (through lane 0: the compiler must keep seeing warp-uniform bounds)
+        lo = __shfl_sync(0xffffffffu, __ldg(p.unit_lo + unit), 0);
+        hi = __shfl_sync(0xffffffffu, __ldg(p.unit_lo + unit + 1), 0);
+      } else {
+        lo = unit * p.lin_len;
+        hi = min(lo + p.lin_len, p.n_strips * R);
+      }
       while (lo < hi) {
         const int k = lo / R;
         const int a = lo - k * R;
@@ -593,14 +601,8 @@ struct Sweeper {
     } else {
       const int k = unit % p.n_strips;
       const int rb = unit / p.n_strips;
-      int y0, y1;                                             // rows [y0, y1)
-      if (P2P && p.rows_edge > 0) {
-        y0 = rb == 0 ? p.y_begin : p.y_begin + p.rows_edge + (rb - 1) * p.rows_inner;
-        y1 = min(p.y_begin + p.rows_edge + rb * p.rows_inner, p.y_end);
-      } else {
-        y0 = p.y_begin + rb * p.rows_per_unit;
-        y1 = min(y0 + p.rows_per_unit, p.y_end);
-      }
+      const int y0 = p.y_begin + rb * p.rows_per_unit;      // rows [y0, y1)
+      const int y1 = min(y0 + p.rows_per_unit, p.y_end);
       run_segment(k, y0, y1, lane);
     }
   }

@@ -91,18 +91,18 @@ def test_single_process_multi_gpu_handle_matches_the_oracle(n):
         assert np.array_equal(mdp.optimal_action, A)
 
 
-@pytest.mark.parametrize("short", [0, 12, 40])
-def test_shorter_boundary_row_blocks_keep_the_bits(monkeypatch, short):
-    """The row blocks that do the peer-to-peer hand-shake are made shorter than
-    the others (PP2D_P2P_EDGE_SHORT) so that their extra work does not delay
-    the launch; the partition of the rows must not change a bit."""
+@pytest.mark.parametrize("shape,short", [((3000, 300), 0), ((3000, 300), 20), ((3000, 300), 60),
+                                         ((1200, 1000), 20), ((160, 4000), 20)])
+def test_cost_balanced_units_keep_the_bits(monkeypatch, shape, short):
+    """The peer-to-peer kernels cut the strip-major row sequence into units of
+    equal COST (a unit that does the hand-shake gets PP2D_P2P_EDGE_SHORT fewer
+    rows; 0 = equal rows) read from a table; the partition must not change a
+    bit, whatever the shape (many short units, units spanning several strips)."""
     from path_planning_2d_b200 import MdpPathPlanning2d
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    monkeypatch.setenv("PP2D_MDP_ROWS_PER_UNIT", "100")
-    monkeypatch.setenv("PP2D_MDP_LINEAR_UNITS", "0")
     monkeypatch.setenv("PP2D_P2P_EDGE_SHORT", str(short))
-    grid, goal = cases.synthetic_map(3000, 300, 0.2, seed=78)
+    grid, goal = cases.synthetic_map(shape[0], shape[1], 0.2, seed=78)
     ora = oracle_py.OracleMdp(grid, goal, cases.GAMMA)
     with MdpPathPlanning2d(grid, goal, cases.GAMMA, devices=2) as mdp:
         assert mdp.peer_to_peer
