@@ -184,7 +184,7 @@ struct pp2d_mdp {
   struct LaunchCache {
     bool valid = false;
     int ctas_per_sm = 0;
-    int y_rows = 0, lin_len = 0, rows_per_unit = 0, n_units = 0;
+    int y_rows = 0, lin_len = 0, rows_per_unit = 0, n_units = 0, rows_edge = 0, rows_inner = 0;
     int* d_unit_lo = nullptr;            // cost-balanced unit boundaries (P2P LIN kernels)
     std::vector<int> unit_lo_host;
     unsigned int top_segs = 0, bot_segs = 0;
@@ -299,7 +299,7 @@ static int launch_sweep(pp2d_mdp* h) {
       p.rows_per_unit = (int)rpu_blocks;
       p.n_units = p.n_strips * (int)((rows + rpu_blocks - 1) / rpu_blocks);
     }
-    if (P2P && kHasLin && h->p2p_edge_short > 0 && h->linear_units != 0 && rows >= 64) {
+    if (P2P && p.lin_len > 0 && h->p2p_edge_short > 0 && rows >= 64) {
       // Cost-balanced units for the peer-to-peer kernels: rows cost 1, every
       // segment start ~3 rows of pipeline priming, every hand-shake (a segment
       // that touches the first / last two rows of a strip next to a neighbour)
@@ -369,6 +369,8 @@ static int launch_sweep(pp2d_mdp* h) {
     if (lc.valid && lc.y_rows == rows) {
       top_segs = lc.top_segs;
       bot_segs = lc.bot_segs;
+      p.rows_edge = lc.rows_edge;
+      p.rows_inner = lc.rows_inner;
     } else if (p.unit_lo != nullptr) {
       const long long R = rows;
       for (int u = 0; u < p.n_units; ++u) {
@@ -393,12 +395,28 @@ static int launch_sweep(pp2d_mdp* h) {
       }
     } else {
       const int n_rb = (rows + p.rows_per_unit - 1) / p.rows_per_unit;
+      // Edge blocks pay for the hand-shake: make them shorter (same formulas as
+      // Sweeper::run).  Needs interior blocks to take up the rows.
+      p.rows_edge = p.rows_inner = 0;
+      const int m = n_rb - 2, re = p.rows_per_unit - h->p2p_edge_short;
+      if (h->p2p_edge_short > 0 && m >= 1 && re > m + 2 * kPadRows + 8 && 2 * re < rows) {
+        p.rows_edge = re;
+        p.rows_inner = (rows - 2 * re + m - 1) / m;
+      }
       for (int rb = 0; rb < n_rb; ++rb) {
-        const int y0 = rb * p.rows_per_unit;
-        for (int k = 0; k < p.n_strips; ++k)
-          count(y0, std::min(y0 + p.rows_per_unit, (int)h->H));
+        int y0, y1;
+        if (p.rows_edge > 0) {
+          y0 = rb == 0 ? 0 : p.rows_edge + (rb - 1) * p.rows_inner;
+          y1 = std::min(p.rows_edge + rb * p.rows_inner, (int)h->H);
+        } else {
+          y0 = rb * p.rows_per_unit;
+          y1 = std::min(y0 + p.rows_per_unit, (int)h->H);
+        }
+        for (int k = 0; k < p.n_strips; ++k) count(y0, y1);
       }
     }
+    lc.rows_edge = p.rows_edge;
+    lc.rows_inner = p.rows_inner;
     lc.top_segs = top_segs;
     lc.bot_segs = bot_segs;
     h->p2p_iter += 1;

@@ -123,6 +123,10 @@ struct SweepParams {
   // (system fences wait for NVLink write acknowledgements) and gets fewer rows,
   // so that it does not finish after everybody else.  NULL: runs of lin_len.
   const int* unit_lo;
+  // P2P row-block units: the same idea with two numbers: the first and last
+  // row block of a strip get rows_edge < rows_per_unit rows, the blocks between
+  // them rows_inner; rows_edge == 0: all blocks have rows_per_unit rows.
+  int rows_edge, rows_inner;
 };
 
 // Flag block of a shard (uint32 each, cudaMalloc'ed, IPC-shared).
@@ -601,8 +605,14 @@ struct Sweeper {
     } else {
       const int k = unit % p.n_strips;
       const int rb = unit / p.n_strips;
-      const int y0 = p.y_begin + rb * p.rows_per_unit;      // rows [y0, y1)
-      const int y1 = min(y0 + p.rows_per_unit, p.y_end);
+      int y0, y1;                                             // rows [y0, y1)
+      if (P2P && p.rows_edge > 0) {
+        y0 = rb == 0 ? p.y_begin : p.y_begin + p.rows_edge + (rb - 1) * p.rows_inner;
+        y1 = min(p.y_begin + p.rows_edge + rb * p.rows_inner, p.y_end);
+      } else {
+        y0 = p.y_begin + rb * p.rows_per_unit;
+        y1 = min(y0 + p.rows_per_unit, p.y_end);
+      }
       run_segment(k, y0, y1, lane);
     }
   }

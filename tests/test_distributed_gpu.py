@@ -91,17 +91,22 @@ def test_single_process_multi_gpu_handle_matches_the_oracle(n):
         assert np.array_equal(mdp.optimal_action, A)
 
 
-@pytest.mark.parametrize("shape,short", [((3000, 300), 0), ((3000, 300), 20), ((3000, 300), 60),
-                                         ((1200, 1000), 20), ((160, 4000), 20)])
-def test_cost_balanced_units_keep_the_bits(monkeypatch, shape, short):
-    """The peer-to-peer kernels cut the strip-major row sequence into units of
-    equal COST (a unit that does the hand-shake gets PP2D_P2P_EDGE_SHORT fewer
-    rows; 0 = equal rows) read from a table; the partition must not change a
-    bit, whatever the shape (many short units, units spanning several strips)."""
+@pytest.mark.parametrize("shape,short,lin,rpu", [
+    ((3000, 300), 0, 1, 0), ((3000, 300), 20, 1, 0), ((3000, 300), 60, 1, 0),
+    ((1200, 1000), 20, 1, 0), ((160, 4000), 20, 1, 0),          # unit table (strip-major runs)
+    ((3000, 300), 12, 0, 100), ((3000, 300), 40, 0, 100)])       # shorter boundary row blocks
+def test_cost_balanced_units_keep_the_bits(monkeypatch, shape, short, lin, rpu):
+    """The units of the peer-to-peer kernels that do the hand-shake get fewer
+    rows (PP2D_P2P_EDGE_SHORT; 0 = equal rows): a table of unit boundaries over
+    the strip-major row sequence, or shorter first / last row blocks.  The
+    partition must not change a bit, whatever the shape (many short units,
+    units spanning several strips)."""
     from path_planning_2d_b200 import MdpPathPlanning2d
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     monkeypatch.setenv("PP2D_P2P_EDGE_SHORT", str(short))
+    monkeypatch.setenv("PP2D_MDP_LINEAR_UNITS", str(lin))
+    monkeypatch.setenv("PP2D_MDP_ROWS_PER_UNIT", str(rpu))
     grid, goal = cases.synthetic_map(shape[0], shape[1], 0.2, seed=78)
     ora = oracle_py.OracleMdp(grid, goal, cases.GAMMA)
     with MdpPathPlanning2d(grid, goal, cases.GAMMA, devices=2) as mdp:
