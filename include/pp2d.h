@@ -295,7 +295,9 @@ int pp2d_pomdp_model_tables(pp2d_pomdp* h, float* trans_prob, float* meas_prob,
  * decimals, so e.g. 0.02^4 becomes 0.00000016.  The tables replace the ones
  * pp2d_pomdp_create generated (layouts as in pp2d_pomdp_model_tables); any
  * pointer may be NULL (that table is kept).  Parsing the files stays on the
- * host side (include/pp2d/planners.hpp: loadModelDataFromFile).
+ * host side (include/pp2d/planners.hpp: loadModelDataFromFile).  Call it
+ * before any search tree exists on the handle (PP2D_ERR_STATE otherwise), as
+ * the reference loads its tables once in initialize().
  */
 int pp2d_pomdp_set_model_tables(pp2d_pomdp* h, const float* trans_prob,
                                 const float* meas_prob, const float* stage_reward);

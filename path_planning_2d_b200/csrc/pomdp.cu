@@ -811,6 +811,13 @@ int pp2d_pomdp_set_model_tables(pp2d_pomdp* h, const float* trans_prob,
                                 const float* meas_prob, const float* stage_reward) {
   if (!h) return fail(PP2D_ERR_INVALID, "handle is NULL");
   const size_t n = (size_t)h->HW;
+  // Trees keep beliefs that were propagated with the current tables (and were
+  // classified against the current live-cell mask): like the reference, which
+  // loads its tables once in initialize(), the tables are fixed before any tree.
+  if (h->d_bel && h->free_slots.size() != (size_t)h->cap)
+    return fail(PP2D_ERR_STATE, "pp2d_pomdp_set_model_tables: destroy the search trees of this "
+                                "handle first (%zu beliefs are resident)",
+                (size_t)h->cap - h->free_slots.size());
   // every stream that reads the tables (rounds of a batch in flight)
   PP2D_CUDA(cudaDeviceSynchronize());
   if (trans_prob)
