@@ -581,6 +581,10 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   h->trapped.push_back(0.0f);
   h->cw2 = env_int("PP2D_MDP_CW2", 2);
   h->cw1 = env_int("PP2D_MDP_CW1", 4);
+  if (PP2D_TMA) {            // 10 pad columns: the 16-byte per-lane vectors of CW = 4 are misaligned
+    if (h->cw2 == 4) h->cw2 = 2;
+    if (h->cw1 == 4) h->cw1 = 2;
+  }
   h->fused_policy = env_int("PP2D_MDP_FUSED_POLICY", 1) != 0;
   h->linear_units = env_int("PP2D_MDP_LINEAR_UNITS", -1);
   h->pdl = env_int("PP2D_MDP_PDL", 1) != 0;

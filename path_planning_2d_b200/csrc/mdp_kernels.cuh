@@ -52,7 +52,17 @@ constexpr int kPrefetch = 2;  // CW == 1 path: rows held in registers ahead of u
 #define PP2D_KRING 3
 #endif
 constexpr int kRing = PP2D_KRING;  // CW >= 2 path: cp.async ring slots per lane (1, 2, 3 or 6)
-constexpr int kPadLeft = 8;   // zero columns left of x = 0 (32 B)
+// PP2D_TMA = 1 (experiment, A/B-timed in profiles/): the row ring of the fused
+// CW = 2 kernel is filled by bulk async copies (cp.async.bulk, the TMA engine)
+// issued by one lane per warp and completed on a per-slot mbarrier, instead of
+// per-lane cp.async.  A bulk copy needs 16-byte aligned addresses: with 10 pad
+// columns a warp's 64-float row segment (strip k starts at column 60 k - 2)
+// is aligned; the CW = 4 kernels (16-byte per-lane vectors) then are not, so
+// such a build only runs CW <= 2.
+#ifndef PP2D_TMA
+#define PP2D_TMA 0
+#endif
+constexpr int kPadLeft = PP2D_TMA ? 10 : 8;   // zero columns left of x = 0
 // Table layouts (build-time choice, both give the same bits):
 //   PP2D_LUT6 = 0: 4 tables (one per action pair) x 16 rows (4 ring bits) x 8
 //     lane replicas of one float4 = 8 KB; a cell needs 4 row addresses.
@@ -351,15 +361,59 @@ __device__ __forceinline__ void lds_codes(uint32_t saddr,
   }
 }
 
+// ---- bulk-copy (TMA) staging helpers (PP2D_TMA builds) -----------------------
+// (lane 0 only, predicated: no divergent branch)
+__device__ __forceinline__ void mbar_init_lane0(int lane, uint32_t bar, uint32_t count) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P0;\n"
+      "setp.eq.s32 P0, %0, 0;\n"
+      "@P0 mbarrier.init.shared::cta.b64 [%1], %2;\n"
+      "}\n" :: "r"(lane), "r"(bar), "r"(count) : "memory");
+}
+// Spin until the phase with the given parity of the barrier has completed.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+// Lane 0 (predicated, no branch: the warp stays converged for the compiler):
+// expect JB + CB bytes on the barrier and start the two bulk copies.
+template <int JB, int CB>
+__device__ __forceinline__ void tma_fill(int lane, uint32_t bar, uint32_t dst_j, const void* src_j,
+                                         uint32_t dst_c, const void* src_c) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P0;\n"
+      "setp.eq.s32 P0, %0, 0;\n"
+      "@P0 mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %6;\n"
+      "@P0 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %7, [%1];\n"
+      "@P0 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%5], %8, [%1];\n"
+      "}\n"
+      :: "r"(lane), "r"(bar), "r"(dst_j), "l"(src_j), "r"(dst_c), "l"(src_c), "n"(JB + CB),
+         "n"(JB), "n"(CB)
+      : "memory");
+}
+
 template <int T, int CW>
 struct StripGeom {
   static constexpr int HL = (T + CW - 1) / CW;          // halo lanes per side
   static constexpr int S = (32 - 2 * HL) * CW;          // valid columns/strip
   static constexpr int XOFF = -HL * CW;                 // x of lane 0, cell 0
   // cp.async ring: per warp and slot, 32 lanes x (CW floats + CW codes).
-  static constexpr int kSlotBytes = 32 * CW * 6;
+  // (TMA builds: 16 more bytes of codes per slot -- the code segment is copied
+  // from the 16-byte boundary below it -- and kRing mbarriers per warp.)
+  static constexpr int kSlotBytes = 32 * CW * 6 + (PP2D_TMA ? 16 : 0);
   static constexpr int kCodeOff = 32 * CW * 4;
-  static constexpr int kRingBytesPerWarp = (CW >= 2) ? kRing * kSlotBytes : 0;
+  static constexpr int kBarOff = kRing * kSlotBytes;
+  static constexpr int kRingBytesPerWarp =
+      (CW >= 2) ? kRing * kSlotBytes + (PP2D_TMA ? 32 : 0) : 0;
 };
 
 // LIN: units are runs of the strip-major row sequence (see run()); a separate
@@ -368,6 +422,10 @@ struct StripGeom {
 template <int T, int CW, bool POLICY, bool P2P = false, bool LIN = false>
 struct Sweeper {
   using G = StripGeom<T, CW>;
+  // bulk-copy ring: the fused row-block kernel only (one march per warp)
+  static constexpr bool kTma = PP2D_TMA && T == 2 && CW == 2 && !P2P && !LIN;
+  uint32_t ring_base = 0;    // kTma: shared address of this warp's ring (slot 0)
+  int lane_id = 0;
   float A[3][CW + 2];        // J^0 rows y-1, y, y+1 (rotating)
   float B[3][CW + 2];        // J^1 rows y-2, y-1, y (T == 2)
   float4 L[2][CW][4];        // LUT rows of row y (cur) and y-1 (prev)
@@ -401,7 +459,17 @@ struct Sweeper {
     constexpr int a0 = I % 3, a1 = (I + 1) % 3, a2 = (I + 2) % 3;
     constexpr int lc = I % 2, lp = (I + 1) % 2;
     uint32_t cc[(CW + 1) / 2];
-    if constexpr (CW >= 2) {
+    if constexpr (kTma) {
+      constexpr int slot = I % kRing;
+      // use number (step / kRing) of this slot: its parity is a compile-time
+      // constant because the unrolled period (6) is a multiple of 2 * kRing
+      static_assert(6 % (2 * kRing) == 0 || kRing == 3, "ring depth vs unroll");
+      mbar_wait(ring_base + G::kBarOff + 8 * slot, (I / kRing) & 1);
+      float own[CW];
+      lds_row<CW, slot * G::kSlotBytes>(ring_j, own);
+      lds_codes<CW, slot * G::kSlotBytes + G::kCodeOff>(ring_c, cc);
+      fill_row<CW>(own, A[a2]);
+    } else if constexpr (CW >= 2) {
       constexpr int slot = I % kRing;
       // The oldest of the kRing groups in flight (row y+1, codes of row y)
       // has landed in this lane's slot.
@@ -424,8 +492,10 @@ struct Sweeper {
       asm volatile("prefetch.global.L1 [%0];" :: "l"(pin + l1_ahead));
       asm volatile("prefetch.global.L1 [%0];" :: "l"(pcode + l1_ahead));
     }
-    pin += p.pitch;
-    pcode += p.pitch;
+    if constexpr (!kTma) {
+      pin += p.pitch;
+      pcode += p.pitch;
+    }
     // Table rows of row y.
 #pragma unroll
     for (int j = 0; j < CW; ++j) {
@@ -505,6 +575,17 @@ struct Sweeper {
         for (int j = 0; j < (CW + 1) / 2; ++j) cprev[j] = cc[j];
       }
     }
+    if constexpr (kTma) {
+      // Refill the slot read at the top of this step (its values have been
+      // consumed by the arithmetic above) with row y+1+kRing / codes of row
+      // y+kRing; pcode points at the 16-byte boundary below the code segment.
+      constexpr int slot = I % kRing;
+      tma_fill<32 * CW * 4, 32 * CW * 2 + 16>(
+          lane_id, ring_base + G::kBarOff + 8 * slot, ring_base + slot * G::kSlotBytes, pin,
+          ring_base + slot * G::kSlotBytes + G::kCodeOff, pcode);
+      pin += p.pitch;
+      pcode += p.pitch;
+    }
   }
 
   // March over rows [y0, y1) of this lane's columns.  PEER: rows 0,1 / H-2,H-1
@@ -526,7 +607,27 @@ struct Sweeper {
     }
     pin = jin + 2 * pitch;                                  // row ys+1
     pcode = p.code + col + (size_t)(ys + kPadRows) * pitch; // row ys
-    if constexpr (CW >= 2) {
+    const int total_steps = steps;
+    if constexpr (kTma) {
+      // lane 0's pointers are the warp's row segment; codes are fetched from
+      // the 16-byte boundary below it and read back at that offset
+      const uint32_t coff =
+          __shfl_sync(0xffffffffu, (uint32_t)(reinterpret_cast<uintptr_t>(pcode) & 15u), 0);
+      pcode = reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(pcode) - coff);
+      ring_c += coff;
+#pragma unroll
+      for (int d = 0; d < kRing; ++d) mbar_init_lane0(lane_id, ring_base + G::kBarOff + 8 * d, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < kRing; ++d) {
+        tma_fill<32 * CW * 4, 32 * CW * 2 + 16>(
+            lane_id, ring_base + G::kBarOff + 8 * d, ring_base + d * G::kSlotBytes, pin,
+            ring_base + d * G::kSlotBytes + G::kCodeOff, pcode);
+        pin += pitch;
+        pcode += pitch;
+      }
+    } else if constexpr (CW >= 2) {
 #pragma unroll
       for (int d = 0; d < kRing; ++d) {
         cp_async<CW * 4>(ring_j + d * G::kSlotBytes, pin);
@@ -570,7 +671,15 @@ struct Sweeper {
       }
     }
     // Do not leave the slot ring with copies in flight.
-    if constexpr (CW >= 2) cp_async_wait<0>();
+    if constexpr (kTma) {
+      // slot d was filled once by the priming and once by every step j with
+      // j % kRing == d; wait for its last fill (use number fills - 1)
+#pragma unroll
+      for (int d = 0; d < kRing; ++d) {
+        const int fills = 1 + (total_steps > d ? (total_steps - d + kRing - 1) / kRing : 0);
+        mbar_wait(ring_base + G::kBarOff + 8 * d, (uint32_t)(fills - 1) & 1u);
+      }
+    } else if constexpr (CW >= 2) cp_async_wait<0>();
   }
 
   // A unit is a run of `lin_len` rows of the strip-major sequence (strip 0 rows
@@ -626,6 +735,8 @@ struct Sweeper {
     if constexpr (!LIN) {
       l1_ahead = (size_t)(p.prefetch_rows - kPrefetch) * (size_t)p.pitch;
       if constexpr (CW >= 2) {
+        ring_base = ring_j;
+        lane_id = lane;
         ring_j += lane * (CW * 4);
         ring_c += lane * (CW * 2);
       }
