@@ -119,7 +119,7 @@ struct pp2d_pomdp {
   pp2d::DevBuf<float> d_prefix, d_draws, d_vals, d_rows, d_sums;
   pp2d::DevBuf<uint8_t> d_obs;
   pp2d::DevBuf<float> d_out;               // 4 floats per evaluated belief
-  void* round_ctx[2] = {nullptr, nullptr};   // RoundCtx of pomdp.cu (lazily created)
+  void* round_ctx[4] = {nullptr, nullptr, nullptr, nullptr};   // RoundCtx of pomdp.cu (lazily created)
   cudaStream_t stream = nullptr;
   uint64_t n_bayes = 0, n_vnodes = 0;
   double t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // PP2D_POMDP_PROFILE=1: seconds per phase
