@@ -83,7 +83,7 @@ struct Cublas {
 Cublas g_cublas;
 
 // ---------------------------------------------------------------------------
-// belief-set expansion kernels (belief pool layout bel[cell * cap + slot])
+// belief-set expansion kernels (belief pool layout: bel_off of pomdp_kernels.cuh)
 
 // pbvi:147-162 sampleFromProbDensity three times (pbvi:216-222): one thread
 // per (belief i, action a).  prefix[i * HW + s] is partial_sum(b_i); draws are
@@ -137,7 +137,7 @@ pbvi_sample_kernel(int H, int W, int n, const float* __restrict__ trans_prob,
 // best`).
 constexpr int kL1M = 64, kL1N = 64, kL1K = 16;
 __global__ void __launch_bounds__(256)
-pbvi_l1_kernel(int HW, int cap, const float* __restrict__ bel,
+pbvi_l1_kernel(int HW, const float* __restrict__ bel,
                const int* __restrict__ cand, int n_cand, const int* __restrict__ set,
                int n_set, unsigned int* __restrict__ l1_bits) {
   __shared__ __align__(16) float sa[kL1K][kL1M + 4];
@@ -158,8 +158,8 @@ pbvi_l1_kernel(int HW, int cap, const float* __restrict__ bel,
     for (int e = tid; e < kL1K * kL1M; e += 256) {
       const int kk = e / kL1M, mm = e % kL1M;
       const int s = min(k0 + kk, HW - 1);
-      sa[kk][mm] = bel[(size_t)s * cap + sca[mm]];
-      sb[kk][mm] = bel[(size_t)s * cap + sse[mm]];
+      sa[kk][mm] = bel[bel_off(HW, s, sca[mm])];
+      sb[kk][mm] = bel[bel_off(HW, s, sse[mm])];
     }
     __syncthreads();
     const int kend = min(kL1K, HW - k0);
@@ -464,7 +464,7 @@ int expand_belief_set(pp2d_pomdp* h, const float* b0, uint32_t max_size, uint32_
           d_l1.p, nc, 0x7f7fffffu /* FLT_MAX */);
       count_launch();
       dim3 grid((nc + kL1M - 1) / kL1M, (n + kL1N - 1) / kL1N);
-      pbvi_l1_kernel<<<grid, 256, 0, h->stream>>>(HW, h->cap, h->d_bel, d_cand.p, nc, d_set.p,
+      pbvi_l1_kernel<<<grid, 256, 0, h->stream>>>(HW, h->d_bel, d_cand.p, nc, d_set.p,
                                                   n, d_l1.p);
       count_launch();
       PP2D_CUDA(cudaGetLastError());

@@ -115,9 +115,9 @@ struct pp2d_tree {
 
 namespace pp2d {
 
-// Grow the belief pool [HW][cap] to at least slots_wanted columns.  Live
-// beliefs keep their slot numbers: the old matrix is copied row by row into
-// the wider one (the slot index is the fastest dimension).
+// Grow the belief pool (blocks of 32 slots, see bel_off) to at least
+// slots_wanted slots.  Live beliefs keep their slot numbers: the blocks of the
+// old pool are the first blocks of the new one, one contiguous copy.
 int pool_reserve(pp2d_pomdp* h, size_t slots_wanted) {
   if ((size_t)h->cap >= slots_wanted && h->d_bel) return PP2D_OK;
   const size_t cap = (slots_wanted + 31) / 32 * 32;
@@ -129,9 +129,8 @@ int pool_reserve(pp2d_pomdp* h, size_t slots_wanted) {
   if (old_cap && h->free_slots.size() != old_cap) {
     cudaError_t e = cudaDeviceSynchronize();     // every stream that touches the pool
     if (e == cudaSuccess)
-      e = cudaMemcpy2DAsync(nb, cap * sizeof(float), h->d_bel, old_cap * sizeof(float),
-                            old_cap * sizeof(float), (size_t)h->HW, cudaMemcpyDeviceToDevice,
-                            h->stream);
+      e = cudaMemcpyAsync(nb, h->d_bel, old_cap * (size_t)h->HW * sizeof(float),
+                          cudaMemcpyDeviceToDevice, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) {
       cudaFree(nb);
@@ -166,7 +165,7 @@ int launch_bayes(pp2d_pomdp* h, const std::vector<BayesItem>& items) {
   PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), n * sizeof(BayesItem),
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((n + 31) / 32, (h->HW + 7) / 8);
-  pomdp_bayes_kernel<<<grid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+  pomdp_bayes_kernel<<<grid, 256, 0, h->stream>>>(h->H, h->W, h->d_tp, h->d_mp,
                                                   h->d_items.p, n, h->d_bel, h->d_bel);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -183,10 +182,10 @@ int launch_normalize(pp2d_pomdp* h, const std::vector<int>& slots) {
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   pomdp_colsum_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
-      h->HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_sums.p);
+      h->HW, h->d_slots.p, n, h->d_bel, h->d_sums.p);
   count_launch();
   dim3 grid((n + 31) / 32, (h->HW + 7) / 8);
-  pomdp_scale_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n,
+  pomdp_scale_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->d_slots.p, n,
                                                   h->d_sums.p, h->d_bel);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -202,7 +201,7 @@ int launch_prefix(pp2d_pomdp* h, const std::vector<int>& slots) {
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   pomdp_prefix_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(
-      h->HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_prefix.p);
+      h->HW, h->d_slots.p, n, h->d_bel, h->d_prefix.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
   return PP2D_OK;
@@ -218,7 +217,7 @@ int launch_scatter(pp2d_pomdp* h, const std::vector<int>& slots, const float* ho
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((h->HW + 255) / 256, n);
-  pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n,
+  pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->d_slots.p, n,
                                                     h->d_rows.p, h->d_bel);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -232,7 +231,7 @@ int launch_gather(pp2d_pomdp* h, const std::vector<int>& slots, float* dev_rows)
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((h->HW + 255) / 256, n);
-  pomdp_gather_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n, h->d_bel,
+  pomdp_gather_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->d_slots.p, n, h->d_bel,
                                                    dev_rows);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -291,7 +290,9 @@ namespace {
 // cells, or all cells when some belief involved may be non-zero elsewhere.
 struct InnerDim { const int* kidx; int K; const float* alpha; const uint8_t* dead; };
 InnerDim inner_dim(const pp2d_pomdp* h, bool dense) {
-  if (dense || !h->skip_dead) return {h->d_kidx_all, h->HW, h->d_alpha, nullptr};
+  // (a non-finite bound makes 0 * alpha a NaN in the reference: nothing is skipped then)
+  if (dense || !h->skip_dead || !h->alphas_finite)
+    return {h->d_kidx_all, h->HW, h->d_alpha, nullptr};
   return {h->d_kidx, h->K, h->d_alpha_live, h->d_dead};
 }
 
@@ -333,9 +334,9 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out, boo
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((n + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
   const InnerDim in = inner_dim(h, dense);
-  pomdp_values_kernel<<<grid, 256, 0, h->stream>>>(
-      in.K, in.kidx, h->cap, h->ld, h->ncol, h->d_slots.p, n, h->d_bel, in.alpha,
-      h->d_vals.p);
+  pomdp_values_kernel<false><<<grid, 256, 0, h->stream>>>(
+      in.K, in.kidx, h->HW, h->ld, h->ncol, h->d_slots.p, n, h->d_bel, in.alpha,
+      h->d_vals.p, nullptr, nullptr, nullptr, 0);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
   pomdp_bounds_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(
@@ -352,10 +353,10 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out, boo
 int normalize_slots(pp2d_pomdp* h, int n, float* sums_out_dev) {
   PP2D_TRY(h->d_sums.ensure(n));
   pomdp_colsum_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(
-      h->HW, h->cap, h->d_slots.p, n, h->d_bel, h->d_sums.p);
+      h->HW, h->d_slots.p, n, h->d_bel, h->d_sums.p);
   count_launch();
   dim3 grid((n + 31) / 32, (h->HW + 7) / 8);
-  pomdp_scale_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n,
+  pomdp_scale_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->d_slots.p, n,
                                                   h->d_sums.p, h->d_bel);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -394,7 +395,7 @@ int make_roots(pp2d_pomdp* h, std::vector<Tree*>& trees, const float* beliefs) {
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((h->HW + 255) / 256, n);
-  pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->cap, h->d_slots.p, n,
+  pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(h->HW, h->d_slots.p, n,
                                                     h->d_rows.p, h->d_bel);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
@@ -450,17 +451,20 @@ struct RoundCtx {
   std::vector<Job> jobs;
   int n = 0, nk = 0;
   bool dense = false;                // some tree of this round needs the dense products
-  PinnedBuf<int> slots, kslots, gfirst, kgroup;
+  PinnedBuf<int> slots, kslots, kgroup;
   PinnedBuf<float> draws, rewards, ev;
   PinnedBuf<BayesItem> items;
   PinnedBuf<uint8_t> obs;
   std::vector<int> first;
   std::vector<Child> kids;
-  DevBuf<int> d_jobslots, d_kslots, d_gfirst, d_kgroup;
+  DevBuf<int> d_jobslots, d_kslots, d_kgroup;
   DevBuf<float> d_pred;              // [HW][ngp] predictions of the Q nodes of a round
   DevBuf<float> d_prefix, d_draws, d_rew, d_sums, d_vals, d_out;
   DevBuf<uint8_t> d_obs;
   DevBuf<BayesItem> d_items;
+  DevBuf<int2> d_tlist;              // per-tile inner rows of the values launch
+  DevBuf<int> d_tcount, d_torder;
+  DevBuf<uint32_t> d_tmask;
   cudaEvent_t e1 = nullptr, e2 = nullptr;
   cudaStream_t stream = nullptr;     // own stream: the tail of one group's launches
                                      // overlaps the other group's
@@ -468,12 +472,12 @@ struct RoundCtx {
                                      // that it is not queued behind the other group's
                                      // values launch and the host can move on
   ~RoundCtx() {
-    slots.release(); kslots.release(); gfirst.release(); kgroup.release(); draws.release();
+    slots.release(); kslots.release(); kgroup.release(); draws.release();
     rewards.release(); d_kgroup.release(); d_pred.release();
     ev.release(); items.release(); obs.release();
-    d_jobslots.release(); d_kslots.release(); d_gfirst.release(); d_prefix.release();
+    d_jobslots.release(); d_kslots.release(); d_prefix.release();
     d_draws.release(); d_rew.release(); d_sums.release(); d_vals.release(); d_out.release();
-    d_obs.release(); d_items.release();
+    d_obs.release(); d_items.release(); d_tlist.release(); d_tcount.release(); d_torder.release(); d_tmask.release();
     if (e1) cudaEventDestroy(e1);
     if (e2) cudaEventDestroy(e2);
     if (stream) cudaStreamDestroy(stream);
@@ -540,17 +544,16 @@ int round_stage1(pp2d_pomdp* h, RoundCtx& c, const std::vector<Tree*>& trees) {
                             cudaMemcpyHostToDevice, c.stream_hi));
   PP2D_CUDA(cudaMemcpyAsync(c.d_draws.p, c.draws.p, nd * sizeof(float),
                             cudaMemcpyHostToDevice, c.stream_hi));
-  pomdp_prefix_kernel<<<(n + 3) / 4, 128, 0, c.stream_hi>>>(
-      HW, h->cap, c.d_jobslots.p, n, h->d_bel, c.d_prefix.p);
+  // prefix sums and reward dots of the expanded nodes in one launch, then the
+  // sampling (which needs the prefix sums)
+  const InnerDim in = inner_dim(h, c.dense);
+  pomdp_expand_kernel<<<(n + 3) / 4 + (n * 3 + 3) / 4, 128, 0, c.stream_hi>>>(
+      HW, in.K, in.kidx, c.d_jobslots.p, n, h->d_bel, h->d_sr, c.d_prefix.p, c.d_rew.p);
   count_launch();
   const int nt = (int)nd;
   pomdp_sample_kernel<<<(nt + 127) / 128, 128, 0, c.stream_hi>>>(
       h->H, h->W, n, kSamples, h->d_tp, h->d_mp, c.d_prefix.p, c.d_draws.p,
       h->d_uniforms, c.d_obs.p);
-  count_launch();
-  const InnerDim in = inner_dim(h, c.dense);
-  pomdp_rewards_kernel<<<(n * kActions + 3) / 4, 128, 0, c.stream_hi>>>(
-      in.K, in.kidx, h->cap, c.d_jobslots.p, n, h->d_bel, h->d_sr, c.d_rew.p);
   count_launch();
   PP2D_CUDA(cudaGetLastError());
   PP2D_CUDA(cudaMemcpyAsync(c.obs.p, c.d_obs.p, nd, cudaMemcpyDeviceToHost, c.stream_hi));
@@ -587,17 +590,14 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
   const int nk = c.nk = c.first[n];
   PP2D_TRY(c.kslots.ensure(nk));
   PP2D_TRY(c.items.ensure(nk));
-  PP2D_TRY(c.gfirst.ensure((size_t)n * kActions + 1));
   PP2D_TRY(c.kgroup.ensure(nk));
   PP2D_TRY(c.ev.ensure((size_t)nk * 4));
   for (int k = 0; k < nk; ++k) PP2D_TRY(alloc_slot(h, &c.kslots.p[k]));
   c.kids.resize(nk);
-  c.gfirst.p[(size_t)n * kActions] = nk;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) if (n >= 64)
   for (int i = 0; i < n; ++i) {
     int k = c.first[i];
     for (int a = 0; a < kActions; ++a) {
-      c.gfirst.p[(size_t)i * kActions + a] = k;
       const uint8_t* o = c.obs.p + ((size_t)i * kActions + a) * kSamples;
       int count[16] = {0};
       for (int s = 0; s < kSamples; ++s) count[o[s] & 15]++;
@@ -612,14 +612,11 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
   }
   const int ng = n * kActions;
   PP2D_TRY(c.d_items.ensure(nk));
-  PP2D_TRY(c.d_gfirst.ensure(ng + 1));
   PP2D_TRY(c.d_kslots.ensure(nk));
   PP2D_TRY(c.d_sums.ensure(nk));
   PP2D_TRY(c.d_vals.ensure((size_t)nk * h->ncol));
   PP2D_TRY(c.d_out.ensure((size_t)nk * 4));
   PP2D_CUDA(cudaMemcpyAsync(c.d_items.p, c.items.p, nk * sizeof(BayesItem),
-                            cudaMemcpyHostToDevice, c.stream));
-  PP2D_CUDA(cudaMemcpyAsync(c.d_gfirst.p, c.gfirst.p, (ng + 1) * sizeof(int),
                             cudaMemcpyHostToDevice, c.stream));
   PP2D_CUDA(cudaMemcpyAsync(c.d_kslots.p, c.kslots.p, nk * sizeof(int),
                             cudaMemcpyHostToDevice, c.stream));
@@ -629,24 +626,48 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
   PP2D_CUDA(cudaMemcpyAsync(c.d_kgroup.p, c.kgroup.p, nk * sizeof(int), cudaMemcpyHostToDevice,
                             c.stream));
   const InnerDim in = inner_dim(h, c.dense);
-  dim3 bgrid((ng + 31) / 32, (in.K + 7) / 8);
-  pomdp_predict_kernel<<<bgrid, 256, 0, c.stream>>>(h->H, h->W, in.K, in.kidx, h->cap, ngp,
-                                                     h->d_tp, c.d_items.p, c.d_gfirst.p, ng,
-                                                     h->d_bel, c.d_pred.p);
+  // (group g = 9 * job + action; c.d_jobslots was uploaded in stage 1, which
+  // this stream is behind: the host has waited for e1)
+  dim3 bgrid((n + 31) / 32, (in.K + 7) / 8);
+  pomdp_predict9_kernel<<<bgrid, 256, 0, c.stream>>>(h->H, h->W, in.K, in.kidx, ngp, h->d_tp,
+                                                      c.d_jobslots.p, n, h->d_bel, c.d_pred.p);
   count_launch();
   h->n_bayes += nk;
   pomdp_child_sum_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(
       in.K, in.kidx, ngp, h->d_mp, c.d_items.p, c.d_kgroup.p, nk, c.d_pred.p, c.d_sums.p);
   count_launch();
-  dim3 sgrid((nk + 31) / 32, (HW + 7) / 8);
-  pomdp_child_write_kernel<<<sgrid, 256, 0, c.stream>>>(HW, h->cap, ngp, h->d_mp, in.dead,
+  dim3 sgrid((nk + 31) / 32, (HW + 8 * kCwCells - 1) / (8 * kCwCells));
+  pomdp_child_write_kernel<<<sgrid, 256, 0, c.stream>>>(HW, ngp, h->d_mp, in.dead,
                                                          c.d_items.p, c.d_kgroup.p, nk,
                                                          c.d_pred.p, c.d_sums.p, h->d_bel);
   count_launch();
   dim3 vgrid((nk + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
-  pomdp_values_kernel<<<vgrid, 256, 0, c.stream>>>(in.K, in.kidx, h->cap, h->ld, h->ncol,
-                                                    c.d_kslots.p, nk, h->d_bel, in.alpha,
-                                                    c.d_vals.p);
+  if (h->tile_support && h->alphas_finite) {
+    // the inner rows each tile of kEvM children really needs (exact, see
+    // pomdp_values_kernel<TILED>)
+    const int mstride = (in.K + 31) / 32;
+    PP2D_TRY(c.d_tlist.ensure((size_t)vgrid.x * in.K));
+    PP2D_TRY(c.d_tcount.ensure(vgrid.x));
+    PP2D_TRY(c.d_tmask.ensure((size_t)vgrid.x * mstride));
+    dim3 fgrid(vgrid.x, (in.K + 255) / 256);
+    pomdp_support_flags_kernel<<<fgrid, 256, 0, c.stream>>>(
+        HW, in.K, in.kidx, c.d_kslots.p, nk, h->d_bel, c.d_tmask.p, mstride);
+    count_launch();
+    pomdp_support_list_kernel<<<vgrid.x, 256, 0, c.stream>>>(in.K, in.kidx, c.d_tmask.p, mstride,
+                                                             c.d_tlist.p, c.d_tcount.p);
+    count_launch();
+    PP2D_TRY(c.d_torder.ensure(vgrid.x));
+    pomdp_tile_order_kernel<<<(vgrid.x + 255) / 256, 256, 0, c.stream>>>(
+        (int)vgrid.x, c.d_tcount.p, c.d_torder.p);
+    count_launch();
+    pomdp_values_kernel<true><<<dim3(vgrid.y, vgrid.x), 256, 0, c.stream>>>(
+        in.K, in.kidx, h->HW, h->ld, h->ncol, c.d_kslots.p, nk, h->d_bel, in.alpha, c.d_vals.p,
+        c.d_tlist.p, c.d_tcount.p, c.d_torder.p, in.K);
+  } else {
+    pomdp_values_kernel<false><<<vgrid, 256, 0, c.stream>>>(
+        in.K, in.kidx, h->HW, h->ld, h->ncol, c.d_kslots.p, nk, h->d_bel, in.alpha, c.d_vals.p,
+        nullptr, nullptr, nullptr, 0);
+  }
   count_launch();
   pomdp_bounds_kernel<<<(nk + 3) / 4, 128, 0, c.stream>>>(nk, h->ncol, h->n_pbvi,
                                                                c.d_vals.p, c.d_out.p);
@@ -776,6 +797,10 @@ int pp2d_pomdp_create(uint32_t height, uint32_t width, const uint8_t* map,
     PP2D_CUDA(cudaDeviceSynchronize());
     const char* dense_env = getenv("PP2D_POMDP_DENSE");
     h->skip_dead = !(dense_env && atoi(dense_env) != 0);
+    const char* tile_env = getenv("PP2D_POMDP_TILE_SUPPORT");
+    h->tile_support = !(tile_env && atoi(tile_env) == 0);
+    const char* sort_env = getenv("PP2D_POMDP_SORT");
+    h->sort_queries = !(sort_env && atoi(sort_env) == 0);
     return refresh_live_cells(h);
   }();
   if (rc != PP2D_OK) { pp2d_pomdp_destroy(h); return rc; }
@@ -847,11 +872,16 @@ int pp2d_pomdp_set_alphas(pp2d_pomdp* h, const float* fib_alphas,
   const int ld = (ncol + kEvN - 1) / kEvN * kEvN;   // zero-padded to whole column tiles
   const size_t HW = (size_t)h->HW;
   std::vector<float> mat(HW * ld, 0.0f);
+  bool finite = true;
   for (size_t s = 0; s < HW; ++s) {
     float* row = mat.data() + s * ld;
     memcpy(row + kColFib, fib_alphas + s * 9, 9 * sizeof(float));
     for (uint32_t i = 0; i < n_pbvi; ++i) row[kColPbvi + i] = pbvi_alphas[(size_t)i * HW + s];
+    for (int j = 0; j < ncol; ++j) finite = finite && std::isfinite(row[j]);
   }
+  // The exact skipping of zero belief entries (dead cells, per-tile inner rows)
+  // needs 0 * alpha == 0.
+  h->alphas_finite = finite;
   if (h->d_alpha) cudaFree(h->d_alpha);
   h->d_alpha = nullptr;
   PP2D_CUDA(cudaMalloc(&h->d_alpha, mat.size() * sizeof(float)));
@@ -962,20 +992,20 @@ int pp2d_pomdp_bayes_update(pp2d_pomdp* h, const float* beliefs_in, uint32_t n,
     PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, in.data(), n * sizeof(int),
                               cudaMemcpyHostToDevice, h->stream));
     dim3 grid((HW + 255) / 256, n);
-    pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(HW, h->cap, h->d_slots.p, n,
+    pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(HW, h->d_slots.p, n,
                                                       h->d_rows.p, h->d_bel);
     count_launch();
     PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, items.data(), n * sizeof(BayesItem),
                               cudaMemcpyHostToDevice, h->stream));
     dim3 bgrid((n + 31) / 32, (HW + 7) / 8);
-    pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+    pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->d_tp, h->d_mp,
                                                      h->d_items.p, n, h->d_bel, h->d_bel);
     count_launch();
     h->n_bayes += n;
     PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, outs.data(), n * sizeof(int),
                               cudaMemcpyHostToDevice, h->stream));
     if (normalize) PP2D_TRY(normalize_slots(h, (int)n, nullptr));
-    pomdp_gather_kernel<<<grid, 256, 0, h->stream>>>(HW, h->cap, h->d_slots.p, n, h->d_bel,
+    pomdp_gather_kernel<<<grid, 256, 0, h->stream>>>(HW, h->d_slots.p, n, h->d_bel,
                                                      h->d_rows.p);
     count_launch();
     PP2D_CUDA(cudaGetLastError());
@@ -1014,7 +1044,7 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                               cudaMemcpyHostToDevice, h->stream));
     dim3 grid((HW + 255) / 256, n);
-    pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(HW, h->cap, h->d_slots.p, n,
+    pomdp_scatter_kernel<<<grid, 256, 0, h->stream>>>(HW, h->d_slots.p, n,
                                                       h->d_rows.p, h->d_bel);
     count_launch();
     dim3 vgrid((n + kEvM - 1) / kEvM, (h->ncol + kEvN - 1) / kEvN);
@@ -1022,9 +1052,10 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     for (uint32_t i = 0; i < n && !dense; ++i)
       dense = !zero_on_dead_cells(h, beliefs + (size_t)i * HW);
     const InnerDim in = inner_dim(h, dense);
-    pomdp_values_kernel<<<vgrid, 256, 0, h->stream>>>(in.K, in.kidx, h->cap, h->ld, h->ncol,
-                                                      h->d_slots.p, n, h->d_bel,
-                                                      in.alpha, h->d_vals.p);
+    pomdp_values_kernel<false><<<vgrid, 256, 0, h->stream>>>(in.K, in.kidx, h->HW, h->ld,
+                                                             h->ncol, h->d_slots.p, n, h->d_bel,
+                                                             in.alpha, h->d_vals.p, nullptr,
+                                                             nullptr, nullptr, 0);
     count_launch();
     pomdp_bounds_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(n, h->ncol, h->n_pbvi,
                                                                 h->d_vals.p, h->d_out.p);
@@ -1079,6 +1110,29 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     double tr = now_s();
     for (size_t i = 0; i < gn; ++i) { store[i].rng.seed(1); trees[i] = &store[i]; }
     PP2D_TRY(make_roots(h, trees, beliefs + g0 * (size_t)h->HW));
+    // The trees are planned in the order of their start beliefs' modes (column,
+    // then row): neighbours in that order have overlapping supports, which is
+    // what makes the per-tile inner rows of the values launches short
+    // (pomdp_support_flags_kernel).  Only the order of the work changes: every query
+    // owns its rand() stream and its results land at its own index.
+    const bool sorted = h->sort_queries && gn >= 2 * (size_t)kEvM;
+    if (sorted) {
+      const int gni0 = (int)gn;
+      std::vector<uint32_t> key(gn);
+#pragma omp parallel for schedule(static) num_threads(host_threads()) if (gni0 >= 64)
+      for (int i = 0; i < gni0; ++i) {
+        const float* b = beliefs + (g0 + (size_t)i) * (size_t)h->HW;
+        int best = 0;
+        for (int s = 1; s < h->HW; ++s)
+          if (b[s] > b[best]) best = s;
+        key[i] = (uint32_t)(best % h->W) * (uint32_t)h->H + (uint32_t)(best / h->W);
+      }
+      std::vector<int> order(gn);
+      for (size_t i = 0; i < gn; ++i) order[i] = (int)i;
+      std::stable_sort(order.begin(), order.end(),
+                       [&](int a, int b) { return key[a] < key[b]; });
+      for (size_t i = 0; i < gn; ++i) trees[i] = &store[order[i]];
+    }
     h->t_phase[5] += now_s() - tr;               // roots: upload + bounds
     // Groups of trees a fraction of a round apart: while the device runs the
     // Bayes / bounds launches of one group, the host absorbs the previous round
@@ -1100,6 +1154,21 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
       first_tree[g] = gn * (size_t)g / (size_t)G;
     }
     first_tree[G] = gn;
+    if (sorted && G > 1) {
+      // Sorted trees are dealt to the groups in blocks of 16: every group then
+      // spans the whole map (trees far from the goal grow more children than
+      // those next to it; thirds of the sorted order would be unequal rounds)
+      // while the neighbours inside a group stay neighbours.
+      constexpr size_t kDeal = 16;
+      std::vector<Tree*> dealt;
+      dealt.reserve(gn);
+      for (int g = 0; g < G; ++g) {
+        first_tree[g] = dealt.size();
+        for (size_t b0 = (size_t)g * kDeal; b0 < gn; b0 += (size_t)G * kDeal)
+          for (size_t i = b0; i < std::min(gn, b0 + kDeal); ++i) dealt.push_back(trees[i]);
+      }
+      trees.swap(dealt);
+    }
     std::vector<Tree*> active;
     auto any_more = [&]() { for (int g = 0; g < G; ++g) if (more[g]) return true; return false; };
     for (uint32_t it = 0; it < max_iter && any_more(); ++it) {
@@ -1263,7 +1332,7 @@ int pp2d_tree_update(pp2d_tree* tt, uint8_t a, uint8_t z) {
       PP2D_TRY(h->d_slots.ensure(1));
       PP2D_CUDA(cudaMemcpyAsync(h->d_items.p, &it, sizeof(it), cudaMemcpyHostToDevice, h->stream));
       dim3 bgrid(1, (h->HW + 7) / 8);
-      pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->cap, h->d_tp, h->d_mp,
+      pomdp_bayes_kernel<<<bgrid, 256, 0, h->stream>>>(h->H, h->W, h->d_tp, h->d_mp,
                                                        h->d_items.p, 1, h->d_bel, h->d_bel);
       count_launch();
       h->n_bayes++;

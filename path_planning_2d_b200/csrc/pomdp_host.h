@@ -16,6 +16,14 @@ extern std::atomic<uint64_t> g_launches;
 inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct BayesItem { int src, dst; uint8_t act, obs; };
+
+// Belief pool layout (see the header of pomdp_kernels.cuh): blocks of 32
+// slots, inside a block cell-major.  Offset of (cell, slot); the column of
+// `slot` is bel_off(HW, 0, slot) + cell * kSlotBlock.
+constexpr int kSlotBlock = 32;
+__host__ __device__ __forceinline__ size_t bel_off(int HW, int cell, int slot) {
+  return ((size_t)(slot >> 5) * (size_t)HW + (size_t)cell) * kSlotBlock + (size_t)(slot & 31);
+}
 }  // namespace pp2d
 
 #define PP2D_CUDA(expr)                                                      \
@@ -107,6 +115,11 @@ struct pp2d_pomdp {
   float* d_alpha_live = nullptr;
   int K = 0;
   bool skip_dead = true;                   // PP2D_POMDP_DENSE=1 turns the skipping off
+  bool alphas_finite = true;               // every bound finite (else nothing is skipped)
+  // batched planner: per-tile inner rows of the values launches
+  // (PP2D_POMDP_TILE_SUPPORT=0 off) and queries planned in the order of their
+  // start beliefs' modes (PP2D_POMDP_SORT=0 off)
+  bool tile_support = true, sort_queries = true;
   std::vector<uint8_t> fib_actions, pbvi_actions;
   bool have_alphas = false;
   // belief pool [HW][cap]

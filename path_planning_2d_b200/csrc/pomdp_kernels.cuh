@@ -5,10 +5,15 @@
 //   fib       = src/pomdp/fast_informed_bound_cuda.cu
 //   tree      = src/pomdp/search_tree_cuda.cu
 //
-// Layout: every belief of a batch is a COLUMN of one matrix
-//   bel[s * cap + slot]      s = cell (y*W+x), slot = belief id, cap % 32 == 0
+// Layout: every belief of a batch is a COLUMN of a pool cut into blocks of 32
+// slots (belief ids), inside a block cell-major:
+//   bel[((slot / 32) * HW + s) * 32 + slot % 32]      s = cell (y*W+x)
 // so that "one thread per belief, sequential over the cells" kernels are
-// coalesced.  That shape is what makes bit-exact parity possible: the
+// coalesced (32 neighbouring slots of a cell are one 128-byte line) AND a
+// belief stays inside one HW * 128-byte region: with one [HW][cap] matrix the
+// cells of a column were cap * 4 bytes apart -- 4 000 different pages for the
+// 43 GB pool of a 1 250-query batch -- and every kernel that walks a column
+// waited on the TLB.  That shape is what makes bit-exact parity possible: the
 // reference normalises, prefix-sums and takes inner products with sequential
 // single-accumulator float loops on the host (tree:226-229, 326-328,
 // fib:289-292, pbvi:689-694).  Here each of those loops is run by one thread
@@ -131,7 +136,7 @@ __global__ void pomdp_dead_cells_kernel(int H, int W, const float* __restrict__ 
 // (BayesItem is declared in pomdp_host.h)
 
 __global__ void __launch_bounds__(256)
-pomdp_bayes_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
+pomdp_bayes_kernel(int H, int W, const float* __restrict__ trans_prob,
                    const float* __restrict__ meas_prob,
                    const BayesItem* __restrict__ items, int n_items,
                    const float* bel_in, float* bel_out) {
@@ -150,54 +155,66 @@ pomdp_bayes_kernel(int H, int W, int cap, const float* __restrict__ trans_prob,
     if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
     const size_t sidx = (size_t)sy * W + sx;
     const float tp = __ldg(trans_prob + 81 * sidx + 9 * it.act + (8 - s));
-    const float b = bel_in[sidx * cap + it.src];
+    const float b = bel_in[bel_off(H * W, (int)sidx, it.src)];
     if (s < 8) p = fma_ftz(tp, b, p);
     else p = add_ftz(p, mul_ftz(tp, b));
   }
   p = mul_ftz(p, __ldg(meas_prob + 16 * (size_t)cell + it.obs));
-  bel_out[(size_t)cell * cap + it.dst] = p;
+  bel_out[bel_off(H * W, cell, it.dst)] = p;
 }
 
 // The children of one Q node (same parent belief, same action) differ only in
 // the observation: the predicted belief sum_s P(s,u,s') b(s) is computed once
-// per (Q node, cell).  group g: children items[first[g] .. first[g+1]) (all
-// with the src / act of the group's first item); threadIdx.x runs over groups,
-// so the 9 Q nodes of one expanded node read the same belief addresses.
-// Bayes update, column sum and division of a round without ever storing the
-// un-normalised children: the prediction of a Q node is written
-// once to pred[cell * ngp + g]; the sequential sum of a child and its
-// normalised belief are both formed from pred * L on the fly.  Per element the
-// operations are those of pomdp_bayes_kernel + pomdp_colsum_kernel +
+// per (Q node, cell).  Bayes update, column sum and division of a round
+// without ever storing the un-normalised children: the prediction of a Q node
+// is written once to pred[cell * ngp + g]; the sequential sum of a child and
+// its normalised belief are both formed from pred * L on the fly.  Per element
+// the operations are those of pomdp_bayes_kernel + pomdp_colsum_kernel +
 // pomdp_scale_kernel (FMUL.FTZ by the likelihood, sequential rounded adds,
 // IEEE division), so the bits are the same; the traffic drops from
 // 4 x |children| to 2 x |Q nodes| + 1 x |children| belief-sized passes.
+//
+// Group g = 9 * i + a is action a of expanded node i (column slots[i]): one
+// thread per (node, target cell) reads the 9 neighbour beliefs ONCE and runs
+// the 9 action chains (pomdp_bayes_kernel's) on them.  Lanes run over nodes,
+// so the transition probabilities are warp-uniform loads, one broadcast each
+// (with one thread per (group, cell) and lanes over groups every load was 3-4
+// wavefronts, the belief was read 9 times and the L1 pipe bounded the kernel).
+// Only the K target cells listed in kidx are predicted: on the others (cells
+// no mass can enter, belief +0) the prediction is +0 and nobody reads it --
+// pomdp_child_sum_kernel walks the same list and pomdp_child_write_kernel
+// writes those cells without it.  kidx = identity: every cell.
 __global__ void __launch_bounds__(256)
-pomdp_predict_kernel(int H, int W, int K, const int* __restrict__ kidx, int cap, int ngp,
-                     const float* __restrict__ trans_prob,
-                     const BayesItem* __restrict__ items, const int* __restrict__ first,
-                     int n_groups, const float* __restrict__ bel, float* __restrict__ pred) {
-  // Only the K target cells listed in kidx are predicted: on the others (cells
-  // no mass can enter, belief +0) the prediction is +0 and nobody reads it --
-  // pomdp_child_sum_kernel walks the same list and pomdp_child_write_kernel
-  // writes those cells without it.  kidx = identity: every cell.
-  const int g = blockIdx.x * 32 + (threadIdx.x & 31);
+pomdp_predict9_kernel(int H, int W, int K, const int* __restrict__ kidx, int ngp,
+                      const float* __restrict__ trans_prob, const int* __restrict__ slots,
+                      int n, const float* __restrict__ bel, float* __restrict__ pred) {
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);
   const int kc = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (g >= n_groups || kc >= K) return;
+  if (kc >= K) return;                             // warp-uniform
   const int cell = __ldg(kidx + kc);
-  const BayesItem it = items[first[g]];
   const int x = cell % W, y = cell / W;
-  float p = 0.0f;
+  const float* col = bel + bel_off(H * W, 0, slots[min(i, n - 1)]);
+  float b[9];
 #pragma unroll
   for (int s = 0; s < 9; ++s) {
     const int sx = x + s % 3 - 1, sy = y + s / 3 - 1;
-    if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
-    const size_t sidx = (size_t)sy * W + sx;
-    const float tp = __ldg(trans_prob + 81 * sidx + 9 * it.act + (8 - s));
-    const float b = bel[sidx * cap + it.src];
-    if (s < 8) p = fma_ftz(tp, b, p);
-    else p = add_ftz(p, mul_ftz(tp, b));
+    const bool in = !(sx < 0 || sx >= W || sy < 0 || sy >= H);   // warp-uniform
+    b[s] = in ? col[(size_t)(sy * W + sx) * kSlotBlock] : 0.0f;
   }
-  pred[(size_t)cell * ngp + g] = p;
+  float* out = pred + (size_t)cell * ngp + (size_t)i * 9;
+#pragma unroll
+  for (int a = 0; a < 9; ++a) {
+    float p = 0.0f;
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+      const int sx = x + s % 3 - 1, sy = y + s / 3 - 1;
+      if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
+      const float tp = __ldg(trans_prob + 81 * (size_t)(sy * W + sx) + 9 * a + (8 - s));
+      if (s < 8) p = fma_ftz(tp, b[s], p);
+      else p = add_ftz(p, mul_ftz(tp, b[s]));
+    }
+    if (i < n) out[a] = p;
+  }
 }
 
 // sums[k] = accumulate over cells of pred * L(., z_k), in cell order.  Only
@@ -291,19 +308,38 @@ pomdp_child_sum_kernel(int K, const int* __restrict__ kidx, int ngp,
 // child belief = (pred * L) / sum, written once into its pool column.  dead
 // (may be NULL = no cell is skipped): cells whose prediction is +0 by
 // construction and was not computed: (+0 * L) / sum.
+constexpr int kCwCells = 8;      // cells per thread: their loads are in flight together
 __global__ void __launch_bounds__(256)
-pomdp_child_write_kernel(int HW, int cap, int ngp, const float* __restrict__ meas_prob,
+pomdp_child_write_kernel(int HW, int ngp, const float* __restrict__ meas_prob,
                          const uint8_t* __restrict__ dead,
                          const BayesItem* __restrict__ items, const int* __restrict__ kgroup,
                          int n, const float* __restrict__ pred, const float* __restrict__ sums,
                          float* __restrict__ bel) {
   const int k = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int cell = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (k >= n || cell >= HW) return;
+  const int cell0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kCwCells;
+  if (k >= n || cell0 >= HW) return;
   const BayesItem it = items[k];
-  const float p = (dead != nullptr && dead[cell]) ? 0.0f : pred[(size_t)cell * ngp + kgroup[k]];
-  const float v = mul_ftz(p, __ldg(meas_prob + 16 * (size_t)cell + it.obs));
-  bel[(size_t)cell * cap + it.dst] = __fdiv_rn(v, sums[k]);
+  const float sum = sums[k];
+  const float* pc = pred + kgroup[k];
+  const float* L = meas_prob + it.obs;
+  float p[kCwCells], l[kCwCells];
+#pragma unroll
+  for (int j = 0; j < kCwCells; ++j) {
+    const int cell = min(cell0 + j, HW - 1);
+    p[j] = (dead != nullptr && dead[cell]) ? 0.0f : pc[(size_t)cell * ngp];
+    l[j] = __ldg(L + 16 * (size_t)cell);
+  }
+  // (+-0) / sum == +-0 for a sum > 0: the IEEE division (a dozen instructions)
+  // is skipped on the cells outside the child's support -- the dead cells and
+  // most of the map -- which whole warps share (a warp is 32 children of one or
+  // two trees on one cell).
+  const bool pos = sum > 0.0f;
+#pragma unroll
+  for (int j = 0; j < kCwCells; ++j) {
+    if (cell0 + j >= HW) break;
+    const float v = mul_ftz(p[j], l[j]);
+    bel[bel_off(HW, cell0 + j, it.dst)] = (v == 0.0f && pos) ? v : __fdiv_rn(v, sum);
+  }
 }
 
 // ---------------------------------------------------------------- B3 -------
@@ -312,32 +348,32 @@ pomdp_child_write_kernel(int HW, int cap, int ngp, const float* __restrict__ mea
 // The sum is a serial chain of float adds by construction; the loads are
 // issued 32 at a time so that memory latency overlaps.
 __global__ void __launch_bounds__(128)
-pomdp_colsum_kernel(int HW, int cap, const int* __restrict__ slots, int n,
+pomdp_colsum_kernel(int HW, const int* __restrict__ slots, int n,
                     const float* __restrict__ bel, float* __restrict__ sums) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float* col = bel + slots[i];
+  const float* col = bel + bel_off(HW, 0, slots[i]);
   float sum = 0.0f;
   int s = 0;
   for (; s + 32 <= HW; s += 32) {
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = col[(size_t)(s + j) * cap];
+    for (int j = 0; j < 32; ++j) v[j] = col[(size_t)(s + j) * kSlotBlock];
 #pragma unroll
     for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, v[j]);
   }
-  for (; s < HW; ++s) sum = __fadd_rn(sum, col[(size_t)s * cap]);
+  for (; s < HW; ++s) sum = __fadd_rn(sum, col[(size_t)s * kSlotBlock]);
   sums[i] = sum;
 }
 
 // b /= sum for every cell of every listed column (tree:228-229), IEEE division.
 __global__ void __launch_bounds__(256)
-pomdp_scale_kernel(int HW, int cap, const int* __restrict__ slots, int n,
+pomdp_scale_kernel(int HW, const int* __restrict__ slots, int n,
                    const float* __restrict__ sums, float* __restrict__ bel) {
   const int i = blockIdx.x * 32 + (threadIdx.x & 31);
   const int s = blockIdx.y * 8 + (threadIdx.x >> 5);
   if (i >= n || s >= HW) return;
-  const size_t q = (size_t)s * cap + slots[i];
+  const size_t q = bel_off(HW, s, slots[i]);
   bel[q] = __fdiv_rn(bel[q], sums[i]);
 }
 
@@ -347,28 +383,56 @@ pomdp_scale_kernel(int HW, int cap, const int* __restrict__ slots, int n,
 // addresses are a pool row apart, so all 32 loads are in flight together),
 // then every lane replays the 32 adds in order from registers (shuffles) and
 // keeps the partial sum of its own cell.  prefix[i * HW + s].
-__global__ void __launch_bounds__(128)
-pomdp_prefix_kernel(int HW, int cap, const int* __restrict__ slots, int n,
-                    const float* __restrict__ bel, float* __restrict__ prefix) {
-  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (i >= n) return;
-  const float* col = bel + slots[i];
-  float* out = prefix + (size_t)i * HW;
+constexpr int kSeqDepth = 8;     // chunks of 32 cells requested ahead of the add chain
+// (body shared with pomdp_expand_kernel; one warp, belief column `col`)
+// The 32 values of a chunk reach every lane through the warp's 128 bytes of
+// shared memory (one store, 8 broadcast LDS.128) rather than 32 shuffles: the
+// shuffle unit, one per SM, was what bounded this kernel.
+__device__ __forceinline__ void prefix_body(int HW, int lane, const float* __restrict__ col,
+                                            float* __restrict__ out, float* __restrict__ sw) {
   float acc = 0.0f;
-  float nxt = lane < HW ? col[(size_t)lane * cap] : 0.0f;
-  for (int s0 = 0; s0 < HW; s0 += 32) {
-    const float v = nxt;
-    const int sn = s0 + 32 + lane;
-    nxt = sn < HW ? col[(size_t)sn * cap] : 0.0f;      // next chunk while this one is summed
-    float mine = 0.0f;
-    const int cnt = min(32, HW - s0);
-    for (int j = 0; j < cnt; ++j) {
-      acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, j));
-      if (j == lane) mine = acc;
-    }
-    if (lane < cnt) out[s0 + lane] = mine;
+  // The chain of adds is serial by construction; what can overlap is the memory
+  // latency: kSeqDepth chunks are in flight while one is summed.  Lanes past
+  // the end hold +0 and acc + 0 == acc, so every chunk replays all 32 adds
+  // (no trip count, fully unrolled: the dependent FADD is the only latency).
+  float nxt[kSeqDepth];
+#pragma unroll
+  for (int d = 0; d < kSeqDepth; ++d) {
+    const int sn = d * 32 + lane;
+    nxt[d] = sn < HW ? col[(size_t)sn * kSlotBlock] : 0.0f;
   }
+  for (int s0 = 0; s0 < HW; s0 += 32 * kSeqDepth) {
+#pragma unroll
+    for (int d = 0; d < kSeqDepth; ++d) {
+      const int c0 = s0 + d * 32;
+      if (c0 >= HW) break;                         // warp-uniform
+      __syncwarp();                                // the previous chunk has been read
+      sw[lane] = nxt[d];
+      __syncwarp();
+      const int sn = c0 + 32 * kSeqDepth + lane;
+      nxt[d] = sn < HW ? col[(size_t)sn * kSlotBlock] : 0.0f;
+      float mine = 0.0f;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 t = *reinterpret_cast<const float4*>(sw + 4 * j4);
+        acc = __fadd_rn(acc, t.x); mine = (4 * j4 + 0 == lane) ? acc : mine;
+        acc = __fadd_rn(acc, t.y); mine = (4 * j4 + 1 == lane) ? acc : mine;
+        acc = __fadd_rn(acc, t.z); mine = (4 * j4 + 2 == lane) ? acc : mine;
+        acc = __fadd_rn(acc, t.w); mine = (4 * j4 + 3 == lane) ? acc : mine;
+      }
+      if (c0 + lane < HW) out[c0 + lane] = mine;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+pomdp_prefix_kernel(int HW, const int* __restrict__ slots, int n,
+                    const float* __restrict__ bel, float* __restrict__ prefix) {
+  __shared__ __align__(16) float sw[4][32];
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  prefix_body(HW, threadIdx.x & 31, bel + bel_off(HW, 0, slots[i]), prefix + (size_t)i * HW,
+              sw[threadIdx.x >> 5]);
 }
 
 // The 2*n uniforms cudaForwardSampling consumes (tree:84-92, 117, 134):
@@ -454,15 +518,140 @@ constexpr int kEvM = 128, kEvN = 128, kEvK = 16, kEvPad = 4;
 // dense product; with the live cells only (pomdp_dead_cells_kernel) every
 // belief of the launch must be +0 on the cells left out, and the result is
 // bit-identical: the skipped terms are acc + (+-0).
+//
+// TILED: every tile of kEvM beliefs walks its OWN ascending list of inner rows
+// (pomdp_support_kernel: the rows on which at least one belief of the tile is
+// non-zero; tlist[tile * tstride + i] = {cell, row of alpha}, tcount[tile]
+// entries).  On a row left out all kEvM beliefs are +-0, the products are +-0
+// for finite alpha and acc + (+-0) == acc -- an accumulator that starts at +0
+// never becomes -0 under round-to-nearest -- so the bits do not change.  The
+// beliefs of a tree are spatially compact (a Gaussian start belief widened by
+// one cell per step) and a batch is planned in the order of the start
+// beliefs' modes, so a tile touches about half of the live cells.
+// Per-tile list of inner rows (see TILED above), two launches.
+// pomdp_support_flags_kernel: CTA (tile, chunk of 256 rows): every warp tests
+// 32 rows (all kEvM beliefs of the tile per row, 4 per lane, 32 loads in flight
+// per lane) and writes one 32-bit mask: tmask[tile * mstride + chunk * 8 + warp].
+__global__ void __launch_bounds__(256)
+pomdp_support_flags_kernel(int HW, int K, const int* __restrict__ kidx,
+                           const int* __restrict__ slots, int n,
+                           const float* __restrict__ bel, uint32_t* __restrict__ tmask,
+                           int mstride) {
+  __shared__ int sslot[kEvM];
+  const int tile = blockIdx.x, m0 = tile * kEvM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // (the padding of the last tile repeats one of its members)
+  if (tid < kEvM) sslot[tid] = slots[min(m0 + tid, n - 1)];
+  __syncthreads();
+  const float* c0 = bel + bel_off(HW, 0, sslot[lane]);
+  const float* c1 = bel + bel_off(HW, 0, sslot[lane + 32]);
+  const float* c2 = bel + bel_off(HW, 0, sslot[lane + 64]);
+  const float* c3 = bel + bel_off(HW, 0, sslot[lane + 96]);
+  const int r0 = blockIdx.y * 256 + warp * 32;     // this warp's 32 rows
+  if (r0 >= K) return;                             // (warp-uniform; its mask word is never read)
+  const int myrow = r0 + lane;
+  const int mycell = myrow < K ? __ldg(kidx + myrow) : 0;
+  uint32_t mask = 0;
+#pragma unroll
+  for (int j0 = 0; j0 < 32; j0 += 8) {
+    float v[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cell = __shfl_sync(0xffffffffu, mycell, j0 + j);
+      const size_t q = (size_t)cell * kSlotBlock;
+      v[j][0] = c0[q]; v[j][1] = c1[q]; v[j][2] = c2[q]; v[j][3] = c3[q];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // (NaN != 0: a row holding a NaN is kept)
+      const bool nz = v[j][0] != 0.0f || v[j][1] != 0.0f || v[j][2] != 0.0f || v[j][3] != 0.0f;
+      if (__any_sync(0xffffffffu, nz) && r0 + j0 + j < K) mask |= 1u << (j0 + j);
+    }
+  }
+  if (lane == 0) tmask[(size_t)tile * mstride + (r0 >> 5)] = mask;
+}
+
+// pomdp_support_list_kernel: one CTA per tile turns its ceil(K/32) mask words
+// into the ascending list tlist[tile * K + i] = {cell, row} and tcount[tile].
+__global__ void __launch_bounds__(256)
+pomdp_support_list_kernel(int K, const int* __restrict__ kidx,
+                          const uint32_t* __restrict__ tmask, int mstride,
+                          int2* __restrict__ tlist, int* __restrict__ tcount) {
+  __shared__ int wsum[8];
+  const int tile = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwords = (K + 31) / 32;
+  int2* out = tlist + (size_t)tile * K;
+  int base = 0;
+  for (int w0 = 0; w0 < nwords; w0 += 256) {
+    const int w = w0 + tid;
+    const uint32_t m = w < nwords ? tmask[(size_t)tile * mstride + w] : 0u;
+    const int cnt = __popc(m);
+    int incl = cnt;                                // inclusive scan over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int off = base + incl - cnt, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < warp) off += wsum[i];
+      total += wsum[i];
+    }
+    uint32_t rest = m;
+    while (rest) {
+      const int b = __ffs(rest) - 1;
+      rest &= rest - 1;
+      const int row = w * 32 + b;
+      out[off++] = make_int2(__ldg(kidx + row), row);
+    }
+    base += total;
+    __syncthreads();
+  }
+  if (tid == 0) tcount[tile] = base;
+}
+
+// Tiles in descending order of their row counts (ties: ascending tile):
+// torder[rank] = tile.  The TILED values launch maps blockIdx.y = rank, so the
+// longest tiles start first and the last wave of CTAs is made of the shortest
+// ones (a launch is only ~1.4 waves long).
+__global__ void __launch_bounds__(256)
+pomdp_tile_order_kernel(int ntiles, const int* __restrict__ tcount, int* __restrict__ torder) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntiles) return;
+  const int ci = tcount[i];
+  int rank = 0;
+  for (int j = 0; j < ntiles; ++j) {
+    const int cj = __ldg(tcount + j);
+    rank += (cj > ci || (cj == ci && j < i)) ? 1 : 0;
+  }
+  torder[rank] = i;
+}
+
+// Grid: untiled (ceil(n / kEvM), column tiles); TILED (column tiles, ceil(n /
+// kEvM)) with the belief tile = torder[blockIdx.y].
+template <bool TILED>
 __global__ void __launch_bounds__(256, 2)
-pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cap, int ld, int ncol,
+pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cells, int ld, int ncol,
                     const int* __restrict__ slots, int n,
                     const float* __restrict__ bel,
-                    const float* __restrict__ alpha, float* __restrict__ out) {
+                    const float* __restrict__ alpha, float* __restrict__ out,
+                    const int2* __restrict__ tlist, const int* __restrict__ tcount,
+                    const int* __restrict__ torder, int tstride) {
+  const int mtile = TILED ? torder[blockIdx.y] : (int)blockIdx.x;
+  const int ntile = TILED ? (int)blockIdx.x : (int)blockIdx.y;
+  if constexpr (TILED) {
+    // (HW is a by-value parameter: from here on it is this tile's row count)
+    tlist += (size_t)mtile * tstride;
+    HW = tcount[mtile];
+  }
   __shared__ __align__(16) float sb[2][kEvK][kEvM + kEvPad];
   __shared__ __align__(16) float sa[2][kEvK][kEvN + kEvPad];
   __shared__ int sslot[kEvM];
-  const int m0 = blockIdx.x * kEvM, n0 = blockIdx.y * kEvN;
+  const int m0 = mtile * kEvM, n0 = ntile * kEvN;
   const int tid = threadIdx.x;
   if (tid < kEvM) sslot[tid] = (m0 + tid < n) ? slots[m0 + tid] : slots[0];
   __syncthreads();
@@ -477,20 +666,24 @@ pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cap, int ld, int n
   // Rows past it are clamped to the last row: they are never accumulated (the
   // k loop stops at HW), only kept in bounds.  Columns past ncol read the zero
   // padding of alpha (ld is a multiple of 128).
+  // (tid + e * 256) % kEvM does not depend on e: every thread stages one belief
+  static_assert(256 % kEvM == 0, "one belief column per thread");
+  const float* bcol = bel + bel_off(cells, 0, sslot[tid % kEvM]);
   auto load_tiles = [&](int buf, int k0) {
 #pragma unroll
     for (int e = 0; e < (kEvK * kEvM) / 256; ++e) {
       const int idx = tid + e * 256;
       const int kk = idx / kEvM, mm = idx % kEvM;
-      const int s = __ldg(kidx + min(k0 + kk, HW - 1));
+      const int s = TILED ? __ldg(tlist + min(k0 + kk, HW - 1)).x
+                          : __ldg(kidx + min(k0 + kk, HW - 1));
       cp_async<4>((uint32_t)__cvta_generic_to_shared(&sb[buf][kk][mm]),
-                  bel + (size_t)s * cap + sslot[mm]);
+                  bcol + (size_t)s * kSlotBlock);
     }
 #pragma unroll
     for (int e = 0; e < (kEvK * kEvN / 4) / 256; ++e) {
       const int idx = tid + e * 256;
       const int kk = idx / (kEvN / 4), nn = (idx % (kEvN / 4)) * 4;
-      const int s = min(k0 + kk, HW - 1);
+      const int s = TILED ? __ldg(tlist + min(k0 + kk, HW - 1)).y : min(k0 + kk, HW - 1);
       cp_async<16>((uint32_t)__cvta_generic_to_shared(&sa[buf][kk][nn]),
                    alpha + (size_t)s * ld + n0 + nn);
     }
@@ -498,7 +691,7 @@ pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cap, int ld, int n
   };
 
   const int nchunks = (HW + kEvK - 1) / kEvK;
-  load_tiles(0, 0);
+  if (nchunks > 0) load_tiles(0, 0);               // (a tile of all-zero beliefs has no rows)
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
     if (c + 1 < nchunks) {
@@ -538,37 +731,90 @@ pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cap, int ld, int n
 }
 
 // tree:168-173: reward[i][a] = inner_product(b_i, R(:,a), 0.0f) for the nodes
-// being expanded: one WARP per (belief, action).  The lanes fetch and multiply
-// 32 consecutive cells, then every lane replays the 32 rounded adds in order
-// (the same sequential multiply-then-add chain as pomdp_values_kernel).
-// stage_reward is the reference table [HW][9].
-__global__ void __launch_bounds__(128)
-pomdp_rewards_kernel(int K, const int* __restrict__ kidx, int cap,
-                     const int* __restrict__ slots, int n,
-                     const float* __restrict__ bel, const float* __restrict__ stage_reward,
-                     float* __restrict__ out) {
-  // cells kidx[0..K) only (ascending): the belief is +0 on the others and
-  // acc + (+0 * r) == acc (see pomdp_dead_cells_kernel)
-  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (w >= n * 9) return;
-  const int a = w % 9, i = w / 9;
-  const float* col = bel + slots[i];
-  const float* r = stage_reward + a;
-  float acc = 0.0f;
-  int s = lane < K ? __ldg(kidx + lane) : 0;
-  float nb = lane < K ? col[(size_t)s * cap] : 0.0f;
-  float nr = lane < K ? __ldg(r + (size_t)s * 9) : 0.0f;
-  for (int c0 = 0; c0 < K; c0 += 32) {
-    const float p = __fmul_rn(nb, nr);
-    const int cn = c0 + 32 + lane;
-    s = cn < K ? __ldg(kidx + cn) : 0;
-    nb = cn < K ? col[(size_t)s * cap] : 0.0f;
-    nr = cn < K ? __ldg(r + (size_t)s * 9) : 0.0f;
-    const int cnt = min(32, K - c0);
-    for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, j));
+// being expanded: one WARP per (belief, 3 actions).  The lanes fetch and
+// multiply 32 consecutive cells, then every lane replays the 32 rounded adds in
+// order (the same sequential multiply-then-add chain as pomdp_values_kernel),
+// three independent chains interleaved, the products broadcast through shared
+// memory.  stage_reward is the reference table
+// [HW][9].
+// cells kidx[0..K) only (ascending): the belief is +0 on the others and
+// acc + (+0 * r) == acc (see pomdp_dead_cells_kernel); lanes past the end hold
+// +0 products for the same reason, so every chunk replays all 32 adds.
+constexpr int kRewDepth = 4;     // chunks in flight
+__device__ __forceinline__ void rewards_body(int K, const int* __restrict__ kidx,
+                                             int lane, const float* __restrict__ col,
+                                             const float* __restrict__ r3,
+                                             float* __restrict__ out3,
+                                             float* __restrict__ sw) {   // [3][32]
+  float acc[3] = {0.0f, 0.0f, 0.0f};
+  float nb[kRewDepth], nr[kRewDepth][3];
+#pragma unroll
+  for (int d = 0; d < kRewDepth; ++d) {
+    const int cn = d * 32 + lane;
+    const int s = cn < K ? __ldg(kidx + cn) : 0;
+    nb[d] = cn < K ? col[(size_t)s * kSlotBlock] : 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) nr[d][a] = cn < K ? __ldg(r3 + (size_t)s * 9 + a) : 0.0f;
   }
-  if (lane == 0) out[(size_t)i * 9 + a] = acc;
+  for (int s0 = 0; s0 < K; s0 += 32 * kRewDepth) {
+#pragma unroll
+    for (int d = 0; d < kRewDepth; ++d) {
+      const int c0 = s0 + d * 32;
+      if (c0 >= K) break;                          // warp-uniform
+      float p[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) p[a] = __fmul_rn(nb[d], nr[d][a]);
+      const int cn = c0 + 32 * kRewDepth + lane;
+      const int s = cn < K ? __ldg(kidx + cn) : 0;
+      nb[d] = cn < K ? col[(size_t)s * kSlotBlock] : 0.0f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) nr[d][a] = cn < K ? __ldg(r3 + (size_t)s * 9 + a) : 0.0f;
+      // products to all lanes through shared memory (see prefix_body)
+      __syncwarp();
+#pragma unroll
+      for (int a = 0; a < 3; ++a) sw[a * 32 + lane] = p[a];
+      __syncwarp();
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float4 t[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t[a] = *reinterpret_cast<const float4*>(sw + a * 32 + 4 * j4);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a] = __fadd_rn(acc[a], t[a].x);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a] = __fadd_rn(acc[a], t[a].y);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a] = __fadd_rn(acc[a], t[a].z);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a] = __fadd_rn(acc[a], t[a].w);
+      }
+    }
+  }
+  if (lane < 3) out3[lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
+}
+
+// Stage 1 of an expansion round in ONE launch: the prefix sums of the expanded
+// nodes (blocks [0, ceil(n/4))) and their 9 reward dots (the blocks after
+// them) do not depend on each other.
+__global__ void __launch_bounds__(128)
+pomdp_expand_kernel(int HW, int K, const int* __restrict__ kidx,
+                    const int* __restrict__ slots, int n, const float* __restrict__ bel,
+                    const float* __restrict__ stage_reward, float* __restrict__ prefix,
+                    float* __restrict__ rewards) {
+  __shared__ __align__(16) float sw[4][96];
+  const int nbp = (n + 3) / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((int)blockIdx.x < nbp) {
+    const int i = blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    prefix_body(HW, lane, bel + bel_off(HW, 0, slots[i]), prefix + (size_t)i * HW, sw[warp]);
+  } else {
+    const int w = (blockIdx.x - nbp) * 4 + warp;
+    if (w >= n * 3) return;
+    const int i = w / 3, a0 = (w % 3) * 3;
+    rewards_body(K, kidx, lane, bel + bel_off(HW, 0, slots[i]), stage_reward + a0,
+                 rewards + (size_t)i * 9 + a0, sw[warp]);
+  }
 }
 
 // Bounds of every evaluated belief from its row of values: first maximum over
@@ -673,23 +919,23 @@ pomdp_maxdiff_kernel(const float* __restrict__ a, float* __restrict__ b_and_copy
 }
 
 // Gather host-provided beliefs ([n][HW] row major) into belief columns.
-__global__ void pomdp_scatter_kernel(int HW, int cap, const int* __restrict__ slots,
+__global__ void pomdp_scatter_kernel(int HW, const int* __restrict__ slots,
                                      int n, const float* __restrict__ rows,
                                      float* __restrict__ bel) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
   if (s >= HW || i >= n) return;
-  bel[(size_t)s * cap + slots[i]] = rows[(size_t)i * HW + s];
+  bel[bel_off(HW, s, slots[i])] = rows[(size_t)i * HW + s];
 }
 
 // Belief columns back to [n][HW] rows.
-__global__ void pomdp_gather_kernel(int HW, int cap, const int* __restrict__ slots,
+__global__ void pomdp_gather_kernel(int HW, const int* __restrict__ slots,
                                     int n, const float* __restrict__ bel,
                                     float* __restrict__ rows) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
   if (s >= HW || i >= n) return;
-  rows[(size_t)i * HW + s] = bel[(size_t)s * cap + slots[i]];
+  rows[(size_t)i * HW + s] = bel[bel_off(HW, s, slots[i])];
 }
 
 }  // namespace pp2d

@@ -213,6 +213,45 @@ def test_plan_batch_at_bench_scale_equals_single_query_trees(monkeypatch):
         assert stats[i, 2] == ostats[4], i
 
 
+def test_per_tile_inner_rows_and_query_order_do_not_change_a_bit(monkeypatch):
+    """The values launches of a batch walk, per tile of 128 children, only the
+    inner rows on which some belief of the tile is non-zero, and the queries
+    are planned in the order of their start beliefs' modes so that those lists
+    are short.  Both are exact: with either or both switched off
+    (PP2D_POMDP_TILE_SUPPORT=0, PP2D_POMDP_SORT=0) every action, value bit and
+    tree statistic is the same -- and equals the oracle's for a sample."""
+    name, goal = "sparse_map_100x40", (95, 34)
+    grid = cases.load_bundled(name)
+    fib, pbvi, fa, pa = pf.bundled_alphas(60)
+    n = 300
+    beliefs = pf.gaussian_beliefs(grid, n, sigma=2.0, seed=3)
+    # a start belief that is zero nowhere on the free cells, and one point mass
+    free = np.flatnonzero(grid.reshape(-1) == 0)
+    beliefs[5] = 0
+    beliefs[5, free] = np.float32(1.0 / len(free))
+    beliefs[6] = 0
+    beliefs[6, free[1234]] = 1
+    results = []
+    for tile, sort in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
+        monkeypatch.setenv("PP2D_POMDP_TILE_SUPPORT", tile)
+        monkeypatch.setenv("PP2D_POMDP_SORT", sort)
+        with PomdpPathPlanning2d(grid, goal, cases.GAMMA) as p:
+            p.set_alphas(fib, pbvi, fa, pa)
+            results.append(p.plan_batch(beliefs, max_depth=50, max_iter=6, with_stats=True))
+    acts, vals, stats = results[0]
+    for a, v, s in results[1:]:
+        assert np.array_equal(a, acts) and np.array_equal(bits(v), bits(vals))
+        assert np.array_equal(s, stats)
+    m = po.Model(grid, goal)
+    for i in (0, 5, 6, 150, 299):
+        ot = po.Tree(m, cases.GAMMA, fib, pbvi, pf.uniforms(), beliefs[i], fa, pa)
+        oa, orr, ostats, rc = ot.plan(50, 6)
+        ot.close()
+        assert rc == 0 and acts[i] == oa, i
+        assert bits(np.float32(vals[i])) == bits(np.float32(orr)), i
+        assert stats[i, 0] == ostats[0] and stats[i, 1] == ostats[1], i
+
+
 @pytest.mark.parametrize("dense_env", ["0", "1"])
 def test_beliefs_with_mass_on_dead_cells_take_the_dense_products(monkeypatch, dense_env):
     """The sequential inner products skip the cells no probability mass can
