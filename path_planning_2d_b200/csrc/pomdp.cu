@@ -258,6 +258,17 @@ int refresh_live_cells(pp2d_pomdp* h) {
   if (!h->d_kidx_all) PP2D_CUDA(cudaMalloc(&h->d_kidx_all, HW * sizeof(int)));
   PP2D_CUDA(cudaMemcpy(h->d_kidx, live.data(), live.size() * sizeof(int), cudaMemcpyHostToDevice));
   PP2D_CUDA(cudaMemcpy(h->d_kidx_all, all.data(), HW * sizeof(int), cudaMemcpyHostToDevice));
+  // inverse list and the likelihood rows of the live cells (the Bayes kernels
+  // of a round index their scratch by live row, not by cell)
+  std::vector<int> kinv(HW, -1);
+  for (int k = 0; k < h->K; ++k) kinv[live[k]] = k;
+  if (!h->d_kinv) PP2D_CUDA(cudaMalloc(&h->d_kinv, HW * sizeof(int)));
+  PP2D_CUDA(cudaMemcpy(h->d_kinv, kinv.data(), HW * sizeof(int), cudaMemcpyHostToDevice));
+  if (!h->d_mp_live) PP2D_CUDA(cudaMalloc(&h->d_mp_live, (size_t)HW * 16 * sizeof(float)));
+  for (int k = 0; k < h->K; ++k)
+    PP2D_CUDA(cudaMemcpyAsync(h->d_mp_live + (size_t)k * 16, h->d_mp + (size_t)live[k] * 16,
+                              16 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  PP2D_CUDA(cudaStreamSynchronize(h->stream));
   if (h->have_alphas) {
     std::vector<float> rows((size_t)h->K * h->ld);
     for (int k = 0; k < h->K; ++k)
@@ -288,12 +299,13 @@ namespace {
 
 // The inner dimension of the sequential products of one launch: the live
 // cells, or all cells when some belief involved may be non-zero elsewhere.
-struct InnerDim { const int* kidx; int K; const float* alpha; const uint8_t* dead; };
+// kinv: cell -> inner row (-1: left out); mp: the likelihood rows of the inner rows.
+struct InnerDim { const int* kidx; int K; const float* alpha; const int* kinv; const float* mp; };
 InnerDim inner_dim(const pp2d_pomdp* h, bool dense) {
   // (a non-finite bound makes 0 * alpha a NaN in the reference: nothing is skipped then)
   if (dense || !h->skip_dead || !h->alphas_finite)
-    return {h->d_kidx_all, h->HW, h->d_alpha, nullptr};
-  return {h->d_kidx, h->K, h->d_alpha_live, h->d_dead};
+    return {h->d_kidx_all, h->HW, h->d_alpha, h->d_kidx_all, h->d_mp};
+  return {h->d_kidx, h->K, h->d_alpha_live, h->d_kinv, h->d_mp_live};
 }
 
 // Host threads for the per-tree work of a batch: pp2d_set_host_threads, else
@@ -634,10 +646,10 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
   count_launch();
   h->n_bayes += nk;
   pomdp_child_sum_kernel<<<(nk + 127) / 128, 128, 0, c.stream>>>(
-      in.K, in.kidx, ngp, h->d_mp, c.d_items.p, c.d_kgroup.p, nk, c.d_pred.p, c.d_sums.p);
+      in.K, ngp, in.mp, c.d_items.p, c.d_kgroup.p, nk, c.d_pred.p, c.d_sums.p);
   count_launch();
   dim3 sgrid((nk + 31) / 32, (HW + 8 * kCwCells - 1) / (8 * kCwCells));
-  pomdp_child_write_kernel<<<sgrid, 256, 0, c.stream>>>(HW, ngp, h->d_mp, in.dead,
+  pomdp_child_write_kernel<<<sgrid, 256, 0, c.stream>>>(HW, ngp, h->d_mp, in.kinv,
                                                          c.d_items.p, c.d_kgroup.p, nk,
                                                          c.d_pred.p, c.d_sums.p, h->d_bel);
   count_launch();
@@ -813,6 +825,7 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   cudaFree(h->d_map); cudaFree(h->d_tp); cudaFree(h->d_mp); cudaFree(h->d_sr);
   cudaFree(h->d_uniforms); cudaFree(h->d_alpha); cudaFree(h->d_bel);
   cudaFree(h->d_kidx); cudaFree(h->d_kidx_all); cudaFree(h->d_alpha_live); cudaFree(h->d_dead);
+  cudaFree(h->d_kinv); cudaFree(h->d_mp_live);
   h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();

@@ -112,6 +112,8 @@ struct pp2d_pomdp {
   int* d_kidx = nullptr;
   int* d_kidx_all = nullptr;
   uint8_t* d_dead = nullptr;               // device copy of the mask
+  int* d_kinv = nullptr;                   // cell -> its position in d_kidx, -1 for a dead cell
+  float* d_mp_live = nullptr;              // rows d_kidx[0..K) of the likelihood table [K][16]
   float* d_alpha_live = nullptr;
   int K = 0;
   bool skip_dead = true;                   // PP2D_POMDP_DENSE=1 turns the skipping off

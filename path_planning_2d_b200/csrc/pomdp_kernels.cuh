@@ -167,7 +167,8 @@ pomdp_bayes_kernel(int H, int W, const float* __restrict__ trans_prob,
 // the observation: the predicted belief sum_s P(s,u,s') b(s) is computed once
 // per (Q node, cell).  Bayes update, column sum and division of a round
 // without ever storing the un-normalised children: the prediction of a Q node
-// is written once to pred[cell * ngp + g]; the sequential sum of a child and
+// is written once to pred[row * ngp + g] (row = position of the cell in kidx);
+// the sequential sum of a child and
 // its normalised belief are both formed from pred * L on the fly.  Per element
 // the operations are those of pomdp_bayes_kernel + pomdp_colsum_kernel +
 // pomdp_scale_kernel (FMUL.FTZ by the likelihood, sequential rounded adds,
@@ -201,7 +202,7 @@ pomdp_predict9_kernel(int H, int W, int K, const int* __restrict__ kidx, int ngp
     const bool in = !(sx < 0 || sx >= W || sy < 0 || sy >= H);   // warp-uniform
     b[s] = in ? col[(size_t)(sy * W + sx) * kSlotBlock] : 0.0f;
   }
-  float* out = pred + (size_t)cell * ngp + (size_t)i * 9;
+  float* out = pred + (size_t)kc * ngp + (size_t)i * 9;   // scratch rows = inner rows
 #pragma unroll
   for (int a = 0; a < 9; ++a) {
     float p = 0.0f;
@@ -221,21 +222,21 @@ pomdp_predict9_kernel(int H, int W, int K, const int* __restrict__ kidx, int ngp
 // the K cells listed in kidx (ascending) are visited: the prediction is +0 on
 // the others and sum + (+0 * L) == sum (see pomdp_dead_cells_kernel); with
 // kidx = identity this is the plain loop over all HW cells.
-// PP2D_CHILD_SUM_ORDERED = 0 rebuilds the plain-load version of round 1.
-#ifndef PP2D_CHILD_SUM_ORDERED
-#define PP2D_CHILD_SUM_ORDERED 1
-#endif
 #ifndef PP2D_CS_BATCH
 #define PP2D_CS_BATCH 32
 #endif
-#if PP2D_CHILD_SUM_ORDERED
 // Register double buffer with ordered (volatile) loads: the operands of the
-// NEXT kCsBatch cells are requested before the current ones are added, so
+// NEXT kCsBatch rows are requested before the current ones are added, so
 // 2 * kCsBatch loads per thread are in flight during every batch.  (Plain
 // loads get interleaved with the adds by ptxas -- 40 registers, ~8 loads in
 // flight, long-scoreboard stall 22 per issue, 289 us per launch; this version
-// 132 us.  A cp.async ring through shared memory was no faster than the plain
-// version: 297 us.  Batch 8 / 16 / 32 cells: 217 / 132 / 86 us.)
+// 132 us; batch 8 / 16 / 32 rows: 217 / 132 / 86 us.  Staging the operands of
+// 128 children through shared memory with an 8-stage cp.async pipeline was
+// measured twice -- per-lane ring: 297 us; CTA tile [16 rows][groups + 16
+// likelihoods]: 70 us per launch but a slower batch, its 74 KB of shared
+// memory keep it from sharing an SM with the values launch of another group
+// -- and dropped.)  pred and mp_rows are indexed by inner row, not by cell:
+// an index load in front of every operand load was a dependent round trip.
 constexpr int kCsBatch = PP2D_CS_BATCH;
 __device__ __forceinline__ float ldg_f32_ordered(const float* p) {
   float v;
@@ -243,19 +244,18 @@ __device__ __forceinline__ float ldg_f32_ordered(const float* p) {
   return v;
 }
 __global__ void __launch_bounds__(128)
-pomdp_child_sum_kernel(int K, const int* __restrict__ kidx, int ngp,
-                       const float* __restrict__ meas_prob,
+pomdp_child_sum_kernel(int K, int ngp, const float* __restrict__ mp_rows,
                        const BayesItem* __restrict__ items, const int* __restrict__ kgroup,
                        int n, const float* __restrict__ pred, float* __restrict__ sums) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const float* pc = pred + kgroup[k];
-  const float* L = meas_prob + items[k].obs;
+  const float* L = mp_rows + items[k].obs;
   float v[2][kCsBatch], l[2][kCsBatch];
   auto request = [&](int buf, int c0) {
 #pragma unroll
     for (int j = 0; j < kCsBatch; ++j) {
-      const int s = __ldg(kidx + min(c0 + j, K - 1));        // clamped cells are not added
+      const int s = min(c0 + j, K - 1);                      // clamped rows are not added
       v[buf][j] = ldg_f32_ordered(pc + (size_t)s * ngp);
       l[buf][j] = ldg_f32_ordered(L + (size_t)s * 16);
     }
@@ -274,44 +274,13 @@ pomdp_child_sum_kernel(int K, const int* __restrict__ kidx, int ngp,
   }
   sums[k] = sum;
 }
-#else
-__global__ void __launch_bounds__(128)
-pomdp_child_sum_kernel(int K, const int* __restrict__ kidx, int ngp,
-                       const float* __restrict__ meas_prob,
-                       const BayesItem* __restrict__ items, const int* __restrict__ kgroup,
-                       int n, const float* __restrict__ pred, float* __restrict__ sums) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const float* pc = pred + kgroup[k];
-  const float* L = meas_prob + items[k].obs;
-  float sum = 0.0f;
-  int c = 0;
-  for (; c + 32 <= K; c += 32) {
-    float v[32], l[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int s = __ldg(kidx + c + j);
-      v[j] = pc[(size_t)s * ngp];
-      l[j] = __ldg(L + (size_t)s * 16);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, mul_ftz(v[j], l[j]));
-  }
-  for (; c < K; ++c) {
-    const int s = __ldg(kidx + c);
-    sum = __fadd_rn(sum, mul_ftz(pc[(size_t)s * ngp], __ldg(L + (size_t)s * 16)));
-  }
-  sums[k] = sum;
-}
-
-#endif
-// child belief = (pred * L) / sum, written once into its pool column.  dead
-// (may be NULL = no cell is skipped): cells whose prediction is +0 by
-// construction and was not computed: (+0 * L) / sum.
+// child belief = (pred * L) / sum, written once into its pool column.
+// kinv[cell] < 0: a cell whose prediction is +0 by construction and was not
+// computed: (+0 * L) / sum.
 constexpr int kCwCells = 8;      // cells per thread: their loads are in flight together
 __global__ void __launch_bounds__(256)
 pomdp_child_write_kernel(int HW, int ngp, const float* __restrict__ meas_prob,
-                         const uint8_t* __restrict__ dead,
+                         const int* __restrict__ kinv,
                          const BayesItem* __restrict__ items, const int* __restrict__ kgroup,
                          int n, const float* __restrict__ pred, const float* __restrict__ sums,
                          float* __restrict__ bel) {
@@ -326,7 +295,8 @@ pomdp_child_write_kernel(int HW, int ngp, const float* __restrict__ meas_prob,
 #pragma unroll
   for (int j = 0; j < kCwCells; ++j) {
     const int cell = min(cell0 + j, HW - 1);
-    p[j] = (dead != nullptr && dead[cell]) ? 0.0f : pc[(size_t)cell * ngp];
+    const int row = __ldg(kinv + cell);              // warp-uniform
+    p[j] = row < 0 ? 0.0f : pc[(size_t)row * ngp];
     l[j] = __ldg(L + 16 * (size_t)cell);
   }
   // (+-0) / sum == +-0 for a sum > 0: the IEEE division (a dozen instructions)
@@ -747,7 +717,11 @@ __device__ __forceinline__ void rewards_body(int K, const int* __restrict__ kidx
                                              float* __restrict__ out3,
                                              float* __restrict__ sw) {   // [3][32]
   float acc[3] = {0.0f, 0.0f, 0.0f};
+  // (the cell index of a request is itself loaded one round of the ring
+  // earlier: a dependent load inside the chunk loop stalls the in-order warp
+  // for a full memory latency per chunk)
   float nb[kRewDepth], nr[kRewDepth][3];
+  int sn[kRewDepth];
 #pragma unroll
   for (int d = 0; d < kRewDepth; ++d) {
     const int cn = d * 32 + lane;
@@ -755,6 +729,8 @@ __device__ __forceinline__ void rewards_body(int K, const int* __restrict__ kidx
     nb[d] = cn < K ? col[(size_t)s * kSlotBlock] : 0.0f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) nr[d][a] = cn < K ? __ldg(r3 + (size_t)s * 9 + a) : 0.0f;
+    const int c2 = cn + 32 * kRewDepth;
+    sn[d] = c2 < K ? __ldg(kidx + c2) : 0;
   }
   for (int s0 = 0; s0 < K; s0 += 32 * kRewDepth) {
 #pragma unroll
@@ -765,10 +741,12 @@ __device__ __forceinline__ void rewards_body(int K, const int* __restrict__ kidx
 #pragma unroll
       for (int a = 0; a < 3; ++a) p[a] = __fmul_rn(nb[d], nr[d][a]);
       const int cn = c0 + 32 * kRewDepth + lane;
-      const int s = cn < K ? __ldg(kidx + cn) : 0;
+      const int s = sn[d];
       nb[d] = cn < K ? col[(size_t)s * kSlotBlock] : 0.0f;
 #pragma unroll
       for (int a = 0; a < 3; ++a) nr[d][a] = cn < K ? __ldg(r3 + (size_t)s * 9 + a) : 0.0f;
+      const int c2 = cn + 32 * kRewDepth;
+      sn[d] = c2 < K ? __ldg(kidx + c2) : 0;
       // products to all lanes through shared memory (see prefix_body)
       __syncwarp();
 #pragma unroll
