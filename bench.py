@@ -313,10 +313,12 @@ def qv_tree_section(rank, world, with_cpu):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        w0 = p.work_counters()
         t0 = time.perf_counter()
         acts, vals, stats = p.plan_batch(mine, with_stats=True)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        w1 = p.work_counters()
         p_live = p.live_cells()
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -342,8 +344,10 @@ def qv_tree_section(rank, world, with_cpu):
     # multiply-add; the bound is the FP32 instruction issue rate, 128 lanes x
     # 148 SMs x SM clock (an FMUL or an FADD is one flop each).  Algorithmic
     # flops = V nodes x HW cells x (9 + n_pbvi) columns x 2; the kernel executes
-    # them over the live cells only (cells no probability mass can enter are
-    # skipped exactly), so `executed` is smaller.
+    # fewer: cells no probability mass can enter are skipped exactly, and every
+    # tile of 128 beliefs walks only the cells on which one of them is non-zero
+    # (also exact) -- `executed` counts the belief x cell products really done
+    # (pp2d_pomdp_work_counters), this rank's.
     hw = grid.size
     vnodes = float(stats[:, 0].sum()) * world
     ncols = 9 + pbvi.shape[0]
@@ -358,8 +362,9 @@ def qv_tree_section(rank, world, with_cpu):
     out["roofline"] = {
         "bound": "fp32_issue", "unit": "TFLOP/s (separately rounded FMUL + FADD)",
         "achieved": algo, "peak": peak, "frac": algo / peak,
-        "executed": vnodes * live * ncols * 2 / dt / 1e12,
+        "executed": float(w1[2] - w0[2]) * world * ncols * 2 / dt / 1e12,
         "live_cells": live, "cells": hw,
+        "cells_walked_per_belief": float(w1[2] - w0[2]) / max(1, w1[0] - w0[0]),
         "peak_what": "128 FP32 lanes x 148 SMs x SM clock x GPUs, one flop per instruction "
                      "(tools/ubench/fma_pipes.cu measures 109-119 of the 128 lanes/clk/SM "
                      "for scalar FP32 streams, profiles/r01_ubench_fma_pipes.txt)",

@@ -353,6 +353,13 @@ int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs);
  * when a start belief is uploaded) take the dense products.  mask: HW bytes,
  * 1 = live (may be NULL); count: number of live cells (may be NULL). */
 int pp2d_pomdp_live_cells(pp2d_pomdp* h, uint8_t* mask, uint32_t* count);
+/* Work done on this handle so far (cumulative): out[0] = V nodes created,
+ * out[1] = Bayes updates, out[2] = belief x inner-row products of the bound
+ * evaluations (each one is `ncol` separately rounded multiply-adds; the
+ * launches of pp2d_pomdp_plan_batch walk per tile only the rows on which some
+ * belief of the tile is non-zero, so this is what a FLOP count must use).
+ * Measurement only, no reference counterpart. */
+int pp2d_pomdp_work_counters(pp2d_pomdp* h, uint64_t out[3]);
 /* Host threads used for the per-tree work of pp2d_pomdp_plan_batch (random
  * draws, child lists, tree bookkeeping; the trees of a batch are independent).
  * 0 = default: PP2D_HOST_THREADS, else min(16, CPUs of the process /

@@ -70,6 +70,7 @@ SIGNATURES = {
     "pp2d_pomdp_solve_fib": (_i, [_vp, _vp, _vp, ctypes.POINTER(_u32), _u32]),
     "pp2d_pomdp_reserve": (_i, [_vp, _u32]),
     "pp2d_pomdp_live_cells": (_i, [_vp, _vp, ctypes.POINTER(_u32)]),
+    "pp2d_pomdp_work_counters": (_i, [_vp, _vp]),
     "pp2d_pomdp_bayes_update": (_i, [_vp, _vp, _u32, _vp, _vp, _i, _vp, _vp]),
     "pp2d_pomdp_evaluate": (_i, [_vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "pp2d_pomdp_plan_batch": (_i, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),

@@ -349,6 +349,7 @@ int evaluate_slots(pp2d_pomdp* h, const std::vector<int>& slots, float* out, boo
   pomdp_values_kernel<false><<<grid, 256, 0, h->stream>>>(
       in.K, in.kidx, h->HW, h->ld, h->ncol, h->d_slots.p, n, h->d_bel, in.alpha,
       h->d_vals.p, nullptr, nullptr, nullptr, 0);
+  h->work_rows += (uint64_t)in.K * (uint64_t)n;
   count_launch();
   PP2D_CUDA(cudaGetLastError());
   pomdp_bounds_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(
@@ -666,7 +667,8 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
         HW, in.K, in.kidx, c.d_kslots.p, nk, h->d_bel, c.d_tmask.p, mstride);
     count_launch();
     pomdp_support_list_kernel<<<vgrid.x, 256, 0, c.stream>>>(in.K, in.kidx, c.d_tmask.p, mstride,
-                                                             c.d_tlist.p, c.d_tcount.p);
+                                                             c.d_tlist.p, c.d_tcount.p, nk,
+                                                             h->d_work);
     count_launch();
     PP2D_TRY(c.d_torder.ensure(vgrid.x));
     pomdp_tile_order_kernel<<<(vgrid.x + 255) / 256, 256, 0, c.stream>>>(
@@ -679,6 +681,7 @@ int round_stage2(pp2d_pomdp* h, RoundCtx& c) {
     pomdp_values_kernel<false><<<vgrid, 256, 0, c.stream>>>(
         in.K, in.kidx, h->HW, h->ld, h->ncol, c.d_kslots.p, nk, h->d_bel, in.alpha, c.d_vals.p,
         nullptr, nullptr, nullptr, 0);
+    h->work_rows += (uint64_t)in.K * (uint64_t)nk;
   }
   count_launch();
   pomdp_bounds_kernel<<<(nk + 3) / 4, 128, 0, c.stream>>>(nk, h->ncol, h->n_pbvi,
@@ -809,6 +812,8 @@ int pp2d_pomdp_create(uint32_t height, uint32_t width, const uint8_t* map,
     PP2D_CUDA(cudaDeviceSynchronize());
     const char* dense_env = getenv("PP2D_POMDP_DENSE");
     h->skip_dead = !(dense_env && atoi(dense_env) != 0);
+    PP2D_CUDA(cudaMalloc(&h->d_work, sizeof(unsigned long long)));
+    PP2D_CUDA(cudaMemset(h->d_work, 0, sizeof(unsigned long long)));
     const char* tile_env = getenv("PP2D_POMDP_TILE_SUPPORT");
     h->tile_support = !(tile_env && atoi(tile_env) == 0);
     const char* sort_env = getenv("PP2D_POMDP_SORT");
@@ -825,7 +830,7 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   cudaFree(h->d_map); cudaFree(h->d_tp); cudaFree(h->d_mp); cudaFree(h->d_sr);
   cudaFree(h->d_uniforms); cudaFree(h->d_alpha); cudaFree(h->d_bel);
   cudaFree(h->d_kidx); cudaFree(h->d_kidx_all); cudaFree(h->d_alpha_live); cudaFree(h->d_dead);
-  cudaFree(h->d_kinv); cudaFree(h->d_mp_live);
+  cudaFree(h->d_kinv); cudaFree(h->d_mp_live); cudaFree(h->d_work);
   h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();
@@ -969,6 +974,17 @@ int pp2d_pomdp_live_cells(pp2d_pomdp* h, uint8_t* mask, uint32_t* count) {
   return PP2D_OK;
 }
 
+int pp2d_pomdp_work_counters(pp2d_pomdp* h, uint64_t out[3]) {
+  if (!h || !out) return fail(PP2D_ERR_INVALID, "NULL argument");
+  unsigned long long dev = 0;
+  PP2D_CUDA(cudaDeviceSynchronize());
+  PP2D_CUDA(cudaMemcpy(&dev, h->d_work, sizeof(dev), cudaMemcpyDeviceToHost));
+  out[0] = h->n_vnodes;
+  out[1] = h->n_bayes;
+  out[2] = h->work_rows + (uint64_t)dev;
+  return PP2D_OK;
+}
+
 void pp2d_set_host_threads(int n) { g_host_threads.store(n > 0 ? n : 0); }
 
 int pp2d_pomdp_reserve(pp2d_pomdp* h, uint32_t n_beliefs) {
@@ -1069,6 +1085,7 @@ int pp2d_pomdp_evaluate(pp2d_pomdp* h, const float* beliefs, uint32_t n,
                                                              h->ncol, h->d_slots.p, n, h->d_bel,
                                                              in.alpha, h->d_vals.p, nullptr,
                                                              nullptr, nullptr, 0);
+    h->work_rows += (uint64_t)in.K * (uint64_t)n;
     count_launch();
     pomdp_bounds_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(n, h->ncol, h->n_pbvi,
                                                                 h->d_vals.p, h->d_out.p);

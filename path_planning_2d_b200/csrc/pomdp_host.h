@@ -137,6 +137,11 @@ struct pp2d_pomdp {
   void* round_ctx[4] = {nullptr, nullptr, nullptr, nullptr};   // RoundCtx of pomdp.cu (lazily created)
   cudaStream_t stream = nullptr;
   uint64_t n_bayes = 0, n_vnodes = 0;
+  // belief x inner-row products of the values launches: counted on the host
+  // for the launches over a fixed row list, on the device (d_work) for the
+  // per-tile lists
+  uint64_t work_rows = 0;
+  unsigned long long* d_work = nullptr;
   double t_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // PP2D_POMDP_PROFILE=1: seconds per phase
 };
 

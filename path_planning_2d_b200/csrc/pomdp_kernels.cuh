@@ -478,10 +478,18 @@ pomdp_sample_kernel(int H, int W, int n, int S,
 //   0..8 FIB, 9..9+N-1 PBVI
 // (509 -> 512 = four column tiles for the reference's 500 vectors); ld is a
 // multiple of the column tile and the padding is zero.
-// CTA tile 128 beliefs x 128 columns, 256 threads, 8x8 accumulators each
+// CTA tile 64 beliefs x 256 columns, 256 threads, 8x8 accumulators each
 // (4 LDS.128 per 128 math instructions: the 4x4 version was bound by the
 // shared-memory pipe), K chunks of 16 cells double-buffered with cp.async.
-constexpr int kEvM = 128, kEvN = 128, kEvK = 16, kEvPad = 4;
+// (PP2D_EVM = 128 builds the square 128 x 128 tile: same speed per row walked,
+// but a tile of 128 children is five trees wide and walks 1 175 cells per
+// belief on the bench batch where the 64-wide tile walks 1 128 -- of 2 358 live
+// cells, 4 000 in all: 58.5 vs 56.3 ms per 1 250 plans.)
+#ifndef PP2D_EVM
+#define PP2D_EVM 64
+#endif
+constexpr int kEvM = PP2D_EVM, kEvN = 128 * 128 / PP2D_EVM, kEvK = 16, kEvPad = 4;
+static_assert(kEvM == 64 || kEvM == 128, "8x8 accumulators per thread, 256 threads");
 
 // The inner dimension runs over the K cells listed in kidx (ascending cell
 // order); alpha holds the K matching rows.  K = HW with kidx = identity is the
@@ -500,8 +508,8 @@ constexpr int kEvM = 128, kEvN = 128, kEvK = 16, kEvPad = 4;
 // beliefs' modes, so a tile touches about half of the live cells.
 // Per-tile list of inner rows (see TILED above), two launches.
 // pomdp_support_flags_kernel: CTA (tile, chunk of 256 rows): every warp tests
-// 32 rows (all kEvM beliefs of the tile per row, 4 per lane, 32 loads in flight
-// per lane) and writes one 32-bit mask: tmask[tile * mstride + chunk * 8 + warp].
+// 32 rows (all kEvM beliefs of the tile per row, kEvM / 32 per lane, 8 rows in
+// flight) and writes one 32-bit mask: tmask[tile * mstride + chunk * 8 + warp].
 __global__ void __launch_bounds__(256)
 pomdp_support_flags_kernel(int HW, int K, const int* __restrict__ kidx,
                            const int* __restrict__ slots, int n,
@@ -513,10 +521,10 @@ pomdp_support_flags_kernel(int HW, int K, const int* __restrict__ kidx,
   // (the padding of the last tile repeats one of its members)
   if (tid < kEvM) sslot[tid] = slots[min(m0 + tid, n - 1)];
   __syncthreads();
-  const float* c0 = bel + bel_off(HW, 0, sslot[lane]);
-  const float* c1 = bel + bel_off(HW, 0, sslot[lane + 32]);
-  const float* c2 = bel + bel_off(HW, 0, sslot[lane + 64]);
-  const float* c3 = bel + bel_off(HW, 0, sslot[lane + 96]);
+  constexpr int kPer = kEvM / 32;                  // beliefs per lane
+  const float* col[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) col[q] = bel + bel_off(HW, 0, sslot[lane + 32 * q]);
   const int r0 = blockIdx.y * 256 + warp * 32;     // this warp's 32 rows
   if (r0 >= K) return;                             // (warp-uniform; its mask word is never read)
   const int myrow = r0 + lane;
@@ -524,17 +532,19 @@ pomdp_support_flags_kernel(int HW, int K, const int* __restrict__ kidx,
   uint32_t mask = 0;
 #pragma unroll
   for (int j0 = 0; j0 < 32; j0 += 8) {
-    float v[8][4];
+    float v[8][kPer];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int cell = __shfl_sync(0xffffffffu, mycell, j0 + j);
-      const size_t q = (size_t)cell * kSlotBlock;
-      v[j][0] = c0[q]; v[j][1] = c1[q]; v[j][2] = c2[q]; v[j][3] = c3[q];
+      const size_t off = (size_t)cell * kSlotBlock;
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) v[j][q] = col[q][off];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      // (NaN != 0: a row holding a NaN is kept)
-      const bool nz = v[j][0] != 0.0f || v[j][1] != 0.0f || v[j][2] != 0.0f || v[j][3] != 0.0f;
+      bool nz = false;                             // (NaN != 0: a row holding a NaN is kept)
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) nz = nz || v[j][q] != 0.0f;
       if (__any_sync(0xffffffffu, nz) && r0 + j0 + j < K) mask |= 1u << (j0 + j);
     }
   }
@@ -542,11 +552,13 @@ pomdp_support_flags_kernel(int HW, int K, const int* __restrict__ kidx,
 }
 
 // pomdp_support_list_kernel: one CTA per tile turns its ceil(K/32) mask words
-// into the ascending list tlist[tile * K + i] = {cell, row} and tcount[tile].
+// into the ascending list tlist[tile * K + i] = {cell, row} and tcount[tile]
+// (n = beliefs of the launch).
 __global__ void __launch_bounds__(256)
 pomdp_support_list_kernel(int K, const int* __restrict__ kidx,
                           const uint32_t* __restrict__ tmask, int mstride,
-                          int2* __restrict__ tlist, int* __restrict__ tcount) {
+                          int2* __restrict__ tlist, int* __restrict__ tcount, int n,
+                          unsigned long long* __restrict__ work) {
   __shared__ int wsum[8];
   const int tile = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -581,7 +593,11 @@ pomdp_support_list_kernel(int K, const int* __restrict__ kidx,
     base += total;
     __syncthreads();
   }
-  if (tid == 0) tcount[tile] = base;
+  if (tid == 0) {
+    tcount[tile] = base;
+    // (pp2d_pomdp_work_counters: rows x beliefs this tile's values CTAs walk)
+    atomicAdd(work, (unsigned long long)base * (unsigned long long)min(kEvM, n - tile * kEvM));
+  }
 }
 
 // Tiles in descending order of their row counts (ties: ascending tile):
@@ -625,7 +641,8 @@ pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cells, int ld, int
   const int tid = threadIdx.x;
   if (tid < kEvM) sslot[tid] = (m0 + tid < n) ? slots[m0 + tid] : slots[0];
   __syncthreads();
-  const int tx = tid & 15, ty = tid >> 4;
+  constexpr int kTM = kEvM / 8;                    // threads along the beliefs
+  const int tx = tid % kTM, ty = tid / kTM;
   float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -635,7 +652,7 @@ pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cells, int ld, int
   // Tile loaders (HW = the number K of inner-dimension rows of this launch).
   // Rows past it are clamped to the last row: they are never accumulated (the
   // k loop stops at HW), only kept in bounds.  Columns past ncol read the zero
-  // padding of alpha (ld is a multiple of 128).
+  // padding of alpha (ld is a multiple of kEvN).
   // (tid + e * 256) % kEvM does not depend on e: every thread stages one belief
   static_assert(256 % kEvM == 0, "one belief column per thread");
   const float* bcol = bel + bel_off(cells, 0, sslot[tid % kEvM]);
@@ -675,9 +692,9 @@ pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cells, int ld, int
 #pragma unroll 4
     for (int kk = 0; kk < kend; ++kk) {
       const float4 b0 = *reinterpret_cast<const float4*>(&sb[buf][kk][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&sb[buf][kk][64 + tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sb[buf][kk][kEvM / 2 + tx * 4]);
       const float4 a0 = *reinterpret_cast<const float4*>(&sa[buf][kk][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&sa[buf][kk][64 + ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sa[buf][kk][kEvN / 2 + ty * 4]);
       const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
@@ -690,11 +707,11 @@ pomdp_values_kernel(int HW, const int* __restrict__ kidx, int cells, int ld, int
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int m = m0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
+    const int m = m0 + (i < 4 ? tx * 4 + i : kEvM / 2 + tx * 4 + (i - 4));
     if (m >= n) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int col = n0 + (j < 4 ? ty * 4 + j : 64 + ty * 4 + (j - 4));
+      const int col = n0 + (j < 4 ? ty * 4 + j : kEvN / 2 + ty * 4 + (j - 4));
       if (col < ncol) out[(size_t)m * ncol + col] = acc[i][j];
     }
   }

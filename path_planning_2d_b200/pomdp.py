@@ -151,6 +151,13 @@ class PomdpPathPlanning2d:
             self._h, m.ctypes.data if mask else None, ctypes.byref(n)))
         return (n.value, m.reshape(self.map_height, self.map_width)) if mask else n.value
 
+    def work_counters(self):
+        """(V nodes created, Bayes updates, belief x inner-row products of the
+        bound evaluations) on this handle so far."""
+        out = np.zeros(3, np.uint64)
+        _lib.check(self._lib.pp2d_pomdp_work_counters(self._h, out.ctypes.data))
+        return int(out[0]), int(out[1]), int(out[2])
+
     def sampling_uniforms(self):
         out = np.empty(100, np.float32)
         _lib.check(self._lib.pp2d_pomdp_sampling_uniforms(self._h, out.ctypes.data))

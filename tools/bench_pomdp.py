@@ -36,14 +36,17 @@ def main():
         p.plan_batch(beliefs[:32])                     # warm-up, pool growth
         p.plan_batch(beliefs)
         l0 = lib.pp2d_kernel_launches()
+        w0 = p.work_counters()
         t0 = time.perf_counter()
         acts, vals, stats = p.plan_batch(beliefs, with_stats=True)
         dt = time.perf_counter() - t0
         launches = lib.pp2d_kernel_launches() - l0
+        w1 = p.work_counters()
+        walked = (w1[2] - w0[2]) / max(1, w1[0] - w0[0])
     vn = stats[:, 0].sum()
     macs = float(vn) * grid.size * (18 + 500)
     print(f"queries {n}  time {dt*1e3:.1f} ms  plans/s {n/dt:.1f}  V-nodes {vn} "
-          f"({vn/n:.1f}/plan)  launches {launches}  bounds {2*macs/dt/1e12:.2f} Tflop/s "
+          f"({vn/n:.1f}/plan)  cells/belief {walked:.0f}  launches {launches}  bounds {2*macs/dt/1e12:.2f} Tflop/s "
           f"(mul+add)  actions hist {np.bincount(acts, minlength=9).tolist()}")
     if "--cpu" in sys.argv:
         import pomdp_oracle_py as po
