@@ -363,6 +363,12 @@ def qv_tree_section(rank, world, with_cpu):
         "bound": "fp32_issue", "unit": "TFLOP/s (separately rounded FMUL + FADD)",
         "achieved": algo, "peak": peak, "frac": algo / peak,
         "executed": float(w1[2] - w0[2]) * world * ncols * 2 / dt / 1e12,
+        "frac_executed": float(w1[2] - w0[2]) * world * ncols * 2 / dt / 1e12 / peak,
+        "note": "achieved = the reference's dense count (every V node x every cell x every "
+                "alpha vector); it can exceed the peak because most of those multiply-adds are "
+                "provably +-0 and are skipped bit-exactly (cells no mass can enter; per tile of "
+                "64 beliefs the cells where all of them are zero) -- executed is what the GPU "
+                "really did, over the whole batch time, like roofline.traffic for the sweeps",
         "live_cells": live, "cells": hw,
         "cells_walked_per_belief": float(w1[2] - w0[2]) / max(1, w1[0] - w0[0]),
         "peak_what": "128 FP32 lanes x 148 SMs x SM clock x GPUs, one flop per instruction "

@@ -388,23 +388,49 @@ void init_vnode(VNodeH& v, int slot, uint8_t obs, float weight, int parent,
 }
 
 // Upload host beliefs ([n][HW]) into fresh slots and create the root V nodes.
-int make_roots(pp2d_pomdp* h, std::vector<Tree*>& trees, const float* beliefs) {
+// mode_key (optional, n entries): column * H + row of the first maximum of
+// every start belief (the order a batch is planned in, see pp2d_pomdp_plan_batch).
+int make_roots(pp2d_pomdp* h, std::vector<Tree*>& trees, const float* beliefs,
+               uint32_t* mode_key = nullptr) {
   const int n = (int)trees.size();
   std::vector<int> slots(n);
   for (int i = 0; i < n; ++i) PP2D_TRY(alloc_slot(h, &slots[i]));
+  // A batch goes through page-locked staging: the caller's buffer is pageable
+  // (a copy straight from it is staged by the driver at a fraction of the PCIe
+  // rate, with the host blocked), and the host threads read every belief here
+  // anyway.
+  const size_t row = (size_t)h->HW;
+  const bool staged = n >= 64;
+  if (staged && h->pin_rows_cap < (size_t)n * row) {
+    if (h->pin_rows) cudaFreeHost(h->pin_rows);
+    h->pin_rows = nullptr;
+    h->pin_rows_cap = 0;
+    PP2D_CUDA(cudaHostAlloc((void**)&h->pin_rows, (size_t)n * row * sizeof(float),
+                            cudaHostAllocDefault));
+    h->pin_rows_cap = (size_t)n * row;
+  }
   // Start beliefs that are not +0 on the dead cells (and everything grown from
   // them) are evaluated with the dense inner products.
   bool any_dense = false;
 #pragma omp parallel for schedule(static) num_threads(host_threads()) reduction(|| : any_dense) \
     if (n >= 64)
   for (int i = 0; i < n; ++i) {
-    trees[i]->dense = !zero_on_dead_cells(h, beliefs + (size_t)i * h->HW);
+    const float* b = beliefs + (size_t)i * row;
+    trees[i]->dense = !zero_on_dead_cells(h, b);
     any_dense = any_dense || trees[i]->dense;
+    if (staged) memcpy(h->pin_rows + (size_t)i * row, b, row * sizeof(float));
+    if (mode_key) {
+      int best = 0;
+      for (int s = 1; s < h->HW; ++s)
+        if (b[s] > b[best]) best = s;
+      mode_key[i] = (uint32_t)(best % h->W) * (uint32_t)h->H + (uint32_t)(best / h->W);
+    }
   }
   PP2D_TRY(h->d_slots.ensure(n));
   PP2D_TRY(h->d_rows.ensure((size_t)n * h->HW));
-  PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, beliefs, (size_t)n * h->HW * sizeof(float),
-                            cudaMemcpyHostToDevice, h->stream));
+  PP2D_CUDA(cudaMemcpyAsync(h->d_rows.p, staged ? h->pin_rows : beliefs,
+                            (size_t)n * h->HW * sizeof(float), cudaMemcpyHostToDevice,
+                            h->stream));
   PP2D_CUDA(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * sizeof(int),
                             cudaMemcpyHostToDevice, h->stream));
   dim3 grid((h->HW + 255) / 256, n);
@@ -831,6 +857,7 @@ void pp2d_pomdp_destroy(pp2d_pomdp* h) {
   cudaFree(h->d_uniforms); cudaFree(h->d_alpha); cudaFree(h->d_bel);
   cudaFree(h->d_kidx); cudaFree(h->d_kidx_all); cudaFree(h->d_alpha_live); cudaFree(h->d_dead);
   cudaFree(h->d_kinv); cudaFree(h->d_mp_live); cudaFree(h->d_work);
+  if (h->pin_rows) cudaFreeHost(h->pin_rows);
   h->d_slots.release(); h->d_items.release(); h->d_prefix.release();
   h->d_draws.release(); h->d_vals.release(); h->d_rows.release();
   h->d_sums.release(); h->d_obs.release(); h->d_out.release();
@@ -1139,24 +1166,15 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
     std::vector<Tree*> trees(gn);
     double tr = now_s();
     for (size_t i = 0; i < gn; ++i) { store[i].rng.seed(1); trees[i] = &store[i]; }
-    PP2D_TRY(make_roots(h, trees, beliefs + g0 * (size_t)h->HW));
+    const bool sorted = h->sort_queries && gn >= 2 * (size_t)kEvM;
+    std::vector<uint32_t> key(sorted ? gn : 0);
+    PP2D_TRY(make_roots(h, trees, beliefs + g0 * (size_t)h->HW, sorted ? key.data() : nullptr));
     // The trees are planned in the order of their start beliefs' modes (column,
     // then row): neighbours in that order have overlapping supports, which is
     // what makes the per-tile inner rows of the values launches short
     // (pomdp_support_flags_kernel).  Only the order of the work changes: every query
     // owns its rand() stream and its results land at its own index.
-    const bool sorted = h->sort_queries && gn >= 2 * (size_t)kEvM;
     if (sorted) {
-      const int gni0 = (int)gn;
-      std::vector<uint32_t> key(gn);
-#pragma omp parallel for schedule(static) num_threads(host_threads()) if (gni0 >= 64)
-      for (int i = 0; i < gni0; ++i) {
-        const float* b = beliefs + (g0 + (size_t)i) * (size_t)h->HW;
-        int best = 0;
-        for (int s = 1; s < h->HW; ++s)
-          if (b[s] > b[best]) best = s;
-        key[i] = (uint32_t)(best % h->W) * (uint32_t)h->H + (uint32_t)(best / h->W);
-      }
       std::vector<int> order(gn);
       for (size_t i = 0; i < gn; ++i) order[i] = (int)i;
       std::stable_sort(order.begin(), order.end(),

@@ -134,6 +134,8 @@ struct pp2d_pomdp {
   pp2d::DevBuf<float> d_prefix, d_draws, d_vals, d_rows, d_sums;
   pp2d::DevBuf<uint8_t> d_obs;
   pp2d::DevBuf<float> d_out;               // 4 floats per evaluated belief
+  float* pin_rows = nullptr;               // page-locked staging of a batch's start beliefs
+  size_t pin_rows_cap = 0;
   void* round_ctx[4] = {nullptr, nullptr, nullptr, nullptr};   // RoundCtx of pomdp.cu (lazily created)
   cudaStream_t stream = nullptr;
   uint64_t n_bayes = 0, n_vnodes = 0;

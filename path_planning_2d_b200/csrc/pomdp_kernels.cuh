@@ -476,7 +476,7 @@ pomdp_sample_kernel(int H, int W, int n, int S,
 // (i, j), cells in ascending order, float multiply rounded, then float add
 // rounded (no FMA).  alpha is [HW][ld]: the bound matrix has the columns
 //   0..8 FIB, 9..9+N-1 PBVI
-// (509 -> 512 = four column tiles for the reference's 500 vectors); ld is a
+// (509 -> 512 = two column tiles for the reference's 500 vectors); ld is a
 // multiple of the column tile and the padding is zero.
 // CTA tile 64 beliefs x 256 columns, 256 threads, 8x8 accumulators each
 // (4 LDS.128 per 128 math instructions: the 4x4 version was bound by the

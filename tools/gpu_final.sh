@@ -17,7 +17,7 @@ echo "== ncu full: fused sweep kernel"
 ncu --set full --import-source on --clock-control none -k regex:mdp_sweep_kernel -s 3 -c 1 -o $OUT/prof_fused_$TAG -f \
   python tools/ncu_target.py 4096 12 > $OUT/ncu_full_$TAG.log 2>&1; echo "exit $?"
 echo "== ncu full: values kernel"
-ncu --set full --import-source on --clock-control none -k regex:pomdp_values -s 20 -c 1 -o $OUT/prof_values_$TAG -f \
+ncu --set full --import-source on --clock-control none -k regex:pomdp_values -s 40 -c 1 -o $OUT/prof_values_$TAG -f \
   python tools/bench_pomdp.py 1250 --fixture > $OUT/ncu_full_values_$TAG.log 2>&1; echo "exit $?"
 echo "== SASS of the fused kernel (instruction histogram + one marching step)"
 python tools/sass_summary.py > $OUT/sass_fused_$TAG.txt 2>&1; echo "exit $?"
