@@ -362,7 +362,7 @@ int pp2d_pomdp_live_cells(pp2d_pomdp* h, uint8_t* mask, uint32_t* count);
 int pp2d_pomdp_work_counters(pp2d_pomdp* h, uint64_t out[3]);
 /* Host threads used for the per-tree work of pp2d_pomdp_plan_batch (random
  * draws, child lists, tree bookkeeping; the trees of a batch are independent).
- * 0 = default: PP2D_HOST_THREADS, else min(16, CPUs of the process /
+ * 0 = default: PP2D_HOST_THREADS, else min(8, CPUs of the process /
  * LOCAL_WORLD_SIZE).  The reference is single-threaded (ros::spin). */
 void pp2d_set_host_threads(int n);
 /*

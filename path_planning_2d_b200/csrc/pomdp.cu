@@ -124,8 +124,20 @@ int pool_reserve(pp2d_pomdp* h, size_t slots_wanted) {
   if (cap > (size_t)INT32_MAX)
     return fail(PP2D_ERR_INVALID, "belief pool of %zu slots is too large", cap);
   float* nb = nullptr;
+  size_t old_cap = h->d_bel ? (size_t)h->cap : 0;
+  if (old_cap && h->free_slots.size() == old_cap) {
+    // No belief is live: release the old pool BEFORE asking for the new one (a
+    // batch sizes the pool to half of the memory; old + new need not fit).
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaFree(h->d_bel);
+    h->d_bel = nullptr;
+    h->cap = 0;
+    h->free_slots.clear();
+    old_cap = 0;
+    if (e != cudaSuccess)
+      return fail(PP2D_ERR_CUDA, "CUDA error releasing the belief pool: %s", cudaGetErrorName(e));
+  }
   PP2D_CUDA(cudaMalloc(&nb, cap * (size_t)h->HW * sizeof(float)));
-  const size_t old_cap = h->d_bel ? (size_t)h->cap : 0;
   if (old_cap && h->free_slots.size() != old_cap) {
     cudaError_t e = cudaDeviceSynchronize();     // every stream that touches the pool
     if (e == cudaSuccess)
@@ -310,9 +322,12 @@ InnerDim inner_dim(const pp2d_pomdp* h, bool dense) {
 
 // Host threads for the per-tree work of a batch: pp2d_set_host_threads, else
 // PP2D_HOST_THREADS, else the CPUs this process may run on divided by the
-// ranks sharing the node (LOCAL_WORLD_SIZE, set by torchrun), at most 16.
+// ranks sharing the node (LOCAL_WORLD_SIZE, set by torchrun), at most 8.
 // (Set explicitly rather than left to OMP_NUM_THREADS, which torchrun forces
-// to 1; more threads than cores makes OpenMP's spinning barriers crawl.)
+// to 1; more threads than cores makes OpenMP's spinning barriers crawl, and
+// as many threads as cores leaves none for the thread that feeds the GPU:
+// measured on a 16-core B200 box, 1 250 plans take 56-57 ms with 8 threads,
+// 57-61 ms with 4 and 54-66 ms with occasional 160 ms outliers with 16.)
 std::atomic<int> g_host_threads{0};
 int host_threads() {
   const int forced = g_host_threads.load(std::memory_order_relaxed);
@@ -325,7 +340,7 @@ int host_threads() {
     if (sched_getaffinity(0, sizeof(set), &set) == 0) c = CPU_COUNT(&set);
     const char* lw = getenv("LOCAL_WORLD_SIZE");
     if (lw && atoi(lw) > 1) c /= atoi(lw);
-    return std::max(1, std::min(16, c));
+    return std::max(1, std::min(8, c));
   }();
   return n;
 }
@@ -735,8 +750,12 @@ int round_stage3(pp2d_pomdp* h, RoundCtx& c) {
     const int vi = c.jobs[i].v;
     int kpos = c.first[i];
     const int kend = c.first[i + 1];
-    t.v.reserve(t.v.size() + (size_t)(kend - kpos));
-    t.q.reserve(t.q.size() + kActions);
+    // (room for whole rounds at once: an exact reserve would move every node
+    // of the tree in every round)
+    if (t.v.capacity() < t.v.size() + (size_t)(kend - kpos))
+      t.v.reserve(std::max<size_t>(2 * t.v.capacity(), t.v.size() + 4 * (size_t)(kend - kpos)));
+    if (t.q.capacity() < t.q.size() + kActions)
+      t.q.reserve(std::max<size_t>(2 * t.q.capacity(), t.q.size() + 4 * kActions));
     t.v[vi].children.resize(kActions);
     for (int a = 0; a < kActions; ++a) {
       t.q.emplace_back();
@@ -1151,7 +1170,9 @@ int pp2d_pomdp_plan_batch(pp2d_pomdp* h, const float* beliefs, uint32_t n,
   if (spq && atol(spq) > 0) per_query = std::min<size_t>(per_query, (size_t)atol(spq));
   size_t free_b = 0, total_b = 0;
   PP2D_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = free_b / 2 + (size_t)h->cap * h->HW * sizeof(float);
+  // half of what is free once the current pool is counted as free (the pool
+  // must not ratchet up from call to call)
+  size_t budget = (free_b + (size_t)h->cap * h->HW * sizeof(float)) / 2;
   const char* env = getenv("PP2D_POMDP_POOL_MB");
   if (env && *env) budget = (size_t)atol(env) << 20;
   size_t max_slots = budget / ((size_t)h->HW * sizeof(float));
