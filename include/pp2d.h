@@ -119,6 +119,21 @@ int pp2d_mdp_device_count(const pp2d_mdp* h, int* peer_to_peer);
 int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
                    uint32_t goal_y);
 
+/*
+ * Upload the map of the NEXT pp2d_mdp_reset ahead of time: the rows this handle
+ * needs start travelling to a second device buffer on a separate upload stream
+ * and the call returns at once, so the copy overlaps the solve that is still
+ * running (page-locked host memory is needed for that).  A following
+ * pp2d_mdp_reset(h, map, ...) with the SAME pointer uses the staged rows (it
+ * waits for them in stream order, skips its own copy and does not block the
+ * host); with any other pointer the staged rows are dropped.  The host buffer
+ * must stay unchanged until that reset has been called.  No counterpart in the
+ * reference (one map per process, src/mdp/path_planning_2d.cu:94); for a
+ * planner that re-plans on a stream of maps.
+ */
+int pp2d_mdp_stage_map(pp2d_mdp* h, const uint8_t* map);
+
+
 /* Replaces freeDeviceMemory (src/mdp/path_planning_2d_cuda.cu:66-74). */
 void pp2d_mdp_destroy(pp2d_mdp* h);
 

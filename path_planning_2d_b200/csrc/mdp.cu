@@ -137,6 +137,11 @@ struct pp2d_mdp {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_snapshot = nullptr, ev_copied = nullptr;
   bool download_pending = false;
+  // map of the NEXT reset, uploaded ahead of time (pp2d_mdp_stage_map)
+  uint8_t* occ_next = nullptr;     // same size as occ
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t ev_staged = nullptr, ev_code_built = nullptr;
+  const uint8_t* staged_map = nullptr;   // host pointer the staged rows came from
   float4* lut = nullptr;
   uint32_t* resid = nullptr;       // device float bits
   uint32_t* resid_host = nullptr;  // pinned
@@ -516,9 +521,18 @@ static int upload_map(pp2d_mdp* h, const uint8_t* map) {
   // launch counters in the flag block are cumulative and stay)
   PP2D_CUDA(cudaMemsetAsync(h->flags + kFlagError, 0, sizeof(unsigned int), h->stream));
   h->halo_budget = kPadRows;
-  PP2D_CUDA(cudaMemcpyAsync(h->occ, map + (size_t)occ_row0 * h->W,
-                            (size_t)occ_rows * h->W, cudaMemcpyHostToDevice,
-                            h->stream));
+  // The rows may already be on the device (pp2d_mdp_stage_map of this very
+  // pointer): order the code kernel after that copy and swap the two buffers.
+  const bool staged = h->staged_map != nullptr && h->staged_map == map;
+  h->staged_map = nullptr;
+  if (staged) {
+    PP2D_CUDA(cudaStreamWaitEvent(h->stream, h->ev_staged, 0));
+    std::swap(h->occ, h->occ_next);
+  } else {
+    PP2D_CUDA(cudaMemcpyAsync(h->occ, map + (size_t)occ_row0 * h->W,
+                              (size_t)occ_rows * h->W, cudaMemcpyHostToDevice,
+                              h->stream));
+  }
   CodeParams cp;
   cp.occ = h->occ; cp.code = h->code; cp.W = (int)h->W; cp.Htot = (int)h->Htot;
   cp.pitch = h->pitch; cp.rows_phys = (int)h->H + 2 * kPadRows;
@@ -528,7 +542,10 @@ static int upload_map(pp2d_mdp* h, const uint8_t* map) {
   mdp_code_kernel<<<grid, 256, 0, h->stream>>>(cp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   PP2D_CUDA(cudaGetLastError());
-  PP2D_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->ev_code_built) PP2D_CUDA(cudaEventRecord(h->ev_code_built, h->stream));
+  // (the caller may free `map` on return: wait for the copy; a staged map has
+  // been waited for in stream order and the host is free to run ahead)
+  if (!staged) PP2D_CUDA(cudaStreamSynchronize(h->stream));
   h->has_occupied =
       memchr(map + (size_t)h->row_begin * h->W, 1, owned) != nullptr;
   h->cur = 0;
@@ -909,6 +926,37 @@ int pp2d_mdp_reset(pp2d_mdp* h, const uint8_t* map, uint32_t goal_x,
   return upload_map(h, map);
 }
 
+int pp2d_mdp_stage_map(pp2d_mdp* h, const uint8_t* map) {
+  if (!h || !map) return fail(PP2D_ERR_INVALID, "NULL argument");
+  if (!h->parts.empty()) {
+    DeviceGuard guard;
+    for (pp2d_mdp* part : h->parts) {
+      PP2D_TRY_MDP(multi_set_device(part));
+      PP2D_TRY_MDP(pp2d_mdp_stage_map(part, map));
+    }
+    return PP2D_OK;
+  }
+  const int occ_row0 = (int)h->row_begin - 3 < 0 ? 0 : (int)h->row_begin - 3;
+  const int row_end = (int)(h->row_begin + h->H);
+  const int occ_row1 = row_end + 3 > (int)h->Htot ? (int)h->Htot : row_end + 3;
+  const size_t bytes = (size_t)(occ_row1 - occ_row0) * h->W;
+  if (!h->upload_stream) {
+    PP2D_CUDA(cudaStreamCreateWithFlags(&h->upload_stream, cudaStreamNonBlocking));
+    PP2D_CUDA(cudaEventCreateWithFlags(&h->ev_staged, cudaEventDisableTiming));
+    PP2D_CUDA(cudaEventCreateWithFlags(&h->ev_code_built, cudaEventDisableTiming));
+    PP2D_CUDA(cudaMalloc(&h->occ_next, bytes));
+  } else {
+    // occ_next was the occupancy buffer of an earlier reset: its code kernel
+    // (on the solve stream) must have read it before it is overwritten
+    PP2D_CUDA(cudaStreamWaitEvent(h->upload_stream, h->ev_code_built, 0));
+  }
+  PP2D_CUDA(cudaMemcpyAsync(h->occ_next, map + (size_t)occ_row0 * h->W, bytes,
+                            cudaMemcpyHostToDevice, h->upload_stream));
+  PP2D_CUDA(cudaEventRecord(h->ev_staged, h->upload_stream));
+  h->staged_map = map;
+  return PP2D_OK;
+}
+
 void pp2d_mdp_destroy(pp2d_mdp* h) {
   if (!h) return;
   if (!h->parts.empty()) multi_destroy(h);
@@ -919,6 +967,13 @@ void pp2d_mdp_destroy(pp2d_mdp* h) {
   if (h->ev_snapshot) cudaEventDestroy(h->ev_snapshot);
   if (h->ev_copied) cudaEventDestroy(h->ev_copied);
   cudaFree(h->dense_action);
+  if (h->upload_stream) {
+    cudaStreamSynchronize(h->upload_stream);
+    cudaStreamDestroy(h->upload_stream);
+  }
+  if (h->ev_staged) cudaEventDestroy(h->ev_staged);
+  if (h->ev_code_built) cudaEventDestroy(h->ev_code_built);
+  cudaFree(h->occ_next);
   if (h->owns_stream && h->stream) cudaStreamDestroy(h->stream);
   cudaFree(h->j[0]); cudaFree(h->j[1]); cudaFree(h->jchk); cudaFree(h->code);
   cudaFree(h->action); cudaFree(h->occ); cudaFree(h->dense); cudaFree(h->lut);

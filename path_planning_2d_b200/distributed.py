@@ -94,6 +94,9 @@ class GpuShard:
         torch.cuda.current_stream().synchronize()
         self.mdp.reset(grid, goal)
 
+    def stage_map(self, grid):
+        self.mdp.stage_map(grid)
+
     # peer-to-peer ghost rows (same node): descriptor = CUDA IPC handles
     def p2p_descriptor(self):
         return self.mdp.ipc_export()
@@ -194,6 +197,14 @@ class ShardedValueIteration:
             dist.all_reduce(self._token, group=self.group)
             torch.cuda.current_stream().synchronize()
         self.n_sweeps = 0
+
+    def stage_map(self, grid):
+        """Start uploading the map of the next reset(grid, ...) while the current
+        solve is still running (pp2d_mdp_stage_map); a no-op for shard back ends
+        without it."""
+        stage = getattr(self.shard, "stage_map", None)
+        if stage is not None:
+            stage(grid)
 
     # -- ghost rows --------------------------------------------------------
     def exchange(self):

@@ -99,6 +99,18 @@ class MdpPathPlanning2d:
         _lib.check(self._lib.pp2d_mdp_reset(self._h, self._map.ctypes.data,
                                             self.goal[0], self.goal[1]))
 
+    def stage_map(self, grid_map):
+        """Start uploading the map of the next reset() while the current solve
+        runs (pp2d_mdp_stage_map); pass the SAME array to reset() afterwards.
+        The array must be C-contiguous uint8 (page-locked for a real overlap)
+        and stay unchanged until that reset()."""
+        if (not isinstance(grid_map, np.ndarray) or grid_map.dtype != np.uint8
+                or not grid_map.flags.c_contiguous
+                or grid_map.shape != (self.map_height, self.map_width)):
+            raise ValueError("stage_map() needs a C-contiguous uint8 map of the handle's shape")
+        self._staged = grid_map          # keep it alive
+        _lib.check(self._lib.pp2d_mdp_stage_map(self._h, grid_map.ctypes.data))
+
     # -- solver -----------------------------------------------------------
     def set_stream(self, cuda_stream_ptr, asynchronous=False):
         _lib.check(self._lib.pp2d_mdp_set_stream(self._h, cuda_stream_ptr))

@@ -379,6 +379,49 @@ def test_asynchronous_download_overlaps_the_next_solve():
             _assert_same(mdp, ora2, "after the overlapped downloads")
 
 
+def test_staged_map_upload_overlaps_the_running_solve():
+    """pp2d_mdp_stage_map uploads the NEXT map while sweeps of the current one
+    are queued; reset() with the same pointer uses the staged rows, with
+    another pointer it drops them.  Three maps in a row (both staging buffers
+    are reused), also on a multi-shard handle."""
+    import torch
+    maps = [cases.synthetic_map(301, 257, d, seed=s, goal=g)
+            for d, s, g in ((0.2, 51, None), (0.35, 52, (9, 200)), (0.1, 53, (250, 7)),
+                            (0.3, 54, (128, 150)))]
+    pinned = [torch.from_numpy(m.copy()).pin_memory().numpy() for m, _ in maps]
+    for devices in (None, [0, 0, 0]):
+        with MdpPathPlanning2d(pinned[0], maps[0][1], cases.GAMMA, devices=devices) as mdp:
+            for k in range(1, 4):
+                mdp.sweeps(8)                     # queued work of map k-1
+                mdp.stage_map(pinned[k])          # travels meanwhile
+                ora_prev = oracle_py.OracleMdp(maps[k - 1][0], maps[k - 1][1], cases.GAMMA)
+                ora_prev.sweeps(8)
+                _assert_same(mdp, ora_prev, f"map {k - 1} while map {k} is staged")
+                mdp.reset(pinned[k], maps[k][1])
+                assert mdp.sweep_count == 0
+            ora = oracle_py.OracleMdp(maps[3][0], maps[3][1], cases.GAMMA)
+            mdp.sweeps(11)
+            ora.sweeps(11)
+            _assert_same(mdp, ora, "after three staged resets")
+            # a staged map that is NOT the one reset() gets is dropped
+            mdp.stage_map(pinned[1])
+            mdp.reset(pinned[2], maps[2][1])
+            ora = oracle_py.OracleMdp(maps[2][0], maps[2][1], cases.GAMMA)
+            mdp.sweeps(6)
+            ora.sweeps(6)
+            _assert_same(mdp, ora, "staged map dropped")
+            # ... and the next staged upload still works
+            mdp.stage_map(pinned[0])
+            mdp.reset(pinned[0], maps[0][1])
+            ora = oracle_py.OracleMdp(maps[0][0], maps[0][1], cases.GAMMA)
+            mdp.sweeps(5)
+            ora.sweeps(5)
+            _assert_same(mdp, ora, "staged after a dropped one")
+        with pytest.raises(ValueError):
+            with MdpPathPlanning2d(pinned[0], maps[0][1], cases.GAMMA) as mdp:
+                mdp.stage_map(pinned[0][:100])
+
+
 def test_reset_reuses_the_handle():
     grid, goal = cases.synthetic_map(97, 143, 0.25, seed=21)
     grid2, goal2 = cases.synthetic_map(97, 143, 0.1, seed=22, goal=(5, 90))
