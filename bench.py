@@ -536,7 +536,7 @@ def run_main_arm(args):
 
     trace = [] if os.environ.get("PP2D_E2E_TRACE") else None   # host time per phase (debugging aid)
 
-    def e2e_step(i):
+    def e2e_step(i, with_cost=True):
         t = [time.perf_counter()]
         v.reset(maps_np[i % 2], goal)  # map rows on the device (staged by step i-1, or H2D here), codes, J = 0
         t.append(time.perf_counter())
@@ -549,39 +549,56 @@ def run_main_arm(args):
         if i > 0:
             mdp_handle.download_wait()           # step i-1's J and actions are on the host
         t.append(time.perf_counter())
-        mdp_handle.download_begin(cost_host[i % 2].data_ptr(), act_host[i % 2].data_ptr())
+        mdp_handle.download_begin(cost_host[i % 2].data_ptr() if with_cost else None,
+                                  act_host[i % 2].data_ptr())
         t.append(time.perf_counter())
-        if trace is not None:
+        if trace is not None and with_cost:
             trace.append([round((b - a) * 1e3, 3) for a, b in zip(t, t[1:])])
         return res
 
     e2e_step(0)
     mdp_handle.download_wait()
     first = (cost_host[0].clone(), act_host[0].clone())
-    barrier()
     e2e_steps = max(2, min(args.steps, 20))   # (the drain of the last download is inside the timed region)
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    mdp_handle.download_wait()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+
+    def e2e_run(with_cost):
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i, with_cost)
+        mdp_handle.download_wait()
+        barrier()
+        sec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        # every step solved the same problem: all downloads must hold the same bits
+        for k in range(2):
+            if not ((not with_cost or
+                     torch.equal(cost_host[k].view(torch.int32), first[0].view(torch.int32)))
+                    and torch.equal(act_host[k], first[1])):
+                raise SystemExit("e2e: overlapped downloads disagree")
+        return cells * SWEEPS_PER_STEP * e2e_steps / float(sec.item())
+
+    e2e_val = e2e_run(True)
     if trace is not None:
         print(f"rank {rank} e2e ms per phase [reset, enqueue sweeps, residual, download_wait, "
               f"download_begin]: {trace[1:]}", file=sys.stderr)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = cells * SWEEPS_PER_STEP * e2e_steps / float(e2e_s.item())
-    # every step solved the same problem: all downloads must hold the same bits
-    for k in range(2):
-        if not (torch.equal(cost_host[k].view(torch.int32), first[0].view(torch.int32))
-                and torch.equal(act_host[k], first[1])):
-            raise SystemExit("e2e: overlapped downloads disagree")
+    # the same pipeline for a planner that only needs the policy (beliefCallback
+    # reads optimal_action only; the reference's host copy of J feeds RViz
+    # markers, src/mdp/path_planning_2d.cu:380-393): pp2d_mdp_download_begin(cost = NULL)
+    for t_ in act_host:
+        t_.zero_()
+    e2e_policy_val = e2e_run(False)
     occ_rows = min(H, bounds[1] + 3) - max(0, bounds[0] - 3)
     e2e = {"value": e2e_val, "unit": UNIT,
            "h2d_bytes_per_step": occ_rows * W,
            "d2h_bytes_per_step": (bounds[1] - bounds[0]) * W * 5 + 4,
            "steps": e2e_steps,
+           "policy_only": {"value": e2e_policy_val, "unit": UNIT,
+                           "d2h_bytes_per_step": (bounds[1] - bounds[0]) * W + 4,
+                           "what": "the same pipeline with pp2d_mdp_download_begin(cost = NULL): "
+                                   "only the action grid travels back (all a planner's "
+                                   "beliefCallback reads); NOT the headline e2e"},
            "map_upload": "staged (pp2d_mdp_stage_map, under the previous solve)" if stage
                          else "inside pp2d_mdp_reset",
            "what": "pp2d_mdp_reset(map from pinned host) + 100 sweeps + residual "

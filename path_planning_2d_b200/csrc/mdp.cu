@@ -148,6 +148,7 @@ struct pp2d_mdp {
   int cur = 0;                     // j[cur] holds J_n
   uint32_t n_sweeps = 0;
   uint32_t n_chk = 0;              // sweep count at the last residual call
+  bool chk_is_zero = true;         // jchk stands for J_0 = 0 (not written since the reset)
   uint32_t action_sweep = 0;       // sweep count the action grid belongs to
   bool has_occupied = false;
   std::vector<float> trapped;      // trapped[n] = J_n of an occupied cell
@@ -515,7 +516,7 @@ static int upload_map(pp2d_mdp* h, const uint8_t* map) {
   const int occ_rows = occ_row1 - occ_row0;
   PP2D_CUDA(cudaMemsetAsync(h->j[0], 0, h->plane * sizeof(float), h->stream));
   PP2D_CUDA(cudaMemsetAsync(h->j[1], 0, h->plane * sizeof(float), h->stream));
-  PP2D_CUDA(cudaMemsetAsync(h->jchk, 0, h->plane * sizeof(float), h->stream));
+  h->chk_is_zero = true;          // Jchk = J_0 = 0: the first residual does not read it
   PP2D_CUDA(cudaMemsetAsync(h->action, 0, owned, h->stream));
   // a timed-out hand-shake of an earlier solve must not poison this one (the
   // launch counters in the flag block are cumulative and stay)
@@ -538,8 +539,9 @@ static int upload_map(pp2d_mdp* h, const uint8_t* map) {
   cp.pitch = h->pitch; cp.rows_phys = (int)h->H + 2 * kPadRows;
   cp.row_begin = (int)h->row_begin; cp.occ_row0 = occ_row0; cp.occ_rows = occ_rows;
   cp.gx = (int)h->gx; cp.gy = (int)h->gy;
-  dim3 grid((h->pitch + 255) / 256, cp.rows_phys);
-  mdp_code_kernel<<<grid, 256, 0, h->stream>>>(cp);
+  dim3 grid((h->pitch / 4 + kCodeThreads - 1) / kCodeThreads,
+            (cp.rows_phys + kCodeRows - 1) / kCodeRows);
+  mdp_code_kernel<<<grid, kCodeThreads, 0, h->stream>>>(cp);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   PP2D_CUDA(cudaGetLastError());
   if (h->ev_code_built) PP2D_CUDA(cudaEventRecord(h->ev_code_built, h->stream));
@@ -1069,10 +1071,17 @@ int pp2d_mdp_residual_device(pp2d_mdp* h, void** dev_float_out) {
   int grid = h->sm_count * 8;
   if ((size_t)grid * 256 > n4) grid = (int)((n4 + 255) / 256);
   if (grid < 1) grid = 1;
-  mdp_residual_kernel<<<grid, 256, 0, h->stream>>>(
-      reinterpret_cast<const float4*>(h->j[h->cur] + off),
-      reinterpret_cast<float4*>(h->jchk + off), n4, floor_bits, h->resid,
-      h->p2p ? h->flags + kFlagError : nullptr);
+  if (h->chk_is_zero)
+    mdp_residual_kernel<true><<<grid, 256, 0, h->stream>>>(
+        reinterpret_cast<const float4*>(h->j[h->cur] + off),
+        reinterpret_cast<float4*>(h->jchk + off), n4, floor_bits, h->resid,
+        h->p2p ? h->flags + kFlagError : nullptr);
+  else
+    mdp_residual_kernel<false><<<grid, 256, 0, h->stream>>>(
+        reinterpret_cast<const float4*>(h->j[h->cur] + off),
+        reinterpret_cast<float4*>(h->jchk + off), n4, floor_bits, h->resid,
+        h->p2p ? h->flags + kFlagError : nullptr);
+  h->chk_is_zero = false;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   PP2D_CUDA(cudaGetLastError());
   h->n_chk = h->n_sweeps;
@@ -1200,10 +1209,17 @@ int pp2d_mdp_download_begin(pp2d_mdp* h, float* cost, uint8_t* action) {
   if (h->download_pending) PP2D_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
   if (cost) {
     if (!h->dense) PP2D_CUDA(cudaMalloc(&h->dense, owned * sizeof(float)));
-    dim3 grid((h->W + 255) / 256, h->H);
-    mdp_export_kernel<<<grid, 256, 0, h->stream>>>(
-        h->j[h->cur], h->code, h->dense, (int)h->W, (int)h->H, h->pitch,
-        occupied_cost(h, h->n_sweeps));
+    if ((h->W & 3) == 0 && (kPadLeft & 3) == 0) {
+      dim3 grid((h->W / 4 + 255) / 256, h->H);
+      mdp_export_kernel<true><<<grid, 256, 0, h->stream>>>(
+          h->j[h->cur], h->code, h->dense, (int)h->W, (int)h->H, h->pitch,
+          occupied_cost(h, h->n_sweeps));
+    } else {
+      dim3 grid((h->W + 255) / 256, h->H);
+      mdp_export_kernel<false><<<grid, 256, 0, h->stream>>>(
+          h->j[h->cur], h->code, h->dense, (int)h->W, (int)h->H, h->pitch,
+          occupied_cost(h, h->n_sweeps));
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PP2D_CUDA(cudaGetLastError());
   }

@@ -91,6 +91,13 @@ constexpr int kLutAlign = 2048;
 #ifndef PP2D_MINV
 #define PP2D_MINV 0
 #endif
+// PP2D_ARGMIN_EQ = 1: the arg-min variant takes the minimum with FMNMX3 and
+// finds its first index by equality (see backup()); 0: compare-and-keep chain.
+// (236 against 245 instructions per marching step of the fused arg-min kernel,
+// but the P2P strip-major instantiation then spills two registers: off.)
+#ifndef PP2D_ARGMIN_EQ
+#define PP2D_ARGMIN_EQ 0
+#endif
 #ifndef PP2D_WARPS
 #define PP2D_WARPS 8
 #endif
@@ -184,6 +191,27 @@ __device__ __forceinline__ float backup(float j0, float j1, float j2, float j3,
   float c7 = fmaf(gb, j8, fmaf(ga, j7, fmaf(gb, j6, fmaf(t[2].y, j4, t[2].x))));
   float c8 = fmaf(ga, j8, fmaf(gb, j7, fmaf(gb, j5, fmaf(t[1].w, j4, t[1].z))));
   if (POLICY) {
+#if PP2D_ARGMIN_EQ
+    // path_planning_2d_cuda.cu:244-258 keeps the first strict minimum, u
+    // ascending = the lowest u whose cost equals the minimum.  The minimum is
+    // taken as in the value-only kernel (costs are finite and >= +0: no NaN or
+    // -0 for FMNMX to choose differently), then one compare + select per
+    // action in DESCENDING order, so that the lowest index is written last: 4
+    // FMNMX3 + 8 FSETP + 8 SEL with one live predicate, instead of a chain of
+    // 8 x (FSETP, FSEL, SEL) that keeps 8 predicates alive.
+    const float best = min3(min3(c0, c1, c2), min3(c3, c4, c5), min3(c6, c7, c8));
+    uint32_t a = 8;
+    a = (c7 == best) ? 7u : a;
+    a = (c6 == best) ? 6u : a;
+    a = (c5 == best) ? 5u : a;
+    a = (c4 == best) ? 4u : a;
+    a = (c3 == best) ? 3u : a;
+    a = (c2 == best) ? 2u : a;
+    a = (c1 == best) ? 1u : a;
+    a = (c0 == best) ? 0u : a;
+    act = a;
+    return best;
+#else
     // path_planning_2d_cuda.cu:244-258: first strict minimum, u ascending.
     float best = c0;
     uint32_t a = 0;
@@ -197,6 +225,7 @@ __device__ __forceinline__ float backup(float j0, float j1, float j2, float j3,
     if (c8 < best) { best = c8; a = 8; }
     act = a;
     return best;
+#endif
   } else {
 #if PP2D_MINV == 1
     return fminf(fminf(fminf(c0, c1), fminf(c2, c3)),
@@ -545,17 +574,15 @@ struct Sweeper {
                                  L[lp][j], G4[lp][j], p.gamma, p.ga, p.gb,
                                  act2[j]);
         }
-        if (valid) {
-          store_own<CW>(pout, v2);
-          if constexpr (POLICY) {
+        if (valid) store_own<CW>(pout, v2);
+        if constexpr (POLICY) {
+          // (single predicated stores: no divergent region inside the marching loop)
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-              if (x0 + j < p.W) {
-                const uint32_t cj = (j & 1) ? (cprev[j >> 1] >> 16) : cprev[j >> 1];
-                // Occupied cells tie on every action in the reference -> 0.
-                pact[j] = (cj & kCodeOccBit) ? 0 : (uint8_t)act2[j];
-              }
-            }
+          for (int j = 0; j < CW; ++j) {
+            const uint32_t occ_bit = (j & 1) ? (kCodeOccBit << 16) : kCodeOccBit;
+            // Occupied cells tie on every action in the reference -> 0.
+            const uint32_t a = (cprev[j >> 1] & occ_bit) ? 0u : act2[j];
+            if (valid && x0 + j < p.W) pact[j] = (uint8_t)a;
           }
         }
         if constexpr (PEER) {
@@ -909,39 +936,94 @@ struct CodeParams {
   int gx, gy;
 };
 
-__device__ __forceinline__ uint32_t occ_at(const CodeParams& p, int gx, int gy) {
-  if (gx < 0 || gx >= p.W || gy < 0 || gy >= p.Htot) return 1u;
-  int r = gy - p.occ_row0;
-  if (r < 0 || r >= p.occ_rows) return 1u;   // never needed for owned rows
-  return p.occ[(size_t)r * p.W + gx] == 1 ? 1u : 0u;
+// Occupancy of the 6 columns x0-1 .. x0+4 of global row gy as a bit mask (bit i
+// = column x0-1+i; out of map = occupied, a cell is occupied iff its byte is
+// exactly 1).  FAST: x0 is 4-aligned, inside the map with 3 columns to spare
+// and W % 4 == 0, so the 4 own bytes are one aligned 32-bit load.
+template <bool FAST>
+__device__ __forceinline__ uint32_t occ_mask6(const CodeParams& p, int x0, int gy) {
+  const int r = gy - p.occ_row0;
+  if (gy < 0 || gy >= p.Htot || r < 0 || r >= p.occ_rows) return 0x3Fu;
+  const uint8_t* __restrict__ q = p.occ + (size_t)r * p.W;
+  uint32_t m = 0;
+  if (FAST) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(q + x0));
+    m |= ((w & 0xFFu) == 1u) << 1;
+    m |= (((w >> 8) & 0xFFu) == 1u) << 2;
+    m |= (((w >> 16) & 0xFFu) == 1u) << 3;
+    m |= ((w >> 24) == 1u) << 4;
+    m |= (x0 > 0 ? (uint32_t)(__ldg(q + x0 - 1) == 1) : 1u);
+    m |= (x0 + 4 < p.W ? (uint32_t)(__ldg(q + x0 + 4) == 1) : 1u) << 5;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int gx = x0 - 1 + i;
+      m |= ((gx < 0 || gx >= p.W) ? 1u : (uint32_t)(__ldg(q + gx) == 1)) << i;
+    }
+  }
+  return m;
 }
 
-__global__ void mdp_code_kernel(const CodeParams p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y;
-  if (c >= p.pitch || r >= p.rows_phys) return;
-  const int x = c - kPadLeft;
-  const int gy = p.row_begin + r - kPadRows;
-  uint32_t code = kCodeOccBit;   // padding
-  if (x >= 0 && x < p.W && gy >= 0 && gy < p.Htot) {
-    // slots: 0 1 2 / 3 4 5 / 6 7 8 ; ring: s0 s1 s2 s5 s8 s7 s6 s3 s0 s1
-    const uint32_t s0 = occ_at(p, x - 1, gy - 1), s1 = occ_at(p, x, gy - 1),
-                   s2 = occ_at(p, x + 1, gy - 1), s3 = occ_at(p, x - 1, gy),
-                   s4 = occ_at(p, x, gy), s5 = occ_at(p, x + 1, gy),
-                   s6 = occ_at(p, x - 1, gy + 1), s7 = occ_at(p, x, gy + 1),
-                   s8 = occ_at(p, x + 1, gy + 1);
-    code = s0 | (s1 << 1) | (s2 << 2) | (s5 << 3) | (s8 << 4) | (s7 << 5) |
-           (s6 << 6) | (s3 << 7) | (s0 << 8) | (s1 << 9);
-    if (s4) code |= kCodeOccBit;
-    else if (!(x == p.gx && gy == p.gy)) code |= kCodeLiveBit;
+// One thread builds the codes of 4 consecutive cells and marches kCodeRows rows
+// down with the three 6-column occupancy masks of rows y-1, y, y+1 in
+// registers: 3 loads (1 word + 2 bytes) and one 8-byte store per 4 cells
+// instead of 9 byte loads and a 2-byte store per cell.
+constexpr int kCodeRows = 16;
+constexpr int kCodeThreads = 128;
+
+template <bool FAST>
+__device__ __forceinline__ void code_march(const CodeParams& p, int c0, int r0) {
+  const int x0 = c0 - kPadLeft;
+  const int r1 = min(r0 + kCodeRows, p.rows_phys);
+  int gy = p.row_begin + r0 - kPadRows;
+  uint32_t m0 = occ_mask6<FAST>(p, x0, gy - 1), m1 = occ_mask6<FAST>(p, x0, gy);
+  for (int r = r0; r < r1; ++r, ++gy) {
+    const uint32_t m2 = occ_mask6<FAST>(p, x0, gy + 1);
+    uint32_t code[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + j;
+      uint32_t cd = kCodeOccBit;   // padding
+      if (x >= 0 && x < p.W && gy >= 0 && gy < p.Htot) {
+        // slots: 0 1 2 / 3 4 5 / 6 7 8 ; ring: s0 s1 s2 s5 s8 s7 s6 s3 s0 s1
+        const uint32_t t = m0 >> j, c = m1 >> j, b = m2 >> j;
+        const uint32_t s0 = t & 1u, s1 = (t >> 1) & 1u, s2 = (t >> 2) & 1u, s3 = c & 1u,
+                       s4 = (c >> 1) & 1u, s5 = (c >> 2) & 1u, s6 = b & 1u,
+                       s7 = (b >> 1) & 1u, s8 = (b >> 2) & 1u;
+        cd = s0 | (s1 << 1) | (s2 << 2) | (s5 << 3) | (s8 << 4) | (s7 << 5) |
+             (s6 << 6) | (s3 << 7) | (s0 << 8) | (s1 << 9);
+        if (s4) cd |= kCodeOccBit;
+        else if (!(x == p.gx && gy == p.gy)) cd |= kCodeLiveBit;
+      }
+      code[j] = cd;
+    }
+    // pitch is a multiple of 32 and c0 of 4: the 4 codes are 8-byte aligned
+    *reinterpret_cast<uint2*>(p.code + (size_t)r * p.pitch + c0) =
+        make_uint2(code[0] | (code[1] << 16), code[2] | (code[3] << 16));
+    m0 = m1;
+    m1 = m2;
   }
-  p.code[(size_t)r * p.pitch + c] = (uint16_t)code;
+}
+
+// grid: (ceil(pitch / 4 / kCodeThreads), ceil(rows_phys / kCodeRows))
+__global__ void __launch_bounds__(kCodeThreads) mdp_code_kernel(const CodeParams p) {
+  const int c0 = 4 * (blockIdx.x * kCodeThreads + threadIdx.x);
+  const int r0 = blockIdx.y * kCodeRows;
+  if (c0 >= p.pitch || r0 >= p.rows_phys) return;
+  const int x0 = c0 - kPadLeft;
+  const bool fast = (p.W & 3) == 0 && (x0 & 3) == 0 && x0 >= 0 && x0 + 3 < p.W &&
+                    (reinterpret_cast<uintptr_t>(p.occ) & 3u) == 0;
+  if (fast) code_march<true>(p, c0, r0);
+  else code_march<false>(p, c0, r0);
 }
 
 // ---------------------------------------------------------------------------
 // max |J - Jchk| over the owned rows, then Jchk = J
 // (path_planning_2d.cu:243-251).  result: float bits, atomicMax on uint is
 // order preserving for non-negative floats.
+// CHK_ZERO: first check after a reset -- Jchk is J_0 = 0 by definition and is
+// not read (the reset then does not have to zero it).
+template <bool CHK_ZERO>
 __global__ void __launch_bounds__(256)
 mdp_residual_kernel(const float4* __restrict__ j, float4* __restrict__ chk,
                     size_t n4, uint32_t floor_bits, uint32_t* result,
@@ -952,7 +1034,8 @@ mdp_residual_kernel(const float4* __restrict__ j, float4* __restrict__ chk,
   if (p2p_error != nullptr && *p2p_error != 0u) m = __uint_as_float(0x7f800000u);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
-    float4 a = j[i], b = chk[i];
+    const float4 a = j[i];
+    const float4 b = CHK_ZERO ? make_float4(0.f, 0.f, 0.f, 0.f) : chk[i];
     m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x - b.x), fabsf(a.y - b.y)),
                        fmaxf(fabsf(a.z - b.z), fabsf(a.w - b.w))));
     chk[i] = a;
@@ -1082,15 +1165,28 @@ mdp_policy_kernel(const PolicyParams p) {
 }
 
 // Dense J for download: occupied cells get the closed-form trapped cost.
+// VEC: 4 cells per thread (W % 4 == 0 and 4-aligned pad columns: 16-byte loads
+// and stores); otherwise one cell per thread.
+template <bool VEC>
 __global__ void mdp_export_kernel(const float* __restrict__ j,
                                   const uint16_t* __restrict__ code,
                                   float* __restrict__ out, int W, int H,
                                   int pitch, float occupied_cost) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * (VEC ? 4 : 1);
   const int y = blockIdx.y;
   if (x >= W || y >= H) return;
   const size_t q = (size_t)(y + kPadRows) * pitch + x + kPadLeft;
-  out[(size_t)y * W + x] = (code[q] & kCodeOccBit) ? occupied_cost : j[q];
+  if (VEC) {
+    float4 v = *reinterpret_cast<const float4*>(j + q);
+    const uint2 c = *reinterpret_cast<const uint2*>(code + q);
+    if (c.x & kCodeOccBit) v.x = occupied_cost;
+    if (c.x & (kCodeOccBit << 16)) v.y = occupied_cost;
+    if (c.y & kCodeOccBit) v.z = occupied_cost;
+    if (c.y & (kCodeOccBit << 16)) v.w = occupied_cost;
+    *reinterpret_cast<float4*>(out + (size_t)y * W + x) = v;
+  } else {
+    out[(size_t)y * W + x] = (code[q] & kCodeOccBit) ? occupied_cost : j[q];
+  }
 }
 
 // MdpPathPlanning2d::beliefCallback (path_planning_2d.cu:168-189): index of
