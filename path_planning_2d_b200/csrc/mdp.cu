@@ -169,6 +169,7 @@ struct pp2d_mdp {
   unsigned int p2p_iter = 0, p2p_expect_top = 0, p2p_expect_bot = 0;
   int p2p_debug = 0, p2p_edge_rows = 16;
   int p2p_edge_short = 20;         // rows the boundary row blocks are shorter (hand-shake cost)
+  bool p2p_publisher = true;       // a warp without rows publishes the flags (PP2D_P2P_PUBLISHER)
   unsigned int p2p_spin_limit = 1u << 24;   // polls (32-256 ns apart) before kFlagError
   // ghost-row contract of a shard without peer-to-peer rows: sweeps that may
   // still run before the caller has to refresh the ghost rows (pp2d_mdp_halo)
@@ -333,13 +334,15 @@ static int launch_sweep(pp2d_mdp* h) {
         lo_out.push_back(p.n_strips * rows);
         return (long long)lo_out.size() - 1;
       };
+      // (one slot stays free for the warp that publishes the flags)
+      const long long avail = slots - (h->p2p_publisher ? 1 : 0);
       double lo_t = (double)total / (double)slots, hi_t = 4.0 * lo_t + 4.0 * (c_edge + c_seg) + 16.0;
       for (int it = 0; it < 24; ++it) {
         const double mid = 0.5 * (lo_t + hi_t);
-        if (build(mid) <= slots) hi_t = mid; else lo_t = mid;
+        if (build(mid) <= avail) hi_t = mid; else lo_t = mid;
       }
       const long long nu = build(hi_t);
-      if (nu <= slots) {
+      if (nu <= avail) {
         if (lc.d_unit_lo) cudaFree(lc.d_unit_lo);
         lc.d_unit_lo = nullptr;
         PP2D_CUDA(cudaMalloc(&lc.d_unit_lo, lo_out.size() * sizeof(int)));
@@ -445,6 +448,11 @@ static int launch_sweep(pp2d_mdp* h) {
     p.edge_rows = h->p2p_edge_rows;
     p.spin_limit = h->p2p_spin_limit;
   }
+  // P2P: a warp slot of the launch that has no rows publishes the flags (the
+  // marching warps then never execute a system fence); without a free slot in
+  // the last CTA the last boundary unit does it, as before.
+  p.publisher_unit = -1;
+  if (P2P && h->p2p_publisher && p.n_units % kWarpsPerCta != 0) p.publisher_unit = p.n_units;
   lc.valid = true;
   lc.y_rows = rows;
   lc.lin_len = p.lin_len;
@@ -618,6 +626,7 @@ static int create_impl(uint32_t height, uint32_t width, const uint8_t* map,
   }
   if (h->p2p_edge_rows < kPadRows) h->p2p_edge_rows = kPadRows;
   h->p2p_edge_short = env_int("PP2D_P2P_EDGE_SHORT", 20);
+  h->p2p_publisher = env_int("PP2D_P2P_PUBLISHER", 1) != 0;
   if (h->waves < 1) h->waves = 1;
   if (h->prefetch_rows < kPrefetch) h->prefetch_rows = kPrefetch;
   if (h->prefetch_rows > kSlackRows) h->prefetch_rows = kSlackRows;

@@ -144,6 +144,10 @@ struct SweepParams {
   // row block of a strip get rows_edge < rows_per_unit rows, the blocks between
   // them rows_inner; rows_edge == 0: all blocks have rows_per_unit rows.
   int rows_edge, rows_inner;
+  // P2P: index of the warp that publishes this launch's flags to the
+  // neighbours (see publish_flags), -1: the last boundary unit to finish its
+  // edge rows does it itself.
+  int publisher_unit;
 };
 
 // Flag block of a shard (uint32 each, cudaMalloc'ed, IPC-shared).
@@ -157,6 +161,11 @@ constexpr int kFlagWords = 8;
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -832,8 +841,24 @@ struct Sweeper {
         // counts; the count comes back through a shuffle so that the decision
         // is warp-uniform.)
         if (!(p.p2p_debug & 4u)) {
-          __threadfence_system();        // every lane: its peer stores before the count
-          __syncwarp();                  // ... and all of them before lane 0 counts
+          // Release of this unit's peer stores into the local count.  A system
+          // fence waits for the flush of EVERY egress port of the GPU, PCIe
+          // included: while a download is on its way to the host it takes tens
+          // of microseconds, and a marching warp that executes it becomes the
+          // tail of the launch (measured: +17 us per launch at 2 GPUs).  So the
+          // marching warps only order their stores at GPU scope (barrier, then
+          // fence, then lane 0's atomic: the release pattern of the PTX memory
+          // model, cumulative over the whole warp's stores); the one system
+          // fence per side and launch is executed by whoever publishes the
+          // flag -- a warp without rows (publish_flags) when there is one.
+          const bool gpu_scope = p.publisher_unit >= 0 || (p.p2p_debug & 8u);
+          if (gpu_scope) {
+            __syncwarp();
+            __threadfence();
+          } else {
+            __threadfence_system();        // every lane: its peer stores before the count
+            __syncwarp();                  // ... and all of them before lane 0 counts
+          }
 #pragma unroll
           for (int side = 0; side < 2; ++side) {
             if (!(side == 0 ? top : bot)) continue;
@@ -841,8 +866,8 @@ struct Sweeper {
             if (lane == 0)
               c = atomicAdd(p.flags + (side == 0 ? kFlagCountTop : kFlagCountBot), 1u) + 1u;
             c = __shfl_sync(0xffffffffu, c, 0);
-            if (c == (side == 0 ? p.expect_top : p.expect_bot)) {
-              __threadfence_system();
+            if (p.publisher_unit < 0 && c == (side == 0 ? p.expect_top : p.expect_bot)) {
+              __threadfence_system();      // (acquires the other units' counts, too)
               if (lane == 0)
                 st_release_sys(side == 0 ? p.up_flag_remote : p.down_flag_remote, p.iter);
             }
@@ -853,6 +878,40 @@ struct Sweeper {
     if (r1 > r0) march<false>(r0, r1, col);
   }
 };
+
+// The publisher warp of a P2P launch (SweepParams::publisher_unit): waits until
+// every boundary unit of a side has counted itself in (their peer stores happen
+// before their count, the fence after the last poll acquires it), executes the system fence
+// and writes this launch's number into the neighbour's flag.  The counts are
+// cumulative over launches.  Lane 0 serves the upper, lane 1 the lower side.
+__device__ __forceinline__ void publish_flags(const SweepParams& p, int lane) {
+  if (p.p2p_debug & 4u) return;
+  if (lane < 2) {
+    unsigned int* remote = lane == 0 ? p.up_flag_remote : p.down_flag_remote;
+    const bool feeds = (lane == 0 ? p.peer_up_out : p.peer_down_out) != nullptr;
+    if (feeds && remote != nullptr) {
+      const unsigned int* cnt = p.flags + (lane == 0 ? kFlagCountTop : kFlagCountBot);
+      const unsigned int expect = lane == 0 ? p.expect_top : p.expect_bot;
+      unsigned int spins = 0;
+      bool ok = true;
+      // (relaxed polls: an acquire load invalidates the L1 of the SM on every
+      // poll, which the marching warps of this SM pay for -- 68.0 against 65.8
+      // us per launch; the fence below is the acquire)
+      while ((int)(ld_relaxed_gpu(cnt) - expect) < 0) {
+        if (++spins > p.spin_limit) {       // a unit never finished: do not publish
+          atomicExch(p.flags + kFlagError, 1u);
+          ok = false;
+          break;
+        }
+        __nanosleep(200u);
+      }
+      if (ok) {
+        __threadfence_system();             // acquire of the counts + release of the flag
+        st_release_sys(remote, p.iter);
+      }
+    }
+  }
+}
 
 // Dynamic shared memory of a launch (PP2D_LUT6 builds; the 8 KB table keeps
 // its static buffer so that the default build's code is untouched).
@@ -910,6 +969,12 @@ mdp_sweep_kernel(const SweepParams p) {
   const int warp = (int)(threadIdx.x >> 5);
 #endif
   const int unit = blockIdx.x * (blockDim.x >> 5) + warp;
+  if constexpr (P2P) {
+    if (unit == p.publisher_unit) {
+      publish_flags(p, lane);
+      return;
+    }
+  }
   if (unit >= p.n_units) return;
   // Produced by a volatile asm after the barrier: the table loads (plain asm,
   // free to be scheduled) depend on it and so cannot move above the barrier.
