@@ -17,6 +17,18 @@ class OracleShard:
         self._halo = None
         self._poison()
 
+    def reset(self, grid, goal):
+        # (new map and goal on the same shard, as GpuShard.reset)
+        self.ora = oracle_py.OracleMdp(grid, goal, self.ora.gamma)
+        self.prev = np.zeros((self.h, self.w), np.float32)
+        self._halo = None
+        self.staged = getattr(self, "staged", None)
+        self._poison()
+
+    def stage_map(self, grid):
+        # (the GPU shard starts an upload here; the stand-in only records the call)
+        self.staged = grid
+
     def _poison(self):
         J = self.ora.J[self.ora.cur].reshape(self.h, self.w)
         lo, hi = max(0, self.begin - 2), min(self.h, self.end + 2)

@@ -72,10 +72,22 @@ def _worker(rank, world, port, name, out_dir):
         assert vi.converged
         checksum = vi.checksum()
         cost, action = vi.gather()
+        # a second problem on the same shards: the next map is staged while the
+        # first solution is still there, then reset() starts over from J = 0
+        grid2 = np.ascontiguousarray(grid[::-1])
+        goal2 = (goal[0], grid.shape[0] - 1 - goal[1])
+        vi.stage_map(grid2)
+        assert vi.shard.staged is grid2
+        vi.reset(grid2, goal2)
+        assert vi.n_sweeps == 0
+        vi.sweeps(9)
+        res2 = vi.residual()
+        cost2, action2 = vi.gather()
         if rank == 0:
             np.savez(os.path.join(out_dir, "out.npz"), cost=cost, action=action,
                      sweeps=sweeps, residuals=np.array(residuals),
-                     checksum=np.uint64(checksum))
+                     checksum=np.uint64(checksum), cost2=cost2, action2=action2,
+                     res2=np.float32(res2))
     finally:
         dist.destroy_process_group()
 
@@ -106,3 +118,10 @@ def test_sharded_value_iteration_gloo(tmp_path, world):
     assert np.array_equal(got["action"], ora.act)
     assert not np.isnan(got["cost"]).any()
     assert int(got["checksum"]) == grid_checksum(ora.cost, ora.act)
+    # the staged / reset second problem (the map upside down)
+    grid2 = np.ascontiguousarray(grid[::-1])
+    ora2 = oracle_py.OracleMdp(grid2, (goal[0], grid.shape[0] - 1 - goal[1]), cases.GAMMA)
+    ora2.sweeps(9)
+    assert np.array_equal(got["cost2"].view(np.uint32), ora2.cost.view(np.uint32))
+    assert np.array_equal(got["action2"], ora2.act)
+    assert float(got["res2"]) == float(np.float32(np.abs(ora2.cost).max()))
