@@ -52,6 +52,11 @@ def test_argument_validation_needs_no_gpu():
     rc = lib.pp2d_mdp_create_shard(4, 4, grid.ctypes.data, 0, 0, 0.95, 3, 2,
                                    ctypes.byref(h))
     assert rc == _lib.PP2D_ERR_INVALID
+    # NULL handles / buffers are refused before any CUDA call
+    assert lib.pp2d_mdp_stage_map(None, grid.ctypes.data) == _lib.PP2D_ERR_INVALID
+    assert lib.pp2d_mdp_reset(None, grid.ctypes.data, 0, 0) == _lib.PP2D_ERR_INVALID
+    assert lib.pp2d_mdp_download_begin(None, None, None) == _lib.PP2D_ERR_INVALID
+    assert lib.pp2d_mdp_download_wait(None) == _lib.PP2D_ERR_INVALID
 
 
 def test_no_cpu_fallback():
